@@ -1,0 +1,70 @@
+"""ctypes binding of libdcl_b200.so (the C ABI declared in include/dcl_b200.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100 every call
+raises.  Build the library with `python -m doubly_contrastive_semseg_b200.build`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcl_b200.so")
+
+_c = ctypes
+_vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dcl_b200.h one to one
+SIGNATURES = {
+    "dcl_version": (_i, []),
+    "dcl_last_error": (_c.c_char_p, []),
+    "dcl_check_device": (_i, []),
+    "dcl_sample_classify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "dcl_gather_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "dcl_pack_rows": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "dcl_contrast_workspace_bytes": (_sz, [_i, _i]),
+    "dcl_contrast_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "dcl_contrast_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    "dcl_scatter_grad": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "dcl_unpack_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "dcl_gap_fwd": (_i, [_vp, _i, _i, _vp, _vp]),
+    "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+class DclError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DclError(
+            "libdcl_b200.so not found at %s - build it with "
+            "`python -m doubly_contrastive_semseg_b200.build`; there is no CPU or PyTorch fallback"
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise DclError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.dcl_last_error().decode("utf-8", "replace")
+        raise DclError("%s failed with status %d: %s" % (name, rc, msg))
+    return rc
+
+
+def workspace_bytes(nI, nJ):
+    return int(load().dcl_contrast_workspace_bytes(nI, nJ))

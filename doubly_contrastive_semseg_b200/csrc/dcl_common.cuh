@@ -1,0 +1,30 @@
+// Host-side plumbing shared by the translation units of libdcl_b200.so.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/dcl_b200.h"
+
+namespace dcl {
+
+char* last_error_buf();                       // thread-local, 512 bytes
+int fail(int code, const char* fmt, ...);     // records message, returns code
+int sm_count();                               // SMs of the current device (148 on B200), cached
+
+#define DCL_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return ::dcl::fail(static_cast<int>(e_), "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define DCL_LAUNCH_CHECK(name)                                                             \
+    do {                                                                                   \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess)                                                             \
+            return ::dcl::fail(static_cast<int>(e_), "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace dcl

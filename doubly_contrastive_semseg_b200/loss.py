@@ -1,0 +1,422 @@
+"""Drop-in loss modules: same names, constructor arguments, attributes, forward signatures and
+error behaviour as the reference's `utils/loss.py` (`PixelContrastLoss` :250-415, `SupConLoss`
+:84-205), with all device work done by libdcl_b200.so (hand-written sm_100a CUDA, C ABI in
+include/dcl_b200.h).  PyTorch is used for memory, streams, autograd plumbing and (for the
+image-level term only) the two tiny projection GEMMs.  No CPU path exists here.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+MODE_PIXEL, MODE_SUPCON = 0, 1
+_DIM, _TILE = 128, 128
+_CHUNK, _BINS = 2048, 512
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.DclError("%s must be a CUDA tensor: this library has no CPU path" % name)
+
+
+# ----------------------------------------------------------------------------------------------
+# host-side sampling plan (the part of loss.py:264-337 that is Python control flow + CPU RNG)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class AnchorPlan:
+    A: int                 # anchors = (image, class) pairs == reference `total_classes`
+    n_view: int
+    image: np.ndarray      # [A] global image index, reference order (image asc, class asc)
+    cls: np.ndarray        # [A]
+    num_hard: np.ndarray   # [A]
+    num_easy: np.ndarray   # [A]
+    keep_hard: np.ndarray  # [A]
+    ranks: np.ndarray      # [A, n_view] rank inside the hard (v < keep_hard) or easy list
+
+
+def _split_rule(num_hard: int, num_easy: int, n_view: int):
+    """(keep_hard, keep_easy), reference loss.py:314-325 (true division on n_view)."""
+    if num_hard >= n_view / 2 and num_easy >= n_view / 2:
+        kh = n_view // 2
+        return kh, n_view - kh
+    if num_hard >= n_view / 2:
+        return n_view - num_easy, num_easy
+    if num_easy >= n_view / 2:
+        return num_hard, n_view - num_hard
+    print("this shoud be never touched! {} {} {}".format(num_hard, num_easy, n_view))
+    raise Exception
+
+
+def _torch_randperm_prefix(n: int, k: int) -> np.ndarray:
+    # consumes the global CPU generator exactly like loss.py:327,329
+    return torch.randperm(n)[:k].numpy()
+
+
+def plan_anchors(counts: np.ndarray, ignore_label: int, max_samples: int, max_views: int,
+                 randperm: Callable[[int, int], np.ndarray] = _torch_randperm_prefix
+                 ) -> Optional[AnchorPlan]:
+    """counts [B,256,2] = pixels per (image, label, hard|easy).  Returns None when no class
+    qualifies (reference: `return None, None`, loss.py:287-288)."""
+    tot = counts.sum(axis=2)
+    keep = tot > max_views                                    # loss.py:282
+    if 0 <= ignore_label <= 255:
+        keep[:, ignore_label] = False                         # loss.py:281
+    img, cls = np.nonzero(keep)                               # image asc, class asc
+    A = int(img.shape[0])
+    if A == 0:
+        return None
+    n_view = min(max_samples // A, max_views)                 # loss.py:290-291
+    nh = counts[img, cls, 0].astype(np.int64)
+    ne = counts[img, cls, 1].astype(np.int64)
+    kh = np.zeros(A, dtype=np.int64)
+    ranks = np.zeros((A, n_view), dtype=np.int64)
+    for a in range(A):
+        k_h, k_e = _split_rule(int(nh[a]), int(ne[a]), n_view)
+        kh[a] = k_h
+        ranks[a, :k_h] = randperm(int(nh[a]), k_h)            # hard first, loss.py:327-328
+        ranks[a, k_h:] = randperm(int(ne[a]), k_e)            # then easy, loss.py:329-330
+    return AnchorPlan(A, n_view, img.astype(np.int64), cls.astype(np.int64), nh, ne, kh, ranks)
+
+
+@dataclass
+class RowLayout:
+    """Device row order: anchors stably sorted by class (positives become block-diagonal), views
+    contiguous per anchor, padded to a multiple of 128 rows."""
+    n: int
+    n_pad: int
+    req: np.ndarray        # [n_pad, 4] int32 (local image, label, easy, rank); image -1 = padding
+    y: np.ndarray          # [n_pad] int32, -1 = padding
+    ref_row: np.ndarray    # [n_pad] row index v*A + a in the reference's ordering, -1 = padding
+    anchor: np.ndarray     # [n_pad] anchor id a (reference order), -1 = padding
+
+
+def layout_rows(plan: AnchorPlan, anchors: np.ndarray, image_offset: int, n_pad: Optional[int] = None
+                ) -> RowLayout:
+    """Rows of the anchors listed in `anchors` (indices into the plan), class-sorted."""
+    V = plan.n_view
+    order = anchors[np.argsort(plan.cls[anchors], kind="stable")]
+    n = int(order.shape[0]) * V
+    if n_pad is None:
+        n_pad = max(_TILE, (n + _TILE - 1) // _TILE * _TILE)
+    req = np.full((n_pad, 4), -1, dtype=np.int32)
+    y = np.full(n_pad, -1, dtype=np.int32)
+    ref_row = np.full(n_pad, -1, dtype=np.int64)
+    anchor = np.full(n_pad, -1, dtype=np.int64)
+    if n:
+        a_rep = np.repeat(order, V)
+        v_rep = np.tile(np.arange(V), order.shape[0])
+        req[:n, 0] = plan.image[a_rep] - image_offset
+        req[:n, 1] = plan.cls[a_rep]
+        req[:n, 2] = (v_rep >= plan.keep_hard[a_rep]).astype(np.int32)
+        req[:n, 3] = plan.ranks[a_rep, v_rep]
+        y[:n] = plan.cls[a_rep]
+        ref_row[:n] = v_rep * plan.A + a_rep
+        anchor[:n] = a_rep
+    return RowLayout(n, n_pad, req, y, ref_row, anchor)
+
+
+# ----------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI
+# ----------------------------------------------------------------------------------------------
+def classify(labels: torch.Tensor, predict: torch.Tensor, h: int, w: int):
+    """-> code [B,hw] u16 (as int16 storage), chunk_prefix [B,n_chunks,512] i32, counts [B,512] i32"""
+    B, H, W = labels.shape
+    C = predict.shape[1]
+    hw = h * w
+    n_chunks = (hw + _CHUNK - 1) // _CHUNK
+    dev = labels.device
+    code = torch.empty((B, hw), dtype=torch.int16, device=dev)
+    chunk = torch.empty((B, n_chunks, _BINS), dtype=torch.int32, device=dev)
+    counts = torch.empty((B, _BINS), dtype=torch.int32, device=dev)
+    _lib.call("dcl_sample_classify", _p(labels), _p(predict), B, H, W, h, w, C, _p(code), _p(chunk),
+              _p(counts), _stream())
+    return code, chunk, counts
+
+
+def select_pixels(code, chunk, B, hw, req_dev, n_rows):
+    pix = torch.empty(n_rows, dtype=torch.int32, device=code.device)
+    _lib.call("dcl_sample_select", _p(code), _p(chunk), B, hw, _p(req_dev), n_rows, _p(pix), _stream())
+    return pix
+
+
+def gather_tiles(feats, pix, n_pad):
+    B, C, h, w = feats.shape
+    tiles = torch.empty(n_pad * _DIM * 2, dtype=torch.uint8, device=feats.device)
+    sqnorm = torch.empty(n_pad, dtype=torch.float32, device=feats.device)
+    _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tiles), _p(sqnorm), _stream())
+    return tiles, sqnorm
+
+
+def pack_rows(Z, n_pad):
+    n = Z.shape[0]
+    tiles = torch.empty(n_pad * _DIM * 2, dtype=torch.uint8, device=Z.device)
+    sqnorm = torch.empty(n_pad, dtype=torch.float32, device=Z.device)
+    _lib.call("dcl_pack_rows", _p(Z), n, n_pad, _p(tiles), _p(sqnorm), _stream())
+    return tiles, sqnorm
+
+
+def contrast_forward(tiles, y, sqnorm, nJ, rb0, nI, n_valid, mode, T, Tb, colA=None, colB=None):
+    """Forward sweeps for local row blocks [rb0, rb0+nI).  Returns (colA, colB, rowloss, loss_sum)."""
+    dev = tiles.device
+    if colA is None:
+        colA = torch.empty((nJ * _TILE, 4), dtype=torch.float32, device=dev)
+        colB = torch.empty((nJ * _TILE, 4), dtype=torch.float32, device=dev)
+    rowloss = torch.empty(nJ * _TILE, dtype=torch.float32, device=dev)
+    loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+    nbytes = _lib.workspace_bytes(nI, nJ)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.call("dcl_contrast_fwd", _p(tiles), _p(y), _p(sqnorm), nJ, rb0, nI, n_valid, mode, float(T),
+              float(Tb), _p(ws), nbytes, _p(colA), _p(colB), _p(rowloss), _p(loss_sum), _stream())
+    return colA, colB, rowloss, loss_sum
+
+
+def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
+    dev = tiles.device
+    dF = torch.empty((nI * _TILE, _DIM), dtype=torch.float32, device=dev)
+    nbytes = _lib.workspace_bytes(nI, nJ)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.call("dcl_contrast_bwd", _p(tiles), _p(y), _p(colA), _p(colB), nJ, rb0, nI, mode, _p(ws), nbytes,
+              _p(dF), _stream())
+    return dF
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd glue
+# ----------------------------------------------------------------------------------------------
+class _PixelContrastFn(torch.autograd.Function):
+    """loss(feats) for a fixed set of sampled anchor pixels; gradient only w.r.t. feats."""
+
+    @staticmethod
+    def forward(ctx, feats, pix, y_dev, n_valid, T, Tb):
+        B, C, h, w = feats.shape
+        n_pad = pix.shape[0]
+        tiles, sqnorm = gather_tiles(feats, pix, n_pad)
+        nJ = n_pad // _TILE
+        colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_dev, sqnorm, nJ, 0, nJ, n_valid,
+                                                         MODE_PIXEL, T, Tb)
+        ctx.save_for_backward(tiles, y_dev, colA, colB, pix)
+        ctx.meta = dict(nJ=nJ, rb0=0, nI=nJ, n_local_pad=n_pad, shape=(B, C, h, w))
+        return (loss_sum / n_valid).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tiles, y, colA, colB, pix = ctx.saved_tensors
+        m = ctx.meta
+        dF = contrast_backward(tiles, y, colA, colB, m["nJ"], m["rb0"], m["nI"], MODE_PIXEL)
+        B, C, h, w = m["shape"]
+        dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
+        g = grad_out.to(torch.float32).contiguous()
+        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
+                  _stream())
+        return dfeats, None, None, None, None, None
+
+
+class _ContrastRowsFn(torch.autograd.Function):
+    """Row-normalised contrast of a dense [n,128] matrix (image-level term)."""
+
+    @staticmethod
+    def forward(ctx, Z, y, mode, T, Tb):
+        n = Z.shape[0]
+        n_pad = (n + _TILE - 1) // _TILE * _TILE
+        Zc = Z.contiguous().to(torch.float32)
+        tiles, sqnorm = pack_rows(Zc, n_pad)
+        y_pad = torch.full((n_pad,), -1, dtype=torch.int32, device=Z.device)
+        y_pad[:n] = y.to(torch.int32)
+        nJ = n_pad // _TILE
+        colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_pad, sqnorm, nJ, 0, nJ, n, mode, T, Tb)
+        ctx.save_for_backward(tiles, y_pad, colA, colB)
+        ctx.meta = (n, nJ, mode)
+        return (loss_sum / n).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tiles, y_pad, colA, colB = ctx.saved_tensors
+        n, nJ, mode = ctx.meta
+        dF = contrast_backward(tiles, y_pad, colA, colB, nJ, 0, nJ, mode)
+        dZ = torch.empty((n, _DIM), dtype=torch.float32, device=tiles.device)
+        g = grad_out.to(torch.float32).contiguous()
+        _lib.call("dcl_unpack_rows", _p(dF), n, _p(g), _p(dZ), _stream())
+        return dZ, None, None, None, None
+
+
+class _GapFn(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d((1,1)) + flatten, loss.py:115-116."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B2, C, h, w = x.shape
+        xc = x.contiguous()
+        pooled = torch.empty((B2, C), dtype=torch.float32, device=x.device)
+        _lib.call("dcl_gap_fwd", _p(xc), B2 * C, h * w, _p(pooled), _stream())
+        ctx.shape = (B2, C, h, w)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        B2, C, h, w = ctx.shape
+        dx = torch.empty((B2, C, h, w), dtype=torch.float32, device=g.device)
+        gc = g.contiguous().to(torch.float32)
+        _lib.call("dcl_gap_bwd", _p(gc), B2 * C, h * w, _p(dx), 0, _stream())
+        return dx
+
+
+def contrast_rows(Z, y, mode=MODE_PIXEL, temperature=0.07, base_temperature=0.07):
+    """Differentiable N x N contrast of rows Z [n,128] with integer labels y [n] (the reference's
+    `_contrastive`, loss.py:339-389, on an already gathered anchor matrix)."""
+    _require_cuda(Z, "Z")
+    if Z.dim() != 2 or Z.shape[1] != _DIM:
+        raise ValueError("Z must be [n, 128]")
+    return _ContrastRowsFn.apply(Z, y, mode, temperature, base_temperature)
+
+
+# ----------------------------------------------------------------------------------------------
+# the two modules
+# ----------------------------------------------------------------------------------------------
+class PixelContrastLoss(nn.Module):
+    """Pixel-level supervised contrastive term.  Reference: utils/loss.py:250-415.
+
+    Same constructor (`device=None`) and the same mutable attributes (loss.py:255-262); call as
+    `crit(feats, labels=labels, predict=predict)` like trainer.py:135-136.  The sampled pixel
+    indices are bit-exact with the reference for the same state of torch's global CPU generator.
+    Deviation (documented in DESIGN.md): when no class qualifies the reference crashes
+    (loss.py:287-288 then :341); this returns a zero loss that still back-propagates zeros.
+    """
+
+    def __init__(self, device=None):
+        super().__init__()
+        self.device = device
+        self.temperature = 0.07
+        self.base_temperature = 0.07
+        self.ignore_label = 255
+        self.max_samples = 1024
+        self.max_views = 2
+        self.loss_weight = 1
+        self.contrast_mode = "all"
+        self.last_plan: Optional[AnchorPlan] = None       # exposed for tests / diagnostics
+        self.last_layout: Optional[RowLayout] = None
+        self.last_pix: Optional[torch.Tensor] = None
+
+    # ---- sampling front end ------------------------------------------------------------------
+    def _sample(self, feats, labels, predict):
+        B, C, h, w = feats.shape
+        code, chunk, counts = classify(labels, predict, h, w)
+        counts_host = counts.cpu().numpy().reshape(B, 256, 2)      # the one unavoidable D2H sync
+        plan = plan_anchors(counts_host, int(self.ignore_label), int(self.max_samples),
+                            int(self.max_views))
+        return code, chunk, plan
+
+    def sample(self, feats, labels, predict):
+        """Integer front end: returns (pix [n_pad] i32, y [n_pad] i32, n_valid) on the device, or
+        None when no class qualifies.  Consumes the global CPU RNG like the reference."""
+        B, C, h, w = feats.shape
+        code, chunk, plan = self._sample(feats, labels, predict)
+        self.last_plan = plan
+        if plan is None:
+            return None
+        if plan.n_view <= 0:
+            raise RuntimeError("max_samples // total_classes == 0: no views to sample "
+                               "(the reference fails in torch.cat at loss.py:345)")
+        lay = layout_rows(plan, np.arange(plan.A), 0)
+        self.last_layout = lay
+        host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
+        packed = host.to(feats.device, non_blocking=True)
+        req_dev = packed[: lay.n_pad * 4]
+        y_dev = packed[lay.n_pad * 4:]
+        pix = select_pixels(code, chunk, B, h * w, req_dev, lay.n_pad)
+        self.last_pix = pix
+        return pix, y_dev, lay.n
+
+    def forward(self, feats, labels=None, predict=None):
+        _require_cuda(feats, "feats")
+        if labels is None or predict is None:
+            raise TypeError("PixelContrastLoss needs labels and predict (trainer.py:135-136)")
+        if feats.dim() != 4 or feats.shape[1] != _DIM:
+            raise ValueError("feats must be [B,128,h,w] (SwiftNet decoder width); got %s"
+                             % (tuple(feats.shape),))
+        B, C, h, w = feats.shape
+        assert predict.shape[-1] == feats.shape[-1], "{} {}".format(predict.shape, feats.shape)
+        if labels.dim() != 3 or labels.shape[0] != B or predict.shape[0] != B or \
+                tuple(predict.shape[2:]) != (h, w):
+            raise ValueError("labels must be [B,H,W] and predict [B,C,h,w] matching feats")
+        feats_c = feats.contiguous().to(torch.float32)
+        labels_c = labels.contiguous().to(torch.int64)
+        predict_c = predict.detach().contiguous().to(torch.float32)
+        sampled = self.sample(feats_c, labels_c, predict_c)
+        if sampled is None:
+            return feats_c.sum() * 0.0
+        pix, y_dev, n_valid = sampled
+        return _PixelContrastFn.apply(feats_c, pix, y_dev, n_valid, self.temperature,
+                                      self.base_temperature)
+
+
+class SupConLoss(nn.Module):
+    """Image-level (weather) supervised contrastive / SimCLR term.  Reference: utils/loss.py:84-205.
+
+    Same constructor and sub-modules (`avgpool`, `projection`) so `state_dict()` / `.to()` behave
+    identically; call as `crit(features, class_labels=weather, mask=None)` like trainer.py:117-119.
+    `features` is the two-crop batch [2B,C,h,w] (first B = view 1, next B = view 2).
+    """
+
+    def __init__(self, temperature=0.07, contrast_mode="all", base_temperature=0.07, weight=None,
+                 device=None, opts=None):
+        super().__init__()
+        self.temperature = temperature
+        self.base_temperature = base_temperature
+        self.device = device
+        self.weight = weight
+        self.opts = opts
+        feat_dim = 128
+        dim_in = 2048 if getattr(self.opts, "deeplab", False) else 128        # loss.py:98-101
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))     # kept for state_dict/API parity; pooling runs in dcl_gap_*
+        self.projection = nn.Sequential(nn.Linear(dim_in, dim_in), nn.ReLU(inplace=True),
+                                        nn.Linear(dim_in, feat_dim)).to(self.device)
+        self.contrast_mode = "all"                                           # loss.py:111
+
+    def forward(self, features, class_labels=None, mask=None):
+        _require_cuda(features, "features")
+        if features.dim() != 4:
+            raise ValueError("features must be [2*bsz, C, h, w]")
+        pooled = _GapFn.apply(features.to(torch.float32))                    # loss.py:115-116
+        bsz = pooled.shape[0] // 2
+        z = torch.stack([pooled[:bsz], pooled[bsz:2 * bsz]], dim=1)          # loss.py:117-119
+        z = self.projection(z)                                               # loss.py:120
+        labels = class_labels
+        if len(z.shape) < 3:
+            raise ValueError("`features` needs to be [bsz, n_views, ...],"
+                             "at least 3 dimensions are required")
+        batch_size = z.shape[0]
+        if labels is not None and mask is not None:
+            raise ValueError("Cannot define both `labels` and `mask`")
+        elif labels is None and mask is None:
+            y = torch.arange(batch_size, device=z.device, dtype=torch.int32)     # mask = eye, loss.py:151
+        elif labels is not None:
+            labels = labels.contiguous().view(-1, 1)
+            if labels.shape[0] != batch_size:
+                raise ValueError("Num of labels does not match num of features")
+            y = labels.view(-1).to(device=z.device, dtype=torch.int32)
+            if bool((y < 0).any()):
+                raise ValueError("class_labels must be non-negative integers")
+        else:
+            raise NotImplementedError("an explicit `mask` is not supported by the CUDA path "
+                                      "(trainer.py always passes mask=None)")
+        if self.contrast_mode != "all":
+            raise ValueError("Unknown mode: {}".format(self.contrast_mode))
+        n_views = z.shape[1]
+        Z = torch.cat(torch.unbind(z, dim=1), dim=0)                         # loss.py:161
+        yy = y.repeat(n_views)
+        return _ContrastRowsFn.apply(Z, yy, MODE_SUPCON, self.temperature, self.base_temperature)

@@ -1,0 +1,130 @@
+/* dcl_b200.h - C ABI of the B200-native doubly contrastive loss library (libdcl_b200.so).
+ *
+ * The reference (andyj1/doubly-contrastive-semseg) has no FFI / operator layer: its boundary for
+ * this path is two Python nn.Modules, `PixelContrastLoss` (utils/loss.py:250-415) and `SupConLoss`
+ * (utils/loss.py:84-205), called from trainer.py:116-198.  The functions below are what those two
+ * modules' forward/backward bind through ctypes; each comment names the
+ * reference lines the call replaces.
+ *
+ * Conventions
+ *   - every pointer is a caller-allocated DEVICE buffer unless it says "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *     never synchronises, and returns 0 on success or a negative dcl_status / positive
+ *     cudaError_t; `dcl_last_error()` returns a thread-local message;
+ *   - "anchor rows" are the rows of the N x N contrast matrix; they are stored as "F-tiles":
+ *     128 rows x 128 channels of bf16 = 32 KiB each, in the 128-byte-swizzled image tcgen05.mma
+ *     consumes directly (layout in csrc/dcl_ptx.cuh).  Rows are padded to a multiple of 128 with
+ *     zero features and label -1; padded rows never contribute.
+ *   - D (channels) is fixed at 128 = SwiftNet/ResNet-18 decoder width (`dim_in`, loss.py:98-101).
+ */
+#ifndef DCL_B200_H
+#define DCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCL_DIM 128
+#define DCL_TILE_ROWS 128
+#define DCL_TILE_BYTES 32768
+#define DCL_MODE_PIXEL 0  /* lp_ij = l_ij - log(exp(l_ij) + sum_neg exp(l_ik))   loss.py:376-381 */
+#define DCL_MODE_SUPCON 1 /* lp_ij = l_ij - log(sum_{k!=i} exp(l_ik))            loss.py:196-197 */
+#define DCL_CHUNK_PIXELS 2048 /* pixels per sampler chunk (one CTA) */
+#define DCL_HIST_BINS 512     /* 256 label values x {hard, easy} */
+
+enum dcl_status {
+    DCL_OK = 0,
+    DCL_ERR_ARG = -1,       /* bad argument (shape, alignment, null) */
+    DCL_ERR_WORKSPACE = -2, /* workspace too small */
+    DCL_ERR_ARCH = -3       /* device is not sm_100 */
+};
+
+int dcl_version(void);
+const char* dcl_last_error(void);
+/* 0 iff the current device can run the kernels (compute capability 10.x). */
+int dcl_check_device(void);
+
+/* ---------------------------------------------------------------- sampler front end
+ * Replaces loss.py:396-408 (argmax over classes, nearest down-sampling of labels) and the
+ * counting half of _hard_anchor_sampling (loss.py:278-285, 308-312).
+ *   labels   [B,H,W] int64      predict [B,C_cls,h,w] f32
+ *   code     [B,h*w] u16 out :  low byte = down-sampled label (0..255), bit 8 = easy
+ *                               (label == argmax), 0xFFFF = label outside 0..255
+ *   chunk_hist [B,n_chunks,512] i32 out : on return holds, per (image, bin = label*2+easy),
+ *                               the EXCLUSIVE prefix over chunks of that bin's pixel count
+ *   counts   [B,512] i32 out  : per-image totals per bin  (hard = bin label*2, easy = +1)
+ *   n_chunks = ceil(h*w / DCL_CHUNK_PIXELS)
+ */
+int dcl_sample_classify(const int64_t* labels, const float* predict, int B, int H, int W, int h,
+                        int w, int C_cls, uint16_t* code, int32_t* chunk_hist, int32_t* counts,
+                        void* stream);
+
+/* Rank -> pixel selection: replaces the `nonzero()[perm[:k]]` indexing of loss.py:308-331.
+ *   req [N,4] i32 : (image, label, easy(0/1), rank) - "the rank-th pixel, in raster order, of
+ *                   that image whose code matches"; rank comes from the host's randperm draw.
+ *                   image < 0 marks a padding row.
+ *   pix [N] i32 out : flat pixel id image*h*w + p, or -1 for padding rows.
+ */
+int dcl_sample_select(const uint16_t* code, const int32_t* chunk_hist, int B, int hw,
+                      const int32_t* req, int N, int32_t* pix, void* stream);
+
+/* Gather anchor rows into F-tiles: replaces the NCHW->NHWC copy + per-class advanced-index gather
+ * of loss.py:409-410, :333.
+ *   feats [B,128,h*w] f32 (NCHW), pix [n_pad] (from dcl_sample_select; -1 => zero row)
+ *   tiles [n_pad/128] F-tiles out, sqnorm [n_pad] f32 out (|bf16(f)|^2, the row shift)
+ */
+int dcl_gather_tiles(const float* feats, int B, int hw, const int32_t* pix, int n_pad,
+                     void* tiles, float* sqnorm, void* stream);
+
+/* Same, from a dense row-major matrix Z [n,128] f32 (image-level term, loss.py:161). Rows >= n
+ * are zero padding. */
+int dcl_pack_rows(const float* Z, int n, int n_pad, void* tiles, float* sqnorm, void* stream);
+
+/* ---------------------------------------------------------------- N x N contrast
+ * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
+ * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.
+ *   tiles  [nJ] F-tiles (the whole contrast set; all-gathered by the caller when sharded)
+ *   y      [nJ*128] i32 labels, -1 = padding        sqnorm [nJ*128]
+ *   n_valid : number of valid rows over the WHOLE contrast set (the reference's N)
+ *   colA, colB [nJ*128] float4 out (rows of the local blocks only are written): per-row
+ *            constants consumed by dcl_contrast_bwd; all-gather them before a sharded backward
+ *   rowloss [nJ*128] f32 out (local rows): per-row loss term, 0 for padding
+ *   loss_sum [1] f32 out: sum of rowloss over the local rows (caller divides by n_valid)
+ *   workspace: dcl_contrast_workspace_bytes(nI, nJ) bytes
+ */
+size_t dcl_contrast_workspace_bytes(int nI, int nJ);
+int dcl_contrast_fwd(const void* tiles, const int32_t* y, const float* sqnorm, int nJ, int rb0,
+                     int nI, int n_valid, int mode, float temperature, float base_temperature,
+                     void* workspace, size_t workspace_bytes, float* colA, float* colB,
+                     float* rowloss, float* loss_sum, void* stream);
+
+/* Backward: dF[local rows] = sum_k (dS_ik + dS_ki) F_k, tiles recomputed (autograd of
+ * loss.py:361-388).  colA/colB must hold ALL rows.  dF [nI*128,128] f32 out (d loss / d row,
+ * for loss = mean over n_valid rows; not yet multiplied by the upstream gradient). */
+int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB,
+                     int nJ, int rb0, int nI, int mode, void* workspace, size_t workspace_bytes,
+                     float* dF, void* stream);
+
+/* ---------------------------------------------------------------- gradient back to NCHW
+ * Replaces autograd of the gather (index_put into a zero tensor per class):
+ * dfeats [B,128,h*w] f32 is zero-filled, then row n's gradient * (*grad_out) is written at
+ * pixel pix[n] (pix < 0 skipped).  grad_out: device scalar (upstream dL/dloss). */
+int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const float* grad_out,
+                     float* dfeats, int B, int hw, int zero_fill, void* stream);
+/* dZ [n,128] = dF[:n] * (*grad_out)  (image-level term). */
+int dcl_unpack_rows(const float* dF, int n, const float* grad_out, float* dZ, void* stream);
+
+/* ---------------------------------------------------------------- global average pool
+ * nn.AdaptiveAvgPool2d((1,1)) forward/backward (loss.py:104, :115): x [R,hw] rows = (image,
+ * channel) pairs -> pooled [R]; backward broadcasts g[R]/hw. `accumulate` != 0 adds into dx
+ * (fused with the pixel-term scatter target). */
+int dcl_gap_fwd(const float* x, int R, int hw, float* pooled, void* stream);
+int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCL_B200_H */
