@@ -30,6 +30,10 @@ SIGNATURES = {
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
 }
 
+# kernels launched per call (kept next to the signatures; bench.py reports the total per step)
+FWD_LAUNCHES = 6   # block_ranges, sweep A, sweep B, sweep C, finalize, loss_sum
+BWD_LAUNCHES = 3   # block_ranges, backward, reduce_dF
+
 _lib = None
 
 

@@ -29,6 +29,48 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_LAUNCHES = 0          # kernels of ours launched since reset (bench.py's `gpu_launches`)
+_PROFILE_HOOK = None   # callable(name, start_event, end_event) around the similarity calls
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def set_profile_hook(fn):
+    global _PROFILE_HOOK
+    _PROFILE_HOOK = fn
+
+
+def _count(n):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+class _Timed:
+    """Records a CUDA-event pair on the current stream around a block when a hook is installed."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _PROFILE_HOOK is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE_HOOK is not None:
+            self.b.record()
+            _PROFILE_HOOK(self.name, self.a, self.b)
+
+
 def _require_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise _lib.DclError("%s must be a CUDA tensor: this library has no CPU path" % name)
@@ -145,12 +187,14 @@ def classify(labels: torch.Tensor, predict: torch.Tensor, h: int, w: int):
     counts = torch.empty((B, _BINS), dtype=torch.int32, device=dev)
     _lib.call("dcl_sample_classify", _p(labels), _p(predict), B, H, W, h, w, C, _p(code), _p(chunk),
               _p(counts), _stream())
+    _count(2)
     return code, chunk, counts
 
 
 def select_pixels(code, chunk, B, hw, req_dev, n_rows):
     pix = torch.empty(n_rows, dtype=torch.int32, device=code.device)
     _lib.call("dcl_sample_select", _p(code), _p(chunk), B, hw, _p(req_dev), n_rows, _p(pix), _stream())
+    _count(1)
     return pix
 
 
@@ -159,6 +203,7 @@ def gather_tiles(feats, pix, n_pad):
     tiles = torch.empty(n_pad * _DIM * 2, dtype=torch.uint8, device=feats.device)
     sqnorm = torch.empty(n_pad, dtype=torch.float32, device=feats.device)
     _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tiles), _p(sqnorm), _stream())
+    _count(1)
     return tiles, sqnorm
 
 
@@ -167,6 +212,7 @@ def pack_rows(Z, n_pad):
     tiles = torch.empty(n_pad * _DIM * 2, dtype=torch.uint8, device=Z.device)
     sqnorm = torch.empty(n_pad, dtype=torch.float32, device=Z.device)
     _lib.call("dcl_pack_rows", _p(Z), n, n_pad, _p(tiles), _p(sqnorm), _stream())
+    _count(1)
     return tiles, sqnorm
 
 
@@ -180,8 +226,10 @@ def contrast_forward(tiles, y, sqnorm, nJ, rb0, nI, n_valid, mode, T, Tb, colA=N
     loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
     nbytes = _lib.workspace_bytes(nI, nJ)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.call("dcl_contrast_fwd", _p(tiles), _p(y), _p(sqnorm), nJ, rb0, nI, n_valid, mode, float(T),
-              float(Tb), _p(ws), nbytes, _p(colA), _p(colB), _p(rowloss), _p(loss_sum), _stream())
+    with _Timed("contrast_fwd"):
+        _lib.call("dcl_contrast_fwd", _p(tiles), _p(y), _p(sqnorm), nJ, rb0, nI, n_valid, mode, float(T),
+                  float(Tb), _p(ws), nbytes, _p(colA), _p(colB), _p(rowloss), _p(loss_sum), _stream())
+    _count(_lib.FWD_LAUNCHES)
     return colA, colB, rowloss, loss_sum
 
 
@@ -190,8 +238,10 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
     dF = torch.empty((nI * _TILE, _DIM), dtype=torch.float32, device=dev)
     nbytes = _lib.workspace_bytes(nI, nJ)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.call("dcl_contrast_bwd", _p(tiles), _p(y), _p(colA), _p(colB), nJ, rb0, nI, mode, _p(ws), nbytes,
-              _p(dF), _stream())
+    with _Timed("contrast_bwd"):
+        _lib.call("dcl_contrast_bwd", _p(tiles), _p(y), _p(colA), _p(colB), nJ, rb0, nI, mode, _p(ws), nbytes,
+                  _p(dF), _stream())
+    _count(_lib.BWD_LAUNCHES)
     return dF
 
 
@@ -223,6 +273,7 @@ class _PixelContrastFn(torch.autograd.Function):
         g = grad_out.to(torch.float32).contiguous()
         _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
                   _stream())
+        _count(2)
         return dfeats, None, None, None, None, None
 
 
@@ -251,6 +302,7 @@ class _ContrastRowsFn(torch.autograd.Function):
         dZ = torch.empty((n, _DIM), dtype=torch.float32, device=tiles.device)
         g = grad_out.to(torch.float32).contiguous()
         _lib.call("dcl_unpack_rows", _p(dF), n, _p(g), _p(dZ), _stream())
+        _count(1)
         return dZ, None, None, None, None
 
 
@@ -263,6 +315,7 @@ class _GapFn(torch.autograd.Function):
         xc = x.contiguous()
         pooled = torch.empty((B2, C), dtype=torch.float32, device=x.device)
         _lib.call("dcl_gap_fwd", _p(xc), B2 * C, h * w, _p(pooled), _stream())
+        _count(1)
         ctx.shape = (B2, C, h, w)
         return pooled
 
@@ -272,6 +325,7 @@ class _GapFn(torch.autograd.Function):
         dx = torch.empty((B2, C, h, w), dtype=torch.float32, device=g.device)
         gc = g.contiguous().to(torch.float32)
         _lib.call("dcl_gap_bwd", _p(gc), B2 * C, h * w, _p(dx), 0, _stream())
+        _count(1)
         return dx
 
 
@@ -420,3 +474,126 @@ class SupConLoss(nn.Module):
         Z = torch.cat(torch.unbind(z, dim=1), dim=0)                         # loss.py:161
         yy = y.repeat(n_views)
         return _ContrastRowsFn.apply(Z, yy, MODE_SUPCON, self.temperature, self.base_temperature)
+
+
+# ----------------------------------------------------------------------------------------------
+# multi-GPU: anchor rows sharded over ranks, contrast set all-gathered
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class ShardPlan:
+    plan: AnchorPlan
+    layout: RowLayout          # this rank's rows (padded to n_pad, identical on every rank)
+    n_pad: int                 # rows per rank block (multiple of 128)
+    n_global: int              # valid rows over all ranks == the reference's N on the full batch
+    rows_per_rank: np.ndarray  # [world] valid rows per rank
+
+
+def shard_plan(counts_all: np.ndarray, rank: int, world: int, images_per_rank: int, ignore_label: int,
+               max_samples: int, max_views: int,
+               randperm: Callable[[int, int], np.ndarray] = _torch_randperm_prefix) -> Optional[ShardPlan]:
+    """Host logic of the sharded sampler.  `counts_all` [world*images_per_rank,256,2] is the
+    all-gathered histogram; every rank replays the SAME host RNG stream over the global batch
+    (image order = rank-major) and keeps the anchors of its own images, so the union over ranks is
+    exactly the single-process reference sample of the concatenated batch."""
+    plan = plan_anchors(counts_all, ignore_label, max_samples, max_views, randperm)
+    if plan is None:
+        return None
+    owner = plan.image // images_per_rank
+    rows = np.array([int((owner == r).sum()) * plan.n_view for r in range(world)], dtype=np.int64)
+    n_pad = max(_TILE, int((rows.max() + _TILE - 1) // _TILE * _TILE))
+    mine = np.nonzero(owner == rank)[0]
+    lay = layout_rows(plan, mine, rank * images_per_rank, n_pad=n_pad)
+    return ShardPlan(plan, lay, n_pad, int(rows.sum()), rows)
+
+
+class _ShardedPixelContrastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, pix, y_local, n_global, T, Tb, group):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, C, h, w = feats.shape
+        n_pad = pix.shape[0]
+        dev = feats.device
+        tiles_l, sqnorm_l = gather_tiles(feats, pix, n_pad)
+        tiles = torch.empty(world * n_pad * _DIM * 2, dtype=torch.uint8, device=dev)
+        y_all = torch.empty(world * n_pad, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(tiles, tiles_l, group=group)        # the one real exchange step
+        dist.all_gather_into_tensor(y_all, y_local.contiguous(), group=group)
+        sqnorm = torch.zeros(world * n_pad, dtype=torch.float32, device=dev)
+        sqnorm[rank * n_pad:(rank + 1) * n_pad] = sqnorm_l
+        nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
+        colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_all, sqnorm, nJ, rb0, nI, n_global,
+                                                         MODE_PIXEL, T, Tb)
+        # backward needs every row's constants (the dS_ki terms): 32 B per row
+        la = colA[rank * n_pad:(rank + 1) * n_pad].clone()
+        lb = colB[rank * n_pad:(rank + 1) * n_pad].clone()
+        dist.all_gather_into_tensor(colA, la, group=group)
+        dist.all_gather_into_tensor(colB, lb, group=group)
+        dist.all_reduce(loss_sum, group=group)
+        ctx.save_for_backward(tiles, y_all, colA, colB, pix)
+        ctx.meta = dict(nJ=nJ, rb0=rb0, nI=nI, n_local_pad=n_pad, shape=(B, C, h, w))
+        return (loss_sum / n_global).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        tiles, y_all, colA, colB, pix = ctx.saved_tensors
+        m = ctx.meta
+        dF = contrast_backward(tiles, y_all, colA, colB, m["nJ"], m["rb0"], m["nI"], MODE_PIXEL)
+        B, C, h, w = m["shape"]
+        dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
+        g = grad_out.to(torch.float32).contiguous()
+        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
+                  _stream())
+        _count(2)
+        return dfeats, None, None, None, None, None, None
+
+
+class ShardedPixelContrastLoss(PixelContrastLoss):
+    """Data-parallel form of PixelContrastLoss for one process per GPU (torch.distributed, NCCL).
+
+    Each rank passes ITS images (same per-rank batch size everywhere).  The result equals the
+    reference's loss on the concatenated global batch (rank-major image order) and is identical on
+    every rank; backward yields d(global loss)/d(local feats) exactly, including the terms that
+    come from other ranks' rows.  All ranks must hold the same torch CPU RNG state on entry
+    (e.g. `torch.manual_seed(step)` everywhere), because each replays the full host RNG stream.
+    The reference has no multi-GPU path; this is new design, not a port.
+    """
+
+    def __init__(self, device=None, process_group=None):
+        super().__init__(device=device)
+        self.process_group = process_group
+        self.last_n_global = 0
+
+    def forward(self, feats, labels=None, predict=None):
+        import torch.distributed as dist
+        _require_cuda(feats, "feats")
+        if labels is None or predict is None:
+            raise TypeError("ShardedPixelContrastLoss needs labels and predict")
+        if feats.dim() != 4 or feats.shape[1] != _DIM:
+            raise ValueError("feats must be [B,128,h,w]; got %s" % (tuple(feats.shape),))
+        group = self.process_group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, C, h, w = feats.shape
+        feats_c = feats.contiguous().to(torch.float32)
+        labels_c = labels.contiguous().to(torch.int64)
+        predict_c = predict.detach().contiguous().to(torch.float32)
+        code, chunk, counts = classify(labels_c, predict_c, h, w)
+        counts_all = torch.empty((world * B, _BINS), dtype=torch.int32, device=feats.device)
+        dist.all_gather_into_tensor(counts_all, counts, group=group)
+        counts_host = counts_all.cpu().numpy().reshape(world * B, 256, 2)
+        sp = shard_plan(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
+                        int(self.max_views))
+        self.last_plan = None if sp is None else sp.plan
+        if sp is None:
+            return feats_c.sum() * 0.0
+        if sp.plan.n_view <= 0:
+            raise RuntimeError("max_samples // total_classes == 0: no views to sample")
+        lay = sp.layout
+        self.last_layout, self.last_n_global = lay, sp.n_global
+        host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
+        packed = host.to(feats.device, non_blocking=True)
+        req_dev, y_dev = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
+        pix = select_pixels(code, chunk, B, h * w, req_dev, lay.n_pad)
+        self.last_pix = pix
+        return _ShardedPixelContrastFn.apply(feats_c, pix, y_dev, sp.n_global, self.temperature,
+                                             self.base_temperature, group)

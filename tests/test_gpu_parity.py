@@ -276,3 +276,19 @@ def test_full_size_cfg2_properties_and_oracle(dcl):
     loss_o, dF_o, _ = O.pixel_contrast_closed_form(rows_f.cpu(), torch.from_numpy(lay.y[: lay.n]).long())
     assert abs(loss.item() - loss_o) <= LOSS_RTOL * abs(loss_o)
     assert _relmax(rows_g.cpu(), dF_o) <= GRAD_RTOL
+
+
+# ------------------------------------------------------------------ multi-GPU (needs >= 2 GPUs)
+@pytest.mark.parametrize("workload", ["small"])
+def test_sharded_equals_single_gpu(dcl, workload):
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs on the box (gpurun --gpus 2); host logic is covered by the gloo test")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(root, "tools", "sharded_check.py"), workload]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

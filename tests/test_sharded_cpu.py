@@ -1,0 +1,96 @@
+"""world_size-2 gloo test (CPU) of the sharded sampler's host logic: every rank replays the same
+RNG stream over the all-gathered histograms and keeps its own anchors; the union must be exactly
+the single-process reference sample of the concatenated batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dcl_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _inputs(B, h, w, K, seed):
+    g = np.random.default_rng(seed)
+    lab = g.integers(0, K, size=(B, h // 4, w // 4)).repeat(4, 1).repeat(4, 2).reshape(B, h * w)
+    lab[g.random((B, h * w)) < 0.05] = 255
+    pred = np.where(g.random((B, h * w)) < 0.6, np.minimum(lab, 18), g.integers(0, 19, size=(B, h * w)))
+    return lab.astype(np.int64), pred.astype(np.int64)
+
+
+def _counts(lab, pred):
+    B = lab.shape[0]
+    c = np.zeros((B, 256, 2), dtype=np.int32)
+    for b in range(B):
+        for cls in np.unique(lab[b]):
+            m = lab[b] == cls
+            e = int((m & (pred[b] == cls)).sum())
+            c[b, cls] = (int(m.sum()) - e, e)
+    return c
+
+
+def _worker(rank, world, port, B, h, w, K, mv, ms, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from doubly_contrastive_semseg_b200.loss import shard_plan
+    lab, pred = _inputs(B, h, w, K, seed=5)
+    bl = B // world
+    mine = slice(rank * bl, (rank + 1) * bl)
+    local = torch.from_numpy(_counts(lab[mine], pred[mine]).reshape(bl, 512))
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    counts_all = torch.cat(gathered).numpy().reshape(B, 256, 2)
+    torch.manual_seed(77)                                   # same RNG state on every rank
+    sp = shard_plan(counts_all, rank, world, bl, 255, ms, mv)
+    lay = sp.layout
+    # emulate the select kernel on this rank's images
+    pix = np.full(lay.n_pad, -1, dtype=np.int64)
+    for n in range(lay.n):
+        b, c, easy, rk = (int(v) for v in lay.req[n])
+        assert 0 <= b < bl
+        sel = np.nonzero((lab[mine][b] == c) & ((pred[mine][b] == c) == bool(easy)))[0]
+        pix[n] = sel[rk]
+    out[rank] = dict(A=sp.plan.A, V=sp.plan.n_view, n_pad=sp.n_pad, n_global=sp.n_global,
+                     ref_row=lay.ref_row.copy(), pix=pix, y=lay.y.copy(), n=lay.n,
+                     rows=sp.rows_per_rank.copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,h,w,K,mv,ms", [(4, 16, 32, 5, 6, 1024), (6, 12, 20, 3, 5, 40)])
+def test_shard_plan_union_equals_single_process_reference(B, h, w, K, mv, ms):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, B, h, w, K, mv, ms, out), nprocs=world, join=True)
+    lab, pred = _inputs(B, h, w, K, seed=5)
+    torch.manual_seed(77)
+    plan = O.sample_anchors(lab, pred, 255, ms, mv, O.torch_randperm_prefix)
+    r0, r1 = out[0], out[1]
+    assert r0["A"] == plan.A and r0["V"] == plan.n_view
+    assert r0["n_pad"] == r1["n_pad"] and r0["n_pad"] % 128 == 0
+    assert r0["n_global"] == plan.A * plan.n_view == r0["n"] + r1["n"]
+    assert list(r0["rows"]) == [r0["n"], r1["n"]]
+    got = np.full((plan.A, plan.n_view), -1, dtype=np.int64)
+    for r in (r0, r1):
+        for n in range(r["n"]):
+            v, a = divmod(int(r["ref_row"][n]), plan.A)
+            assert got[a, v] == -1
+            got[a, v] = r["pix"][n]
+            assert r["y"][n] == plan.cls[a]
+        assert np.all(np.diff(r["y"][: r["n"]]) >= 0)          # class-sorted inside the rank block
+        assert np.all(r["y"][r["n"]:] == -1)
+    assert np.array_equal(got, plan.pixels)
