@@ -11,10 +11,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcl_b200.so")
-SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_sampler.cu"]
+SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_sampler.cu", "dcl_host_rng.cpp"]
 HEADERS = ["dcl_ptx.cuh", "dcl_common.cuh", os.path.join("..", "..", "include", "dcl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC,-O3", "--use_fast_math", "-Xptxas", "-v"]
 
 
 def _nvcc():
@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
     objs = []
     log = []
     for s in SOURCES:
-        o = os.path.join(objdir, s.replace(".cu", ".o"))
+        o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)

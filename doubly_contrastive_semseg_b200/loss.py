@@ -91,29 +91,70 @@ class AnchorPlan:
     ranks: np.ndarray      # [A, n_view] rank inside the hard (v < keep_hard) or easy list
 
 
-def _split_rule(num_hard: int, num_easy: int, n_view: int):
-    """(keep_hard, keep_easy), reference loss.py:314-325 (true division on n_view)."""
-    if num_hard >= n_view / 2 and num_easy >= n_view / 2:
-        kh = n_view // 2
-        return kh, n_view - kh
-    if num_hard >= n_view / 2:
-        return n_view - num_easy, num_easy
-    if num_easy >= n_view / 2:
-        return num_hard, n_view - num_hard
-    print("this shoud be never touched! {} {} {}".format(num_hard, num_easy, n_view))
-    raise Exception
-
-
 def _torch_randperm_prefix(n: int, k: int) -> np.ndarray:
     # consumes the global CPU generator exactly like loss.py:327,329
     return torch.randperm(n)[:k].numpy()
 
 
+_HOST_RNG_OK: Optional[bool] = None
+
+
+def _c_sample_ranks(nh: np.ndarray, ne: np.ndarray, kh: np.ndarray, n_view: int) -> np.ndarray:
+    """All randperm prefixes of one call in C, on torch's serialized global CPU generator state
+    (csrc/dcl_host_rng.cpp); the generator ends exactly where the reference's calls would leave it."""
+    st = torch.get_rng_state()
+    buf = st.numpy()
+    A = int(nh.shape[0])
+    out = np.empty((A, n_view), dtype=np.int64)
+    nh, ne, kh = (np.ascontiguousarray(v, dtype=np.int64) for v in (nh, ne, kh))
+    _lib.call("dcl_host_sample_ranks", buf.ctypes.data, buf.nbytes, A, n_view, nh.ctypes.data,
+              ne.ctypes.data, kh.ctypes.data, out.ctypes.data)
+    torch.set_rng_state(st)
+    return out
+
+
+def _torch_sample_ranks(nh, ne, kh, n_view, randperm) -> np.ndarray:
+    A = int(nh.shape[0])
+    out = np.zeros((A, n_view), dtype=np.int64)
+    for a in range(A):
+        k_h = int(kh[a])
+        out[a, :k_h] = randperm(int(nh[a]), k_h)               # hard first, loss.py:327-328
+        out[a, k_h:] = randperm(int(ne[a]), n_view - k_h)      # then easy, loss.py:329-330
+    return out
+
+
+def _verify_host_rng() -> bool:
+    """One-time check that the C replay and torch.randperm agree on this torch build (results and
+    final generator state).  The global generator is restored afterwards."""
+    global _HOST_RNG_OK
+    if _HOST_RNG_OK is not None:
+        return _HOST_RNG_OK
+    saved = torch.get_rng_state()
+    try:
+        nh = np.array([0, 1, 700, 5, 1300, 2], dtype=np.int64)
+        ne = np.array([9, 640, 3, 2000, 1, 625], dtype=np.int64)
+        kh = np.array([0, 1, 3, 3, 5, 2], dtype=np.int64)
+        ne_keep = 6 - kh
+        assert np.all(ne_keep <= ne)
+        torch.default_generator.manual_seed(20221118)
+        got = _c_sample_ranks(nh, ne, kh, 6)
+        end_c = torch.get_rng_state().clone()
+        torch.default_generator.manual_seed(20221118)
+        want = _torch_sample_ranks(nh, ne, kh, 6, _torch_randperm_prefix)
+        end_t = torch.get_rng_state()
+        _HOST_RNG_OK = bool(np.array_equal(got, want) and torch.equal(end_c, end_t))
+    except Exception:
+        _HOST_RNG_OK = False
+    finally:
+        torch.set_rng_state(saved)
+    return _HOST_RNG_OK
+
+
 def plan_anchors(counts: np.ndarray, ignore_label: int, max_samples: int, max_views: int,
-                 randperm: Callable[[int, int], np.ndarray] = _torch_randperm_prefix
-                 ) -> Optional[AnchorPlan]:
+                 randperm: Optional[Callable[[int, int], np.ndarray]] = None) -> Optional[AnchorPlan]:
     """counts [B,256,2] = pixels per (image, label, hard|easy).  Returns None when no class
-    qualifies (reference: `return None, None`, loss.py:287-288)."""
+    qualifies (reference: `return None, None`, loss.py:287-288).  With `randperm=None` the draws
+    come from torch's global CPU generator (C replay when verified, torch.randperm otherwise)."""
     tot = counts.sum(axis=2)
     keep = tot > max_views                                    # loss.py:282
     if 0 <= ignore_label <= 255:
@@ -125,13 +166,22 @@ def plan_anchors(counts: np.ndarray, ignore_label: int, max_samples: int, max_vi
     n_view = min(max_samples // A, max_views)                 # loss.py:290-291
     nh = counts[img, cls, 0].astype(np.int64)
     ne = counts[img, cls, 1].astype(np.int64)
-    kh = np.zeros(A, dtype=np.int64)
-    ranks = np.zeros((A, n_view), dtype=np.int64)
-    for a in range(A):
-        k_h, k_e = _split_rule(int(nh[a]), int(ne[a]), n_view)
-        kh[a] = k_h
-        ranks[a, :k_h] = randperm(int(nh[a]), k_h)            # hard first, loss.py:327-328
-        ranks[a, k_h:] = randperm(int(ne[a]), k_e)            # then easy, loss.py:329-330
+    # split rule, loss.py:314-325 (true division on n_view)
+    half = n_view / 2
+    c1 = (nh >= half) & (ne >= half)
+    c2 = ~c1 & (nh >= half)
+    c3 = ~c1 & ~c2 & (ne >= half)
+    if not bool(np.all(c1 | c2 | c3)):
+        bad = int(np.nonzero(~(c1 | c2 | c3))[0][0])
+        print("this shoud be never touched! {} {} {}".format(int(nh[bad]), int(ne[bad]), n_view))
+        raise Exception
+    kh = np.where(c1, n_view // 2, np.where(c2, n_view - ne, nh)).astype(np.int64)
+    if n_view <= 0:
+        ranks = np.zeros((A, 0), dtype=np.int64)
+    elif randperm is None and _verify_host_rng():
+        ranks = _c_sample_ranks(nh, ne, kh, n_view)
+    else:
+        ranks = _torch_sample_ranks(nh, ne, kh, n_view, randperm or _torch_randperm_prefix)
     return AnchorPlan(A, n_view, img.astype(np.int64), cls.astype(np.int64), nh, ne, kh, ranks)
 
 
@@ -490,7 +540,7 @@ class ShardPlan:
 
 def shard_plan(counts_all: np.ndarray, rank: int, world: int, images_per_rank: int, ignore_label: int,
                max_samples: int, max_views: int,
-               randperm: Callable[[int, int], np.ndarray] = _torch_randperm_prefix) -> Optional[ShardPlan]:
+               randperm: Optional[Callable[[int, int], np.ndarray]] = None) -> Optional[ShardPlan]:
     """Host logic of the sharded sampler.  `counts_all` [world*images_per_rank,256,2] is the
     all-gathered histogram; every rank replays the SAME host RNG stream over the global batch
     (image order = rank-major) and keeps the anchors of its own images, so the union over ranks is

@@ -83,6 +83,15 @@ int dcl_gather_tiles(const float* feats, int B, int hw, const int32_t* pix, int 
  * are zero padding. */
 int dcl_pack_rows(const float* Z, int n, int n_pad, void* tiles, float* sqnorm, void* stream);
 
+/* Host-side (no GPU work): replay of torch's CPU mt19937 for the sampler's randperm draws,
+ * loss.py:327-330.  `torch_rng_state` is the HOST buffer returned by torch.get_rng_state() (updated in
+ * place; write it back with torch.set_rng_state).  For anchor a (reference order) writes
+ * randperm(num_hard[a])[:keep_hard[a]] then randperm(num_easy[a])[:n_view-keep_hard[a]] into
+ * ranks[a][0..n_view) and advances the generator exactly as the reference's calls would. */
+int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int n_view,
+                          const int64_t* num_hard, const int64_t* num_easy, const int64_t* keep_hard,
+                          int64_t* ranks);
+
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.

@@ -75,3 +75,24 @@ def test_host_plan_reproduces_reference_indices(case):
         got[a, v] = sel[rank]
     assert np.array_equal(got, g["pixels"])
     assert np.all(lay.req[lay.n:, 0] == -1) and np.all(lay.y[lay.n:] == -1)
+
+
+def test_c_rng_replay_matches_torch_randperm(built_lib):
+    """dcl_host_sample_ranks == the reference's torch.randperm calls, including the generator state
+    it leaves behind (so later RNG users see the same stream)."""
+    from doubly_contrastive_semseg_b200 import loss as L
+    assert L._verify_host_rng() is True
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        A, n_view = int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        nh = rng.integers(0, 3000, A)
+        ne = rng.integers(n_view, 3000, A)
+        kh = np.minimum(nh, rng.integers(0, n_view + 1, A))
+        torch.manual_seed(100 + trial)
+        got = L._c_sample_ranks(nh, ne, kh, n_view)
+        tail_c = torch.randperm(11)
+        torch.manual_seed(100 + trial)
+        want = L._torch_sample_ranks(nh, ne, kh, n_view, L._torch_randperm_prefix)
+        tail_t = torch.randperm(11)
+        assert np.array_equal(got, want)
+        assert torch.equal(tail_c, tail_t)
