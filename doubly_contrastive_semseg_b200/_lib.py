@@ -17,6 +17,8 @@ SIGNATURES = {
     "dcl_version": (_i, []),
     "dcl_last_error": (_c.c_char_p, []),
     "dcl_check_device": (_i, []),
+    "dcl_debug_flags": (_i, [_i]),
+    "dcl_debug_trace": (_i, [_vp]),
     "dcl_sample_classify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "dcl_host_sample_ranks": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
@@ -32,8 +34,8 @@ SIGNATURES = {
 }
 
 # kernels launched per call (kept next to the signatures; bench.py reports the total per step)
-FWD_LAUNCHES = 6   # block_ranges, sweep A, sweep B, sweep C, finalize, loss_sum
-BWD_LAUNCHES = 3   # block_ranges, backward, reduce_dF
+FWD_LAUNCHES = 4   # sweep A, sweep B, sweep C, finalize
+BWD_LAUNCHES = 2   # backward, reduce_dF
 
 _lib = None
 

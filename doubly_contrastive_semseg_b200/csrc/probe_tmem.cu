@@ -1,0 +1,97 @@
+// TMEM read/write throughput probe: bytes per clock per SM for tcgen05.ld / tcgen05.st with
+// 4, 8 or 16 warps per CTA (one CTA per SM).  Stand-alone.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "dcl_ptx.cuh"
+using namespace dcl;
+
+__device__ __forceinline__ void ld_x32(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void ld_x64(uint32_t taddr, uint32_t (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+          "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+          "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+          "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+          "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr) : "memory");
+}
+
+template <int MODE>   // 0: ld x32, 1: ld x64, 2: st x16, 3: ld x32 + 32 FFMA per load (compute overlap)
+__global__ void k_tmem(unsigned long long* clocks, float* sink, int iters) {
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc<512>(smem_u32(&slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t col_base = (warp >> 2) * 128 % 512;     // warps of the same quadrant use other columns
+    uint32_t acc = 0;
+    float facc = 1.0f;
+    __syncthreads();
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0 || MODE == 3) {
+            uint32_t v[32];
+            ld_x32(tmem + lane_off + ((col_base + (it & 3) * 32) & 511), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (MODE == 3) facc = fmaf(__uint_as_float(v[j]), 1.0001f, facc);
+                else acc ^= v[j];
+            }
+        } else if (MODE == 1) {
+            uint32_t v[64];
+            ld_x64(tmem + lane_off + ((col_base + (it & 1) * 64) & 511), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc ^= v[j];
+        } else {
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = acc + j + it;
+            tmem_st16(tmem + lane_off + ((col_base + (it & 7) * 16) & 511), v);
+            acc += it;
+        }
+    }
+    if (MODE == 2) tmem_st_wait();
+    unsigned long long t1 = clock64();
+    if (threadIdx.x == 0) clocks[blockIdx.x] = t1 - t0;
+    if (acc == 0x12345678u || facc == 3.25f) sink[0] = acc + facc;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+template <int MODE>
+void run(const char* name, int warps, int bytes_per_iter_per_thread) {
+    unsigned long long* d; float* s;
+    cudaMalloc(&d, 148 * 8); cudaMalloc(&s, 4);
+    const int iters = 4096;
+    k_tmem<MODE><<<148, warps * 32>>>(d, s, 64);
+    cudaDeviceSynchronize();
+    k_tmem<MODE><<<148, warps * 32>>>(d, s, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    double clk = 0; for (int i = 0; i < 148; ++i) clk += h[i]; clk /= 148;
+    double bytes = (double)warps * 32 * bytes_per_iter_per_thread * iters;
+    printf("%-34s warps=%2d  %8.0f clk  -> %7.1f B/clk/SM  (%s)\n", name, warps, clk, bytes / clk, cudaGetErrorString(e));
+    cudaFree(d); cudaFree(s);
+}
+
+int main() {
+    for (int w : {4, 8, 16}) run<0>("tcgen05.ld 32x32b.x32 (+xor)", w, 128);
+    for (int w : {4, 8, 16}) run<1>("tcgen05.ld 32x32b.x64 (+xor)", w, 256);
+    for (int w : {4, 8}) run<3>("tcgen05.ld x32 + 32 FFMA", w, 128);
+    for (int w : {4, 8}) run<2>("tcgen05.st 32x32b.x16", w, 64);
+    return 0;
+}

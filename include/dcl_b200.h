@@ -46,6 +46,13 @@ int dcl_version(void);
 const char* dcl_last_error(void);
 /* 0 iff the current device can run the kernels (compute capability 10.x). */
 int dcl_check_device(void);
+/* Diagnostics only: profiling switches for the contrast kernels (1 = skip epilogue math, 2 = skip
+ * the S = F_I F_J^T MMAs, 4 = skip the dF MMAs).  Results are invalid while non-zero.  Returns the
+ * previous value. */
+int dcl_debug_flags(int flags);
+/* Diagnostics only: device buffer (3*32*4 int64, or NULL to disable) that CTA 0 of the backward kernel
+ * fills with per-role clock64 stamps of its first 32 tiles. */
+int dcl_debug_trace(void* device_buffer);
 
 /* ---------------------------------------------------------------- sampler front end
  * Replaces loss.py:396-408 (argmax over classes, nearest down-sampling of labels) and the

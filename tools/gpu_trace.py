@@ -1,0 +1,27 @@
+"""Per-role timeline of CTA 0 of k_backward (diagnostics)."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from doubly_contrastive_semseg_b200 import loss as L, _lib
+lib = _lib.load()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+g = torch.Generator(device="cuda").manual_seed(n)
+y = torch.randint(0, 16, (n,), generator=g, device="cuda").sort().values.int()
+Z = torch.randn(n, 128, generator=g, device="cuda")
+tiles, sq = L.pack_rows(Z, n)
+nJ = n // 128
+colA, colB, rl, ls = L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
+for _ in range(2):
+    L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
+buf = torch.zeros(3 * 32 * 4, dtype=torch.int64, device="cuda")
+lib.dcl_debug_trace(buf.data_ptr())
+L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
+torch.cuda.synchronize()
+lib.dcl_debug_trace(None)
+t = buf.cpu().view(3, 32, 4)
+t0 = int(t[t > 0].min())
+print("tile | producer: wait_empty got_empty | mma: wait_full got_full wait_pfull got_pfull | epilogue: start got_tfull done   (clk since first stamp)")
+for it in range(24):
+    r = lambda role, ev: (int(t[role, it, ev]) - t0) if int(t[role, it, ev]) else -1
+    print(f"{it:4d} | {r(0,0):7d} {r(0,1):7d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} {r(1,3):7d} | {r(2,0):7d} {r(2,1):7d} {r(2,2):7d}")
