@@ -32,17 +32,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile the library if it is missing or older than its sources. Returns the .so path."""
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile the library if it is missing or older than its sources. Returns the .so path.
+    `extra_flags`/`out` build an experimental variant next to the default library (tools only)."""
+    if out is not None:
+        return _build_to(out, list(extra_flags), verbose)
     if not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    return _build_to(LIB, [], verbose)
+
+
+def _build_to(LIB, extra, verbose):
+    objdir = os.path.join(HERE, "build") if not extra else os.path.join(HERE, "build", os.path.basename(LIB) + ".d")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     log = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:
