@@ -19,6 +19,7 @@ SIGNATURES = {
     "dcl_check_device": (_i, []),
     "dcl_debug_flags": (_i, [_i]),
     "dcl_debug_trace": (_i, [_vp]),
+    "dcl_contrast_launches": (_i, [_i, _i]),
     "dcl_sample_classify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "dcl_host_sample_ranks": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
@@ -33,9 +34,11 @@ SIGNATURES = {
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
 }
 
-# kernels launched per call (kept next to the signatures; bench.py reports the total per step)
-FWD_LAUNCHES = 4   # sweep A, sweep B, sweep C, finalize
-BWD_LAUNCHES = 2   # backward, reduce_dF
+
+def contrast_launches(mode, backward):
+    """kernels one dcl_contrast_fwd / dcl_contrast_bwd call launches (bench.py reports the total per step)"""
+    return int(load().dcl_contrast_launches(int(mode), int(backward)))
+
 
 _lib = None
 

@@ -2,26 +2,37 @@
 // as tcgen05/TMEM tile sweeps; the N x N matrix only ever exists as 128x128 fp32 tiles in TMEM.
 //
 // Math, in raw dot-product units s_ij = f_i . f_j (a_ij = s_ij / T):
-//   sweep A : smax_i = max_j s_ij, S1 = sum_j (s_ij - c_i), S2 = sum_j (s_ij - c_i)^2   (c_i = |f_i|^2)
-//             -> kappa_i = 1 / max(sqrt(sum_j (s_ij - smax_i)^2), T*1e-12)   so   l_ij = (s_ij - smax_i) kappa_i
-//   sweep B : Den_i = sum_{den(i,j)} exp(l_ij),  Bt_i = sum_{den} exp(l_ij) * l_ij*log2(e)
-//             den = different label (pixel) | j != i (image)
-//   sweep C : over tiles that can hold positives only: P_i, sum_pos lp_ij, sum_pos 1/(E+Den), sum_pos l/(E+Den)
-//   finalize: per-row loss, Q_i, R_i and the per-row constants the backward consumes
-//   backward: G_ik = dS_ik + dS_ki recomputed per tile -> bf16 in TMEM -> dF_I += G_IJ F_J (TS-form MMA)
+//   l_ij = (s_ij - m_i) kappa_i,  m_i = max_j s_ij (detached),  kappa_i = 1 / max(|s_i - m_i|_2, T*1e-12)
+//   pixel: lp_ij = l_ij - log(e^{l_ij} + Den_i), Den_i = sum_{y_k != y_i} e^{l_ik};  image: lp_ij = l_ij - log sum_{k != i} e^{l_ik}
+//   loss = mean_i [ -(T/T_b) mean_{j in pos(i)} lp_ij ];  dS_ik = kappa_i (g_ik - l_ik R_i);  dF = (dS + dS^T) F
 //
-// Kernel shape (one persistent CTA per SM, 320 threads): warps 0..7 = two epilogue groups of four
-// warps (warp w owns TMEM lanes 32*(w%4)..+31, one thread per anchor row), warp 8 = TMA producer lane
-// + TMEM allocator, warp 9 = MMA issuer lane.  Shared-memory tile slots (4-deep ring) and TMEM
-// accumulator stages (2) are decoupled, so the L2->smem->MMA latency of a tile is hidden under the
-// epilogues of the tiles before it.
-//   sweeps  : a CTA owns a PAIR of row blocks (M = 256): every F_J tile fetched from L2 feeds two
-//             128x128 S tiles, one per epilogue group; TMEM = 2 stages x (2 x 128) columns.
-//   backward: a CTA owns one row block; the two groups alternate column tiles (S double-buffered,
-//             G written over S, dF accumulator in a third 128-column region).
-// Work = the flattened list of (row unit, column block) tiles cut into gridDim.x equal contiguous
-// ranges; a range that crosses a row-unit boundary flushes a deterministic partial ("segment")
-// instead of using atomics, so results are bit-reproducible.
+// Two forward pipelines share the kernels below:
+//   * pixel term ("v3", the hot path).  The row norm needs no N^2 pass:
+//         sum_k (s_ik - m)^2 = f_i^T Mc f_i + n (f_i.mu - m)^2,   Mc = centred Gram matrix (k_gram, k_rowstats)
+//     and the row max of a (near-)normalised embedding is its own diagonal c_i = |f_i|^2, so ONE fused sweep
+//     (SWEEP_F) evaluates E = e^{l} with the speculated m_i = c_i, accumulates Den_i and sum E s, and verifies the
+//     speculation (any s_ik > c_i (1 + 2^-8) flags the row; a tile whose Cauchy-Schwarz bound cannot exceed it
+//     skips the check).  Flagged row pairs are re-swept once with their exact maximum (list mode).  e^{l} on the
+//     row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a per-row economised Chebyshev polynomial of
+//     degree 2..4 in s, evaluated with packed FFMA2 - no MUFU in the sweep.
+//   * image term and the diagnostic legacy path: sweep A (max, sums), sweep B (Den), as in round 1.
+//   Both continue with sweep C (tiles that can hold positives), finalize, and the fused backward
+//         G_ik = dS_ik + dS_ki = rp_i(s_ik) + rp_k(s_ik)   on pairs of different classes,
+//     rp = q E(s) + p (a s + b) folded into one polynomial per row (k_bwd_prep), G written as bf16 over S in TMEM,
+//     dF_I += G F_J with A from TMEM.  Tiles whose label ranges overlap take the exact masked path.
+//
+// Kernel shape: one persistent CTA per SM, 352 threads: warps 0..7 = two epilogue groups of four warps (warp w owns
+// TMEM lanes 32*(w%4).., one thread per anchor row), warp 8 = TMA producer lane + TMEM allocator, warps 9 and 10 =
+// two MMA issuer lanes.  tcgen05.mma issue blocks its thread while the tensor pipe drains, and every mbarrier
+// round trip costs ~150-200 clocks, so a single issuer thread leaves the tensor pipe idle half of the time
+// (profiles/r01f_*): with two issuers one thread's waits overlap the other's MMAs.
+//   sweeps  : a CTA owns a PAIR of row blocks (M = 256): every F_J tile fetched from L2 feeds two 128x128 S tiles,
+//             one per epilogue group / issuer; TMEM = 2 stages x 2 groups x 128 columns.
+//   backward: a CTA owns one row block; issuer 0 produces S tiles (3 TMEM stages), issuer 1 the G.F_J products; the
+//             two epilogue groups alternate column tiles.
+// Work = the flattened list of (row unit, column block) tiles cut into gridDim.x equal contiguous ranges; a range
+// that crosses a row-unit boundary flushes a deterministic partial ("segment") instead of using atomics, so results
+// are bit-reproducible.
 #include <cfloat>
 #include <cuda_bf16.h>
 #include "dcl_common.cuh"
@@ -31,13 +42,14 @@ namespace dcl {
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;
 constexpr int kTmemCols = 512;
-// The SM's warp arbiter favours high warp ids: the two single-lane pipeline drivers get the highest
-// ids so they are never starved by the eight issue-bound epilogue warps (0..7).
 constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kMaxBlocks = 1024;   // column blocks whose label ranges are cached in shared memory
+constexpr int kIssuerWarp0 = 9;       // issuer g is warp 9 + g
+constexpr int kMaxBlocks = 1024;      // column blocks whose info is cached in shared memory
+constexpr float kSpecTol = 1.0f / 256.0f;   // speculation holds while no s_ik exceeds c_i (1 + tol)
+constexpr int kGramLd = 132;          // padded row length (floats) of the Gram kernels' shared tiles
+constexpr int kCoefPairFloats = 12;   // backward column coefficients of one column pair: 3 x float4
 
 // ---------------------------------------------------------------------------------------------
 // flattened-range partition of nU row units x nJ column blocks over G CTAs
@@ -59,58 +71,59 @@ struct Params {
     const uint8_t* tiles;    // [nJ] F-tiles
     const int32_t* y;        // [nJ*128]
     const float* sqnorm;     // [nJ*128]
-    int nJ, rb0, nI, nP, n_valid, mode;
+    int nJ, rb0, nI, nP, n_valid, mode, ctas;
     float T, Tb;
-    Part partS;              // sweeps A/B: units = pairs of row blocks
-    Part partD;              // backward:   units = row blocks
+    Part partS;              // sweeps: units = pairs of row blocks
+    Part partD;              // backward: units = row blocks
     int maxsegS, maxsegD;
     int splitc;              // sweep C: CTAs per row-block pair
+    // block info (all nJ column blocks)
+    int4* binfo;             // (ymin, ymax, nvalid, 0); (INT_MAX, -1, 0) when the block has no valid row
+    float2* bnorm;           // (max, min) of |f|^2 over the block's valid rows
+    // legacy sweeps A / B
     float4* pA;              // [nI][maxsegS][128] (max(s-c), S1, S2, -)
     float2* pB;              // [nI][maxsegS][128] (Den, Bt)
+    // v3 closed-form statistics
+    float* gram_part;        // [P][128*128] partial Gram matrices of (f - ref)
+    float* fsum_part;        // [P][128]
+    float* cmax_part;        // [P]
+    float* ref;              // [128] reference vector (mean of the first block)
+    float* Mc;               // [128*128] centred Gram
+    float* mu;               // [128]
+    float* scal;             // [0] cmax over all rows
+    int* iscal;              // [0] fwd poly degree pass 1, [1] degree pass 2, [2] flagged unit count, [3] bwd degree
+    int gramP;
+    float2* rowq;            // [nI*128] (f^T Mc f, f.mu)
+    float* rowc;             // [nI*128][8] (d0..d4 of E(s), threshold c(1+tol), m, L)
+    float4* pF;              // [nI][maxsegS][128] pass-1 partials (sum E, sum E s, max s, -)
+    float4* pF2;             // [ctas + nP + 2][2][128] pass-2 partials, slot = first_cta(u) + u + seg
+    int* unit_flag;          // [nP]
+    int* unit_list;          // [nP]
+    int list_mode;           // SWEEP_F pass 2: units come from unit_list[0 .. iscal[2])
+    // per-row state shared by sweep C / finalize
+    float4* rowS;            // [nI*128] (a, b, kappa, m)   t = a s + b = l log2(e)
+    float4* rowD;            // [nI*128] (Den, Bt = sum_den E t, L, 0)
     float4* pC;              // [nI][splitc][128] (P, sum lp | sum l, sum inv, sum inv*l)
     float* pD;               // [nI][maxsegD][128][128] dF partials
     float4* colA;            // [nJ*128] (a, b, p, q)
-    float4* colB;            // [nJ*128] (wn, Den, y bits, 0)
+    float4* colB;            // [nJ*128] (wn, Den, y bits, L)
+    float* coefR;            // [nJ*128][8] backward row polynomial rp (r0..r4, 0, 0, 0)
+    float* coefP;            // [nJ*64][12] the same, pair-interleaved for the column side
     float* rowloss;          // [nJ*128]
     float* blockloss;        // [nI]
     float* loss_sum;
-    unsigned int* ticket;    // finalize's last-block counter (zeroed by sweep A)
-    long long* trace;        // diagnostics only: per-role clock64 stamps of CTA 0 (dcl_debug_trace)
-    int debug;               // diagnostics only (dcl_debug_flags): 1 skip epilogue math, 2 skip S MMAs, 4 skip dF MMAs
+    unsigned int* ticket;    // last-block counters: [0] finalize, [1] k_check
+    long long* trace;        // diagnostics only (dcl_debug_trace)
+    int debug;               // diagnostics only (dcl_debug_flags)
 };
 
+// ---------------------------------------------------------------------------------------------
+// small math helpers
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^t for t in [-1.4427, 0] (l = t*ln2 lies in [-1, 0]: the rows are unit-normalised, loss.py:366) on the
-// FMA pipe: minimax-fitted polynomials, no range reduction needed.  The MUFU pipe (16 ex2/clk/SM) is
-// the epilogues' bottleneck, so a fixed 3-of-8 share of the exponentials goes here instead.
-// Max relative error 1.6e-5 (degree 4, forward sums) / 3.2e-4 (degree 3, backward).
-__device__ __forceinline__ float ex2_poly4(float t) {
-    float p = 0.005771667696535587f;
-    p = fmaf(p, t, 0.05083702877163887f);
-    p = fmaf(p, t, 0.23775413632392883f);
-    p = fmaf(p, t, 0.6926645040512085f);
-    return fmaf(p, t, 0.9999837875366211f);
-}
-__device__ __forceinline__ float ex2_poly3(float t) {
-    float p = 0.033237408846616745f;
-    p = fmaf(p, t, 0.22061625123023987f);
-    p = fmaf(p, t, 0.6871119737625122f);
-    return fmaf(p, t, 0.9996766448020935f);
-}
-// j is a compile-time (unrolled) column index: DCL_POLY_* of every 8 columns take the polynomial
-#ifndef DCL_POLY_FWD
-#define DCL_POLY_FWD 3
-#endif
-#ifndef DCL_POLY_BWD
-#define DCL_POLY_BWD 3
-#endif
-#define DCL_EX2_FWD(t, j) ((((j) & 7) < DCL_POLY_FWD) ? ex2_poly4(t) : ex2f(t))
-#define DCL_EX2_BWD(t, j) ((((j) & 7) < DCL_POLY_BWD) ? ex2_poly3(t) : ex2f(t))
-
 __device__ __forceinline__ float lg2f(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -120,6 +133,36 @@ __device__ __forceinline__ float rcpf(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// packed fp32 pairs (FFMA2 / FADD2): one issue slot for two lanes of work
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+    float lo, hi;
+    unpack2(v, lo, hi);
+    return lo + hi;
 }
 
 // tcgen05.wait::ld with the destination registers threaded through as in/out operands, so the
@@ -160,111 +203,366 @@ __device__ __forceinline__ void for_each_chunk(uint32_t taddr, Fn&& fn) {
     }
 }
 
-// diagnostics: stamp (role, tile, event) for CTA 0's first 32 tiles
+// diagnostics: stamp (role, tile, event) for CTA 0's first 32 tiles; roles: 0 producer, 1/2 issuers, 3/4 epilogue groups
 __device__ __forceinline__ void trace_stamp(const Params& p, int role, int it, int ev) {
-    if (p.trace && blockIdx.x == 0 && it < 32) p.trace[(role * 32 + it) * 4 + ev] = clock64();   // caller enables it around ONE launch
+    if (p.trace && blockIdx.x == 0 && it < 32) p.trace[(role * 32 + it) * 8 + ev] = clock64();
 }
 
 __device__ __forceinline__ bool ranges_overlap(int2 a, int2 b) { return a.x <= b.y && b.x <= a.y; }
 
-// Label range (min,max over valid rows; (INT_MAX,-1) if none) and valid-row count of every column
-// block, computed by the whole CTA into shared memory before the roles split.
-__device__ __forceinline__ void compute_block_info(const int32_t* __restrict__ y, int nJ, int2* sRange,
-                                                   int* sNv) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int J = warp; J < nJ; J += nwarps) {
-        const int4 v = __ldg(reinterpret_cast<const int4*>(y + static_cast<size_t>(J) * 128) + lane);
-        const int e[4] = {v.x, v.y, v.z, v.w};
-        int lo = INT_MAX, hi = -1, n = 0;
+// =============================================================================================
+// Per-row exponential polynomial.  For l = kappa (s - m) in [-L, 0]:
+//   e^l = e^{-r} e^z,  z = l + r in [-r, r],  r = L/2,   e^z ~ truncated Chebyshev series (modified Bessel I_k(r)),
+// re-expanded in s.  Truncation error ~ 2 I_{deg+1}(r): deg 2 for L <= 1/8 (1.1e-5), 3 for L <= 1/2 (2e-5), else 4
+// (1.6e-5 at L = 1).
+// =============================================================================================
+__device__ __forceinline__ int poly_degree_for(double L) { return L <= 0.125 ? 2 : (L <= 0.5 ? 3 : 4); }
+
+__device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, double (&d)[5]) {
+    double r = 0.5 * L;
+    if (r < 1e-8) r = 1e-8;
+    // a_k = (2 - [k == 0]) I_k(r)
+    double a[5];
+    const double h = 0.5 * r, h2 = h * h;
+    double hk = 1.0, kfact = 1.0;
+    for (int k = 0; k <= 4; ++k) {
+        if (k > 0) { hk *= h; kfact *= k; }
+        double term = hk / kfact, sum = term;      // j = 0 term: h^k / k!
+        for (int j = 1; j <= 8; ++j) {
+            term *= h2 / (static_cast<double>(j) * (j + k));
+            sum += term;
+        }
+        a[k] = (k == 0 ? 1.0 : 2.0) * sum;
+    }
+    // Chebyshev -> monomials in x = z / r
+    double cx[5] = {0, 0, 0, 0, 0};
+    cx[0] = a[0] - a[2];
+    cx[1] = a[1];
+    cx[2] = 2.0 * a[2];
+    if (deg >= 3) { cx[1] -= 3.0 * a[3]; cx[3] = 4.0 * a[3]; }
+    if (deg >= 4) { cx[0] += a[4]; cx[2] -= 8.0 * a[4]; cx[4] = 8.0 * a[4]; }
+    const double er = exp(-r);
+    double cz[5], rn = 1.0;
+    for (int n = 0; n <= 4; ++n) { cz[n] = (n <= deg) ? er * cx[n] / rn : 0.0; rn *= r; }
+    // z = al s + be
+    const double al = kappa, be = r - kappa * m;
+    const double binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+    double alp[5], bep[5];
+    alp[0] = bep[0] = 1.0;
+    for (int n = 1; n <= 4; ++n) { alp[n] = alp[n - 1] * al; bep[n] = bep[n - 1] * be; }
+    for (int j = 0; j <= 4; ++j) {
+        double s = 0.0;
+        for (int n = j; n <= deg; ++n) s += cz[n] * binom[n][j] * alp[j] * bep[n - j];
+        d[j] = s;
+    }
+}
+
+// kappa and logit-range bound of a row from its closed-form norm.  A row whose every s_ik equals the maximum to
+// 1e-6 relative (all embeddings identical) has l = 0 in the reference (0 / eps); it is mapped to kappa = 0.
+__device__ __forceinline__ void row_scale(double qf, double fm, double m, double c, double cmax, int n_valid, float T,
+                                          double& kappa, double& L) {
+    const double e = fm - m;
+    double nrm2 = qf + static_cast<double>(n_valid) * e * e;
+    if (!(nrm2 > 0.0)) nrm2 = 0.0;
+    const double nrm = sqrt(nrm2);
+    if (nrm <= 1e-6 * fabs(m) || nrm <= static_cast<double>(T) * 1e-12) {
+        kappa = 0.0;
+        L = 0.0;
+        return;
+    }
+    kappa = 1.0 / nrm;
+    // s_ik >= -sqrt(c_i c_k) (Cauchy-Schwarz) and |l_i|_2 = 1
+    L = fmin(1.0, kappa * (m + sqrt(c * cmax)) * (1.0 + 1e-6));
+    if (L < 0.0) L = 0.0;
+}
+
+// =============================================================================================
+// Closed-form statistics: block info, Gram matrix of (f - ref), per-row quadratic forms
+// =============================================================================================
+// register-tiled outer-product accumulation  acc[u][v] += sum_k X[k][rm(ty,u)] Y[k][rm(tx,v)]
+// with rm(t, u) = (u < 4 ? 4t + u : 64 + 4t + u - 4)  (conflict-free float4 reads)
+__device__ __forceinline__ int rmap(int t, int u) { return u < 4 ? 4 * t + u : 64 + 4 * t + (u - 4); }
+__device__ __forceinline__ void outer_accumulate(const float* __restrict__ X, const float* __restrict__ Y, int ty, int tx,
+                                                 float (&acc)[8][8]) {
+#pragma unroll 4
+    for (int k = 0; k < 128; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(X + k * kGramLd + 4 * ty);
+        const float4 a1 = *reinterpret_cast<const float4*>(X + k * kGramLd + 64 + 4 * ty);
+        const float4 b0 = *reinterpret_cast<const float4*>(Y + k * kGramLd + 4 * tx);
+        const float4 b1 = *reinterpret_cast<const float4*>(Y + k * kGramLd + 64 + 4 * tx);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (e[u] >= 0) { lo = min(lo, e[u]); hi = max(hi, e[u]); ++n; }
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+}
+
+// F-tile image (global) -> fp32 shared tile; kTranspose: dst[d][r] else dst[r][d]; rows with y < 0 become zero;
+// `sub` (may be null) is subtracted from valid rows
+template <bool kTranspose>
+__device__ __forceinline__ void load_tile_f32(const uint8_t* __restrict__ tile, const int* __restrict__ yrow,
+                                              const float* __restrict__ sub, float* __restrict__ dst) {
+    for (int q = threadIdx.x; q < 2048; q += blockDim.x) {
+        const int hpanel = q >> 10, r = (q & 1023) >> 3, cs = q & 7;
+        const int c = cs ^ (r & 7);
+        const int d0 = hpanel * 64 + c * 8;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tile) + q);
+        const bool valid = yrow[r] >= 0;
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+            if (sub) { lo -= sub[d0 + 2 * e]; hi -= sub[d0 + 2 * e + 1]; }
+            if (!valid) { lo = 0.f; hi = 0.f; }
+            if (kTranspose) {
+                dst[(d0 + 2 * e) * kGramLd + r] = lo;
+                dst[(d0 + 2 * e + 1) * kGramLd + r] = hi;
+            } else {
+                dst[r * kGramLd + d0 + 2 * e] = lo;
+                dst[r * kGramLd + d0 + 2 * e + 1] = hi;
+            }
+        }
+    }
+}
+
+// (ymin, ymax, nvalid) and (cmax, cmin) of one 128-row block; threads 0..127 hold one row each, the result is valid
+// in thread 0 after the second barrier.  Must be called by all threads of the CTA (it uses __syncthreads).
+struct BlockStat {
+    int lo, hi, n;
+    float cx, cn;
+};
+__device__ __forceinline__ BlockStat block_stat(int yv, float c, bool participates, int* si, float* sf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int lo = yv >= 0 ? yv : INT_MAX, hi = yv >= 0 ? yv : -1, n = yv >= 0;
+    float cx = yv >= 0 ? c : 0.f, cn = yv >= 0 ? c : FLT_MAX;
+    if (participates) {
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             n += __shfl_xor_sync(0xffffffffu, n, o);
+            cx = fmaxf(cx, __shfl_xor_sync(0xffffffffu, cx, o));
+            cn = fminf(cn, __shfl_xor_sync(0xffffffffu, cn, o));
         }
-        if (lane == 0) { sRange[J] = make_int2(lo, hi); sNv[J] = n; }
+        if (lane == 0) { si[warp] = lo; si[4 + warp] = hi; si[8 + warp] = n; sf[warp] = cx; sf[4 + warp] = cn; }
+    }
+    __syncthreads();
+    BlockStat b;
+    b.lo = min(min(si[0], si[1]), min(si[2], si[3]));
+    b.hi = max(max(si[4], si[5]), max(si[6], si[7]));
+    b.n = si[8] + si[9] + si[10] + si[11];
+    b.cx = fmaxf(fmaxf(sf[0], sf[1]), fmaxf(sf[2], sf[3]));
+    b.cn = fminf(fminf(sf[4], sf[5]), fminf(sf[6], sf[7]));
+    __syncthreads();
+    return b;
+}
+
+// one CTA per strided set of column blocks: block info for its blocks + partial Gram of (f - ref)
+__global__ void __launch_bounds__(256) k_gram(const Params p) {
+    extern __shared__ float gsm[];
+    float* G = gsm;                         // [128][kGramLd]
+    __shared__ float sref[128];
+    __shared__ int sy[128];
+    __shared__ int si[12];
+    __shared__ float sf[8];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    // reference vector = mean of block 0's valid rows (every CTA derives the same one)
+    if (tid < 128) sy[tid] = p.y[tid];
+    __syncthreads();
+    load_tile_f32<false>(p.tiles, sy, nullptr, G);
+    __syncthreads();
+    if (tid < 128) {
+        float s = 0.f;
+        int nv = 0;
+        for (int r = 0; r < 128; ++r) { s += G[r * kGramLd + tid]; nv += sy[r] >= 0; }
+        sref[tid] = nv > 0 ? s / nv : 0.f;
+        if (blockIdx.x == 0) p.ref[tid] = sref[tid];
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+    float fs = 0.f, cmx = 0.f;
+    for (int J = blockIdx.x; J < p.nJ; J += gridDim.x) {
+        __syncthreads();                     // readers of sy / G from the previous block are done
+        float c = 0.f;
+        int yv = -1;
+        if (tid < 128) {
+            yv = p.y[J * 128 + tid];
+            sy[tid] = yv;
+            c = p.sqnorm[J * 128 + tid];
+        }
+        const BlockStat b = block_stat(yv, c, tid < 128, si, sf);
+        if (tid == 0) {
+            p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
+            p.bnorm[J] = make_float2(b.cx, b.cn);
+            cmx = fmaxf(cmx, b.cx);
+        }
+        load_tile_f32<false>(p.tiles + static_cast<size_t>(J) * kTileBytes, sy, sref, G);
+        __syncthreads();
+        outer_accumulate(G, G, ty, tx, acc);
+        if (tid < 128) {
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r) s += G[r * kGramLd + tid];
+            fs += s;
+        }
+    }
+    float* gp = p.gram_part + static_cast<size_t>(blockIdx.x) * 128 * 128;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int a = rmap(ty, u);
+        *reinterpret_cast<float4*>(gp + a * 128 + 4 * tx) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        *reinterpret_cast<float4*>(gp + a * 128 + 64 + 4 * tx) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+    }
+    if (tid < 128) p.fsum_part[blockIdx.x * 128 + tid] = fs;
+    if (tid == 0) p.cmax_part[blockIdx.x] = cmx;
+}
+
+// Mc = sum_p Gram_p - n delta delta^T,  mu = ref + delta,  delta = sum_p fsum_p / n   (fp64 combination, fixed order)
+__global__ void __launch_bounds__(256) k_gram_reduce(const Params p) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int a = e >> 7, b = e & 127;
+    double g = 0.0, da = 0.0, db = 0.0;
+    for (int q = 0; q < p.gramP; ++q) {
+        g += p.gram_part[static_cast<size_t>(q) * 16384 + e];
+        da += p.fsum_part[q * 128 + a];
+        db += p.fsum_part[q * 128 + b];
+    }
+    const double n = p.n_valid;
+    p.Mc[e] = static_cast<float>(g - da * db / n);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 128) {
+            double d = 0.0;
+            for (int q = 0; q < p.gramP; ++q) d += p.fsum_part[q * 128 + threadIdx.x];
+            p.mu[threadIdx.x] = static_cast<float>(p.ref[threadIdx.x] + d / n);
+        }
+        if (threadIdx.x == 0) {
+            float cm = 0.f;
+            for (int q = 0; q < p.gramP; ++q) cm = fmaxf(cm, p.cmax_part[q]);
+            p.scal[0] = cm;
+            p.iscal[0] = 2;
+            p.iscal[1] = 2;
+            p.iscal[2] = 0;
+            p.ticket[0] = 0u;
+            p.ticket[1] = 0u;
+        }
     }
 }
 
-// Row constants derived from sweep A partials: t_ij = fma(s_ij, a, b) = l_ij * log2(e).
-struct RowA {
-    float a, b, kappa, smax;
-};
-__device__ __forceinline__ RowA combine_A(const Params& p, int I, int r) {
-    const int ns = p.partS.nseg(I >> 1);
-    float mx = -FLT_MAX;
-    double S1 = 0.0, S2 = 0.0;
-    for (int s = 0; s < ns; ++s) {
-        float4 v = p.pA[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
-        mx = fmaxf(mx, v.x);
-        S1 += v.y;
-        S2 += v.z;
+// writes one row's forward polynomial block: (d0..d4, threshold, m, L)
+__device__ __forceinline__ int write_rowc(const Params& p, int lrow, double kappa, double m, double L, float thr) {
+    double d[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
+    int deg = 2;
+    if (kappa > 0.0) {
+        deg = poly_degree_for(L);
+        exp_poly_in_s(kappa, m, L, deg, d);
     }
-    const float c = p.sqnorm[(p.rb0 + I) * 128 + r];
-    const double d = mx;                                         // smax - c
-    double S2s = S2 - 2.0 * d * S1 + static_cast<double>(p.n_valid) * d * d;
-    if (!(S2s > 0.0)) S2s = 0.0;
-    const float rT = fmaxf(static_cast<float>(sqrt(S2s)), p.T * 1e-12f);   // F.normalize eps, loss.py:366
-    RowA o;
-    o.kappa = 1.0f / rT;
-    o.smax = c + mx;
-    o.a = o.kappa * kLog2e;
-    o.b = -o.smax * o.a;
-    return o;
-}
-__device__ __forceinline__ float2 combine_B(const Params& p, int I, int r) {
-    const int ns = p.partS.nseg(I >> 1);
-    float den = 0.f, bt = 0.f;
-    for (int s = 0; s < ns; ++s) {
-        float2 v = p.pB[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
-        den += v.x;
-        bt += v.y;
-    }
-    return make_float2(den, bt);
+    float4* out = reinterpret_cast<float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
+    out[0] = make_float4(static_cast<float>(d[0]), static_cast<float>(d[1]), static_cast<float>(d[2]), static_cast<float>(d[3]));
+    out[1] = make_float4(static_cast<float>(d[4]), thr, static_cast<float>(m), static_cast<float>(L));
+    return deg;
 }
 
-// ---------------------------------------------------------------------------------------------
+// per local row block: qf_i = f_i^T Mc f_i, fm_i = f_i . mu, then kappa / polynomial with the speculated m_i = c_i
+__global__ void __launch_bounds__(256) k_rowstats(const Params p) {
+    extern __shared__ float gsm[];
+    float* X = gsm;                          // F^T : [d][i]
+    float* Y = gsm + 128 * kGramLd;          // Mc  : [d][e]
+    __shared__ int sy[128];
+    __shared__ float smu[128];
+    __shared__ float sqf[128];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int I = blockIdx.x, gb = p.rb0 + I;
+    if (tid < 128) { sy[tid] = p.y[gb * 128 + tid]; smu[tid] = p.mu[tid]; }
+    for (int q = tid; q < 128 * 32; q += 256) {
+        const int d = q >> 5, c4 = q & 31;
+        *reinterpret_cast<float4*>(Y + d * kGramLd + 4 * c4) = __ldg(reinterpret_cast<const float4*>(p.Mc) + q);
+    }
+    __syncthreads();
+    load_tile_f32<true>(p.tiles + static_cast<size_t>(gb) * kTileBytes, sy, nullptr, X);
+    __syncthreads();
+    float acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+    outer_accumulate(X, Y, ty, tx, acc);      // acc[u][v] = (F Mc)[i = rmap(ty,u)][e = rmap(tx,v)]
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int i = rmap(ty, u);
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) s = fmaf(acc[u][v], X[rmap(tx, v) * kGramLd + i], s);
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tx == 0) sqf[i] = s;
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int lrow = I * 128 + tid, gi = gb * 128 + tid;
+        float fm = 0.f;
+        for (int d = 0; d < 128; ++d) fm = fmaf(X[d * kGramLd + tid], smu[d], fm);
+        p.rowq[lrow] = make_float2(sqf[tid], fm);
+        int deg = 2;
+        if (sy[tid] >= 0) {
+            const double c = p.sqnorm[gi];
+            double kappa, L;
+            row_scale(sqf[tid], fm, c, c, p.scal[0], p.n_valid, p.T, kappa, L);
+            deg = write_rowc(p, lrow, kappa, c, L, static_cast<float>(c) * (1.0f + kSpecTol));
+            p.rowS[lrow] = make_float4(static_cast<float>(kappa * kLog2e), static_cast<float>(-c * kappa * kLog2e),
+                                       static_cast<float>(kappa), static_cast<float>(c));
+        } else {
+            float4* out = reinterpret_cast<float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
+            out[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            out[1] = make_float4(0.f, FLT_MAX, 0.f, 0.f);
+            p.rowS[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (deg > 2) atomicMax(&p.iscal[0], deg);
+    }
+    if (tid == 0 && (I & 1) == 0) p.unit_flag[I >> 1] = 0;
+}
+
+// =============================================================================================
 // shared-memory carve-up (bytes from a 1024-aligned base)
+// =============================================================================================
 struct SmemSweep {
     static constexpr int kI = 0;                          // 2 row-block tiles
     static constexpr int kJ = 2 * kTileBytes;             // 4 slots
-    static constexpr int kY = 6 * kTileBytes;             // 8 x 512 B labels of column blocks
-    static constexpr int kRange = kY + 8 * 512;           // int2[kMaxBlocks]
-    static constexpr int kNv = kRange + 8 * kMaxBlocks;   // int[kMaxBlocks]
-    static constexpr int kBar = kNv + 4 * kMaxBlocks;     // full[4] empty[4] tfull[2] tempty[2] ifull iempty yfull[8]
+    static constexpr int kInfo = 6 * kTileBytes;          // int4[kMaxBlocks]
+    static constexpr int kNorm = kInfo + 16 * kMaxBlocks; // float2[kMaxBlocks]
+    static constexpr int kBar = kNorm + 8 * kMaxBlocks;   // full[4] empty[4] tfull[4] tempty[4] ifull iempty
     static constexpr int kTmem = kBar + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;      // + alignment slack
 };
 struct SmemBwd {
-    static constexpr int kSlots = 5;                      // F_J tile + its column constants
+    static constexpr int kSlots = 5;                      // F_J tile + its column polynomial block
     static constexpr int kStages = 3;                     // TMEM S/G stages (G aliases its S)
+    static constexpr int kCoefBytes = 64 * kCoefPairFloats * 4;   // 3072
     static constexpr int kI = 0;
     static constexpr int kJ = kTileBytes;
-    static constexpr int kCA = (1 + kSlots) * kTileBytes; // kSlots x 2 KiB colA
-    static constexpr int kCB = kCA + kSlots * 2048;       // kSlots x 2 KiB colB
-    static constexpr int kRange = kCB + kSlots * 2048;
-    static constexpr int kBar = kRange + 8 * kMaxBlocks;  // full[5] empty[5] tfull[3] pfull[3] dfull dempty ifull iempty
+    static constexpr int kCP = (1 + kSlots) * kTileBytes;
+    static constexpr int kRange = kCP + kSlots * kCoefBytes;      // int2[kMaxBlocks]
+    static constexpr int kBar = kRange + 8 * kMaxBlocks;  // full[5] empty[5] tfull[3] pfull[3] sfree[3] dfull dempty ifull iempty
     static constexpr int kTmem = kBar + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;
 };
 
-enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2 };
+enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2, SWEEP_F = 3 };
 
-// Tile sequence of one CTA: (row unit U, column block J).  Flat mode: contiguous range of the
-// flattened U-major list.  Relevant mode (sweep C): CTA = (pair, split s) walks the column blocks
-// whose label range overlaps either row block of the pair and keeps every splitc-th one.  All warp
-// roles run an identical copy of this iterator, which keeps their barrier phases in step.
+// Tile sequence of one CTA: (row unit U, column block J).  Flat mode: contiguous range of the flattened U-major
+// list (in list mode the units are positions in unit_list).  Relevant mode (sweep C): CTA = (pair, split s) walks
+// the column blocks whose label range overlaps either row block of the pair and keeps every splitc-th one.  All
+// warp roles run an identical copy of this iterator, which keeps their barrier phases in step.
 template <bool kRelevantOnly>
 struct TileIter {
     int left;                 // flat mode: tiles remaining
     int nJ, U, J, r, s, splitc;
     int2 r0, r1;
-    const int2* rng;
-    __device__ TileIter(const Params& p, const Part& part, const int2* sRange) {
+    const int4* info;
+    __device__ TileIter(const Params& p, const Part& part, const int4* sInfo) {
         nJ = p.nJ;
-        rng = sRange;
+        info = sInfo;
         left = 0;
         U = J = r = s = 0;
         splitc = 1;
@@ -273,9 +571,13 @@ struct TileIter {
             U = blockIdx.x / p.splitc;
             s = blockIdx.x % p.splitc;
             splitc = p.splitc;
-            r0 = sRange[p.rb0 + 2 * U];
-            if (2 * U + 1 < p.nI) r1 = sRange[p.rb0 + 2 * U + 1];
-        } else {
+            const int4 a = sInfo[p.rb0 + 2 * U];
+            r0 = make_int2(a.x, a.y);
+            if (2 * U + 1 < p.nI) {
+                const int4 b = sInfo[p.rb0 + 2 * U + 1];
+                r1 = make_int2(b.x, b.y);
+            }
+        } else if (part.total > 0) {
             const long long t0 = part.begin(blockIdx.x), t1 = part.begin(blockIdx.x + 1);
             left = static_cast<int>(t1 - t0);
             U = static_cast<int>(t0 / nJ);            // the only divisions: once per CTA and role
@@ -286,7 +588,8 @@ struct TileIter {
         if (kRelevantOnly) {
             while (J < nJ) {
                 const int j = J++;
-                const int2 rj = rng[j];
+                const int4 q = info[j];
+                const int2 rj = make_int2(q.x, q.y);
                 if (ranges_overlap(r0, rj) || ranges_overlap(r1, rj)) {
                     if ((r++ % splitc) == s) {
                         oU = U;
@@ -309,8 +612,25 @@ struct TileIter {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// SWEEP_F fast-tile body: E = poly(s) for 32 columns (16 packed pairs); accE += E, accS += E s; optional row max
+template <int kDeg, bool kCheck>
+__device__ __forceinline__ void fsweep_chunk(const uint32_t (&v)[32], const f32x2 (&dd)[5], f32x2 (&accE)[4],
+                                             f32x2 (&accS)[4], float& mx) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
+        f32x2 e = ffma2(dd[kDeg], s, dd[kDeg - 1]);
+#pragma unroll
+        for (int d = kDeg - 2; d >= 0; --d) e = ffma2(e, s, dd[d]);
+        accE[j & 3] = fadd2(accE[j & 3], e);
+        accS[j & 3] = ffma2(e, s, accS[j & 3]);
+        if (kCheck) mx = fmaxf(mx, fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+    }
+}
+
 // =============================================================================================
-// Sweeps A / B / C
+// Sweeps A / B / C / F
 // =============================================================================================
 template <int kSweep, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
@@ -319,54 +639,58 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sI = base + SmemSweep::kI;
     const uint32_t sJ = base + SmemSweep::kJ;
-    const uint32_t sY = base + SmemSweep::kY;
-    const int32_t* sYg = reinterpret_cast<const int32_t*>(gen + SmemSweep::kY);
-    int2* sRange = reinterpret_cast<int2*>(gen + SmemSweep::kRange);
-    int* sNv = reinterpret_cast<int*>(gen + SmemSweep::kNv);
+    int4* sInfo = reinterpret_cast<int4*>(gen + SmemSweep::kInfo);
+    float2* sNorm = reinterpret_cast<float2*>(gen + SmemSweep::kNorm);
     const uint32_t bar = base + SmemSweep::kBar;
     // tfull / tempty are per (stage, group): index st * 2 + g
     const uint32_t b_full = bar, b_empty = bar + 32, b_tfull = bar + 64, b_tempty = bar + 96,
-                   b_ifull = bar + 128, b_iempty = bar + 136, b_yfull = bar + 144;
+                   b_ifull = bar + 128, b_iempty = bar + 136;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemSweep::kTmem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kProducerWarp) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
-    if (threadIdx.x == kMmaWarp * 32) {
+    if (threadIdx.x == kIssuerWarp0 * 32) {
         for (int s = 0; s < 4; ++s) {
             mbar_init(b_full + 8 * s, 1);
-            mbar_init(b_empty + 8 * s, 1);      // MMA commit
-        }
-        for (int s = 0; s < 4; ++s) {
+            mbar_init(b_empty + 8 * s, 2);      // one commit per issuer
             mbar_init(b_tfull + 8 * s, 1);
             mbar_init(b_tempty + 8 * s, 4);     // the 4 warps of one epilogue group
         }
         mbar_init(b_ifull, 1);
-        mbar_init(b_iempty, 1);
-        // Labels of a column block ride their own 8-deep ring + barriers: an epilogue warp may lag
-        // the producer by more than one phase of a 4-deep tile slot (1-bit parity would alias),
-        // but never by 8 tiles (slot it&7 is refilled only after MMA(it+4), i.e. epilogue(it+2)).
-        for (int s = 0; s < 8; ++s) mbar_init(b_yfull + 8 * s, 1);
+        mbar_init(b_iempty, 2);
         mbar_fence_init();
     }
-    if (kSweep == SWEEP_A && blockIdx.x == 0 && threadIdx.x == 0) *p.ticket = 0u;
-    compute_block_info(p.y, p.nJ, sRange, sNv);
+    for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
+        sInfo[j] = p.binfo[j];
+        sNorm[j] = p.bnorm[j];
+    }
+    // list mode (SWEEP_F pass 2): the unit count lives in device memory
+    const bool list_mode = (kSweep == SWEEP_F) && p.list_mode;
+    Part part = p.partS;
+    if (list_mode) {
+        part.total = static_cast<long long>(p.iscal[2]) * p.nJ;
+        part.G = gridDim.x;
+    }
+    const int deg = (kSweep == SWEEP_F) ? (list_mode ? max(p.iscal[0], p.iscal[1]) : p.iscal[0]) : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    auto unit_of = [&](int U) { return list_mode ? p.unit_list[U] : U; };
 
     if (warp == kProducerWarp) {
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer
-            TileIter<kSweep == SWEEP_C> iter(p, p.partS, sRange);
+            TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
             int U, J, curU = -1, it = 0, seg = 0;
             bool last;
             while (iter.next(U, J, last)) {
                 if (U != curU) {
-                    const bool two = 2 * U + 1 < p.nI;
+                    const int Ua = unit_of(U);
+                    const bool two = 2 * Ua + 1 < p.nI;
                     mbar_wait(b_iempty, (seg & 1) ^ 1);
                     mbar_arrive_expect_tx(b_ifull, two ? 2 * kTileBytes : kTileBytes);
-                    tma_bulk_g2s(sI, p.tiles + static_cast<size_t>(p.rb0 + 2 * U) * kTileBytes,
+                    tma_bulk_g2s(sI, p.tiles + static_cast<size_t>(p.rb0 + 2 * Ua) * kTileBytes,
                                  two ? 2 * kTileBytes : kTileBytes, b_ifull);   // the pair is contiguous
                     curU = U;
                     ++seg;
@@ -378,53 +702,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes);
                 tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(J) * kTileBytes,
                              kTileBytes, b_full + 8 * slot);
-                mbar_arrive_expect_tx(b_yfull + 8 * (it & 7), 512);
-                tma_bulk_g2s(sY + (it & 7) * 512, p.y + static_cast<size_t>(J) * 128, 512,
-                             b_yfull + 8 * (it & 7));
                 ++it;
             }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp >= kIssuerWarp0) {
         if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
-            TileIter<kSweep == SWEEP_C> iter(p, p.partS, sRange);
+            // ------------------------------------------------------------------ MMA issuer of group g
+            const int g = warp - kIssuerWarp0;
+            TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
             const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+            // descriptors are built once; a slot only shifts the 16-byte-granular start address
+            uint64_t dI[8], dJ0[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dI[k] = ftile_desc_kmajor(sI + g * kTileBytes, k);
+                dJ0[k] = ftile_desc_kmajor(sJ, k);
+            }
             int U, J, curU = -1, it = 0, seg = 0;
-            bool last, two = false;
+            bool last, have = false;
             while (iter.next(U, J, last)) {
                 if (U != curU) {
                     mbar_wait(b_ifull, seg & 1);
-                    two = 2 * U + 1 < p.nI;
+                    have = 2 * unit_of(U) + g < p.nI;
                     curU = U;
                     ++seg;
                 }
                 const int slot = it & 3, st = it & 1;
-                trace_stamp(p, 1, it, 0);
+                trace_stamp(p, 1 + g, it, 0);
                 mbar_wait(b_full + 8 * slot, (it >> 2) & 1);
-                trace_stamp(p, 1, it, 1);
-                const uint32_t par_e = ((it >> 1) & 1) ^ 1;
-                mbar_wait(b_tempty + 8 * (st * 2), par_e);
-                trace_stamp(p, 1, it, 2);
+                trace_stamp(p, 1 + g, it, 1);
+                mbar_wait(b_tempty + 8 * (st * 2 + g), ((it >> 1) & 1) ^ 1);
+                trace_stamp(p, 1 + g, it, 2);
                 tc_fence_after();
-                if (!(p.debug & 2)) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_ss(tmem + st * 256, ftile_desc_kmajor(sI, k),
-                            ftile_desc_kmajor(sJ + slot * kTileBytes, k), idesc, k > 0);
-                }
-                tc_commit(b_tfull + 8 * (st * 2));            // group 0 can start while group 1's tile runs
-                mbar_wait(b_tempty + 8 * (st * 2 + 1), par_e);
-                tc_fence_after();
-                if (two && !(p.debug & 2)) {
+                const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
+                if (have && !(p.debug & 2)) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_ss(tmem + st * 256 + 128, ftile_desc_kmajor(sI + kTileBytes, k),
-                                ftile_desc_kmajor(sJ + slot * kTileBytes, k), idesc, k > 0);
+                        umma_ss(tmem + (st * 2 + g) * 128, dI[k], dJ0[k] + soff, idesc, k > 0);
                 }
+                tc_commit(b_tfull + 8 * (st * 2 + g));
                 tc_commit(b_empty + 8 * slot);
-                tc_commit(b_tfull + 8 * (st * 2 + 1));
                 if (kSweep != SWEEP_C && last) tc_commit(b_iempty);
-                trace_stamp(p, 1, it, 3);
+                trace_stamp(p, 1 + g, it, 3);
                 ++it;
             }
         }
@@ -434,34 +753,49 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         const int q = warp & 3;
         const int r = q * 32 + lane;                       // row inside the block == TMEM lane
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        TileIter<kSweep == SWEEP_C> iter(p, p.partS, sRange);
+        TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
         int U, J, curU = -1, it = 0;
         bool last, valid = false;
         float acc0[4], acc1[4], acc2[4], acc3[4];
-        float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f;
-        int yi = -1, gi = -1, Iloc = 0;
+        f32x2 accE[4], accS[4], dd[5];
+        float dsc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f, mx = -FLT_MAX, chk_lim = 0.f;
+        int yi = -1, gi = -1, Iloc = 0, lrow = 0;
         int2 rI = make_int2(INT_MAX, -1);
+#pragma unroll
+        for (int d = 0; d < 5; ++d) dd[d] = 0ull;
 
         auto reset = [&]() {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 acc0[u] = (kSweep == SWEEP_A) ? -FLT_MAX : 0.f;
                 acc1[u] = acc2[u] = acc3[u] = 0.f;
+                accE[u] = accS[u] = 0ull;
             }
+            mx = -FLT_MAX;
         };
         auto flush = [&]() {
             if (!valid) return;
+            const int seg = blockIdx.x - part.first_cta(curU);
             if (kSweep == SWEEP_A) {
-                const int seg = blockIdx.x - p.partS.first_cta(curU);
-                float mx = fmaxf(fmaxf(acc0[0], acc0[1]), fmaxf(acc0[2], acc0[3]));
+                float m4 = fmaxf(fmaxf(acc0[0], acc0[1]), fmaxf(acc0[2], acc0[3]));
                 p.pA[(static_cast<size_t>(Iloc) * p.maxsegS + seg) * 128 + r] =
-                    make_float4(mx, (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]),
+                    make_float4(m4, (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]),
                                 (acc2[0] + acc2[1]) + (acc2[2] + acc2[3]), 0.f);
             } else if (kSweep == SWEEP_B) {
-                const int seg = blockIdx.x - p.partS.first_cta(curU);
                 p.pB[(static_cast<size_t>(Iloc) * p.maxsegS + seg) * 128 + r] =
                     make_float2((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
                                 (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]));
+            } else if (kSweep == SWEEP_F) {
+                const float se = (sum2(accE[0]) + sum2(accE[1])) + (sum2(accE[2]) + sum2(accE[3])) +
+                                 ((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]));
+                const float ss = (sum2(accS[0]) + sum2(accS[1])) + (sum2(accS[2]) + sum2(accS[3])) +
+                                 ((acc1[0] + acc1[1]) + (acc1[2] + acc1[3]));
+                const float4 o = make_float4(se, ss, mx, 0.f);
+                if (list_mode)
+                    p.pF2[(static_cast<size_t>(part.first_cta(curU) + curU + seg) * 2 + g) * 128 + r] = o;
+                else
+                    p.pF[(static_cast<size_t>(Iloc) * p.maxsegS + seg) * 128 + r] = o;
             } else {
                 p.pC[(static_cast<size_t>(Iloc) * p.splitc + (blockIdx.x % p.splitc)) * 128 + r] =
                     make_float4((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
@@ -472,19 +806,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         };
         auto begin_segment = [&](int nU) {
             curU = nU;
-            Iloc = 2 * nU + g;
+            Iloc = 2 * unit_of(nU) + g;
             valid = Iloc < p.nI;
             if (!valid) return;
+            lrow = Iloc * 128 + r;
             gi = (p.rb0 + Iloc) * 128 + r;
             yi = p.y[gi];
-            rI = sRange[p.rb0 + Iloc];
+            const int4 bi = sInfo[p.rb0 + Iloc];
+            rI = make_int2(bi.x, bi.y);
             if (kSweep == SWEEP_A) {
                 cshift = p.sqnorm[gi];
+            } else if (kSweep == SWEEP_F) {
+                const float4 c0 = *reinterpret_cast<const float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
+                const float4 c1 = *reinterpret_cast<const float4*>(p.rowc + static_cast<size_t>(lrow) * 8 + 4);
+                dsc[0] = c0.x; dsc[1] = c0.y; dsc[2] = c0.z; dsc[3] = c0.w; dsc[4] = c1.x;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) dd[d] = pack2(dsc[d], dsc[d]);
+                // a tile needs the max check unless max_k c_k <= min_i c_i (1 + tol)^2  (Cauchy-Schwarz)
+                chk_lim = sNorm[p.rb0 + Iloc].y * ((1.0f + kSpecTol) * (1.0f + kSpecTol) * (1.0f - 1e-6f));
+                if (list_mode) chk_lim = FLT_MAX;         // pass 2 runs with the exact maximum
             } else {
-                RowA ra_ = combine_A(p, Iloc, r);
-                ra = ra_.a;
-                rb = ra_.b;
-                if (kSweep == SWEEP_C) rden = combine_B(p, Iloc, r).x;
+                const float4 rs = p.rowS[lrow];
+                ra = rs.x;
+                rb = rs.y;
+                if (kSweep == SWEEP_C) rden = p.rowD[lrow].x;
             }
             reset();
         };
@@ -496,19 +841,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 begin_segment(U);
             }
             const int st = it & 1;
-            if (threadIdx.x == 0) trace_stamp(p, 2, it, 0);
-            mbar_wait(b_yfull + 8 * (it & 7), (it >> 3) & 1);   // labels of the column block have landed
+            if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 0);
             mbar_wait(b_tfull + 8 * (st * 2 + g), (it >> 1) & 1);
-            if (threadIdx.x == 0) trace_stamp(p, 2, it, 1);
+            if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 1);
             tc_fence_after();
-            const int32_t* ys = sYg + (it & 7) * 128;
             const int col0 = J * 128;
-            const int2 rJ = sRange[J];
-            const bool all_valid = sNv[J] == 128;
-            const uint32_t taddr = tmem + st * 256 + g * 128 + lane_off;
+            const int4 bj = sInfo[J];
+            const int2 rJ = make_int2(bj.x, bj.y);
+            const bool all_valid = bj.z == 128;
+            const uint32_t taddr = tmem + (st * 2 + g) * 128 + lane_off;
+            const int32_t* yJ = p.y + col0;
 
             if (!valid || (p.debug & 1)) {
                 // odd tail: this group has no row block; just release the stage
+            } else if (kSweep == SWEEP_F) {
+                const bool fast = all_valid && !ranges_overlap(rI, rJ);
+                const bool chk = sNorm[J].x > chk_lim;
+                if (fast) {
+                    if (deg == 2) {
+                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<2, false>(v, dd, accE, accS, mx); });
+                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<2, true>(v, dd, accE, accS, mx); });
+                    } else if (deg == 3) {
+                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<3, false>(v, dd, accE, accS, mx); });
+                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<3, true>(v, dd, accE, accS, mx); });
+                    } else {
+                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<4, false>(v, dd, accE, accS, mx); });
+                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<4, true>(v, dd, accE, accS, mx); });
+                    }
+                } else {
+                    // masked tile: negatives feed the sums, every valid column feeds the max
+                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]);
+                            const int yj = __ldg(yJ + c0 + j);
+                            float e = fmaf(dsc[4], s, dsc[3]);
+                            e = fmaf(e, s, dsc[2]);
+                            e = fmaf(e, s, dsc[1]);
+                            e = fmaf(e, s, dsc[0]);
+                            if (yj >= 0) {
+                                mx = fmaxf(mx, s);
+                                if (yj != yi) {
+                                    acc0[j & 3] += e;
+                                    acc1[j & 3] = fmaf(e, s, acc1[j & 3]);
+                                }
+                            }
+                        }
+                    });
+                }
             } else if (kSweep == SWEEP_A) {
                 if (all_valid) {
                     for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
@@ -525,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float x = __uint_as_float(v[j]) - cshift;
-                            if (ys[c0 + j] >= 0) {
+                            if (__ldg(yJ + c0 + j) >= 0) {
                                 acc0[j & 3] = fmaxf(acc0[j & 3], x);
                                 acc1[j & 3] += x;
                                 acc2[j & 3] = fmaf(x, x, acc2[j & 3]);
@@ -541,7 +921,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float t = fmaf(__uint_as_float(v[j]), ra, rb);
-                            float e = DCL_EX2_FWD(t, j);
+                            float e = ex2f(t);
                             acc0[j & 3] += e;
                             acc1[j & 3] = fmaf(e, t, acc1[j & 3]);
                         }
@@ -551,8 +931,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float t = fmaf(__uint_as_float(v[j]), ra, rb);
-                            float e = DCL_EX2_FWD(t, j);
-                            const int yj = ys[c0 + j];
+                            float e = ex2f(t);
+                            const int yj = __ldg(yJ + c0 + j);
                             const bool den = (yj >= 0) && (kMode == DCL_MODE_PIXEL ? (yj != yi)
                                                                                    : (col0 + c0 + j != gi));
                             if (den) {
@@ -566,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int yj = ys[c0 + j];
+                        const int yj = __ldg(yJ + c0 + j);
                         const bool pos = (yj == yi) && (col0 + c0 + j != gi);
                         float t = fmaf(__uint_as_float(v[j]), ra, rb);
                         float l = t * kLn2;
@@ -592,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_tempty + 8 * (st * 2 + g));
-            if (threadIdx.x == 0) trace_stamp(p, 2, it, 2);
+            if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 2);
             ++it;
         }
         if (curU >= 0) flush();
@@ -603,20 +983,125 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 }
 
 // =============================================================================================
-// finalize: partials -> per-row loss and backward constants (one thread per local row); the last
-// block to finish adds the per-block losses in fixed order
+// legacy combines: sweep A partials -> rowS, sweep B partials -> rowD
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_combine_A(const Params p) {
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
+    if (I == 0 && r == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
+    const int ns = p.partS.nseg(I >> 1);
+    float mx = -FLT_MAX;
+    double S1 = 0.0, S2 = 0.0;
+    for (int s = 0; s < ns; ++s) {
+        float4 v = p.pA[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
+        mx = fmaxf(mx, v.x);
+        S1 += v.y;
+        S2 += v.z;
+    }
+    const float c = p.sqnorm[(p.rb0 + I) * 128 + r];
+    const double d = mx;                                         // smax - c
+    double S2s = S2 - 2.0 * d * S1 + static_cast<double>(p.n_valid) * d * d;
+    if (!(S2s > 0.0)) S2s = 0.0;
+    const float rT = fmaxf(static_cast<float>(sqrt(S2s)), p.T * 1e-12f);   // F.normalize eps, loss.py:366
+    const float kappa = 1.0f / rT, smax = c + mx, a = kappa * kLog2e;
+    p.rowS[lrow] = make_float4(a, -smax * a, kappa, smax);
+}
+__global__ void __launch_bounds__(128) k_combine_B(const Params p) {
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
+    const int ns = p.partS.nseg(I >> 1);
+    float den = 0.f, bt = 0.f;
+    for (int s = 0; s < ns; ++s) {
+        float2 v = p.pB[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
+        den += v.x;
+        bt += v.y;
+    }
+    p.rowD[lrow] = make_float4(den, bt, 1.0f, 0.f);
+}
+
+// =============================================================================================
+// v3: verify the speculated maxima, build the list of row pairs to re-sweep, combine the partials
+// =============================================================================================
+__global__ void __launch_bounds__(128) k_check(const Params p) {
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
+    const int ns = p.partS.nseg(I >> 1);
+    float mx = -FLT_MAX;
+    for (int s = 0; s < ns; ++s) mx = fmaxf(mx, p.pF[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r].z);
+    const float thr = p.rowc[static_cast<size_t>(lrow) * 8 + 5];
+    const bool flagged = p.y[gi] >= 0 && mx > thr;
+    if (flagged) {
+        // exact maximum known (the violating tiles were all checked): redo the row's scale and polynomial
+        const float2 q = p.rowq[lrow];
+        const double c = p.sqnorm[gi], m = mx;
+        double kappa, L;
+        row_scale(q.x, q.y, m, c, p.scal[0], p.n_valid, p.T, kappa, L);
+        const int deg = write_rowc(p, lrow, kappa, m, L, FLT_MAX);
+        p.rowS[lrow] = make_float4(static_cast<float>(kappa * kLog2e), static_cast<float>(-m * kappa * kLog2e),
+                                   static_cast<float>(kappa), static_cast<float>(m));
+        if (deg > 2) atomicMax(&p.iscal[1], deg);
+        p.unit_flag[I >> 1] = 1;          // same value from every flagged row
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (r == 0) is_last = atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && r == 0) {
+        __threadfence();
+        const volatile int* fl = p.unit_flag;
+        int n = 0;
+        for (int u = 0; u < p.nP; ++u)
+            if (fl[u]) p.unit_list[n++] = u;
+        p.iscal[2] = n;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_combine_F(const Params p) {
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
+    const int U = I >> 1, g = I & 1;
+    double se = 0.0, ss = 0.0;
+    if (p.unit_flag[U]) {
+        // position of the unit in the list = number of flagged units before it
+        int pos = 0;
+        for (int u = 0; u < U; ++u) pos += p.unit_flag[u] != 0;
+        Part part = p.partS;
+        part.total = static_cast<long long>(p.iscal[2]) * p.nJ;
+        part.G = p.ctas;
+        const int fc = part.first_cta(pos), ns = part.nseg(pos);
+        for (int s = 0; s < ns; ++s) {
+            const float4 v = p.pF2[(static_cast<size_t>(fc + pos + s) * 2 + g) * 128 + r];
+            se += v.x;
+            ss += v.y;
+        }
+    } else {
+        const int ns = p.partS.nseg(U);
+        for (int s = 0; s < ns; ++s) {
+            const float4 v = p.pF[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
+            se += v.x;
+            ss += v.y;
+        }
+    }
+    const float4 rs = p.rowS[lrow];                 // (a, b, kappa, m)
+    const float L = p.rowc[static_cast<size_t>(lrow) * 8 + 7];
+    // Bt = sum_den E t = log2(e) kappa (sum E s - m sum E)
+    const double bt = static_cast<double>(rs.x) * (ss - static_cast<double>(rs.w) * se);
+    p.rowD[lrow] = make_float4(static_cast<float>(se), static_cast<float>(bt), L, 0.f);
+}
+
+// =============================================================================================
+// finalize: per-row loss and backward constants (one thread per local row); the last block to finish adds the
+// per-block losses in fixed order
 // =============================================================================================
 template <int kMode>
 __global__ void __launch_bounds__(128) k_finalize(const Params p) {
-    const int I = blockIdx.x, r = threadIdx.x;
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
     const int gi = (p.rb0 + I) * 128 + r;
     const int yi = p.y[gi];
     float rl = 0.f;
     float4 cA = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 cB = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
     if (yi >= 0) {
-        RowA ra = combine_A(p, I, r);
-        float2 db = combine_B(p, I, r);
+        const float4 rs = p.rowS[lrow];
+        const float4 db = p.rowD[lrow];
+        const float kappa = rs.z;
         float P = 0.f, SL = 0.f, SI = 0.f, SIL = 0.f;
         for (int s = 0; s < p.splitc; ++s) {
             float4 v = p.pC[(static_cast<size_t>(I) * p.splitc + s) * 128 + r];
@@ -631,15 +1116,15 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
             rl = -ratio * SL / P;
             Q = w * SI;
             R = w * db.x * SIL - Q * Bl;
-            wn = ra.kappa * w * db.x;
+            wn = kappa * w * db.x;
         } else {
             rl = -ratio * (SL - P * logf(db.x)) / P;
             Q = -c / db.x;
             R = w * SL - Q * Bl;
-            wn = ra.kappa * w;
+            wn = kappa * w;
         }
-        cA = make_float4(ra.a, ra.b, -ra.kappa * R * kLn2, -ra.kappa * Q);
-        cB = make_float4(wn, db.x, __int_as_float(yi), 0.f);
+        cA = make_float4(rs.x, rs.y, -kappa * R * kLn2, -kappa * Q);
+        cB = make_float4(wn, db.x, __int_as_float(yi), db.z);
     }
     p.colA[gi] = cA;
     p.colB[gi] = cB;
@@ -669,8 +1154,70 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
 }
 
 // =============================================================================================
-// Backward: per tile  S = F_I F_J^T  ->  G (bf16, TMEM, aliasing S)  ->  dF_I += G F_J
+// Backward
 // =============================================================================================
+// per row (all nJ*128 of them): the polynomial rp(s) = q E(s) + p (a s + b), in row order (coefR) and
+// pair-interleaved for the column side (coefP: [c0k c0k' c1k c1k'] [c2k c2k' c3k c3k'] [c4k c4k' 0 0])
+__global__ void __launch_bounds__(128) k_bwd_prep(const Params p) {
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    const float4 cA = p.colA[row];
+    const float4 cB = p.colB[row];
+    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int deg = 2;
+    if (__float_as_int(cB.z) >= 0) {
+        const double a = cA.x, b = cA.y;
+        double e[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
+        if (a > 0.0) {
+            const double kappa = a / static_cast<double>(kLog2e), m = -b / a, L = cB.w;
+            deg = poly_degree_for(L);
+            exp_poly_in_s(kappa, m, L, deg, e);
+        }
+        for (int j = 0; j < 5; ++j) d[j] = static_cast<double>(cA.w) * e[j];
+        d[1] += static_cast<double>(cA.z) * a;
+        d[0] += static_cast<double>(cA.z) * b;
+    }
+    float4* o = reinterpret_cast<float4*>(p.coefR + static_cast<size_t>(row) * 8);
+    o[0] = make_float4(static_cast<float>(d[0]), static_cast<float>(d[1]), static_cast<float>(d[2]), static_cast<float>(d[3]));
+    o[1] = make_float4(static_cast<float>(d[4]), 0.f, 0.f, 0.f);
+    float* cp = p.coefP + static_cast<size_t>(row >> 1) * kCoefPairFloats + (row & 1);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) cp[2 * j] = static_cast<float>(d[j]);
+    cp[10] = 0.f;
+    if (deg > 2) atomicMax(&p.iscal[3], deg);
+}
+
+// G for 32 columns of a fast tile: rp_i(s) + rp_k(s), packed bf16 into pk[16]
+template <int kDeg>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], const f32x2 (&rr)[5], const float4* __restrict__ cp,
+                                          uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
+        const float4 q0 = cp[3 * j], q1 = cp[3 * j + 1];
+        f32x2 gsum = ffma2(rr[kDeg], s, rr[kDeg - 1]);
+#pragma unroll
+        for (int d = kDeg - 2; d >= 0; --d) gsum = ffma2(gsum, s, rr[d]);
+        f32x2 h;
+        if (kDeg == 2) {
+            h = ffma2(pack2(q1.x, q1.y), s, pack2(q0.z, q0.w));
+        } else if (kDeg == 3) {
+            h = ffma2(pack2(q1.z, q1.w), s, pack2(q1.x, q1.y));
+            h = ffma2(h, s, pack2(q0.z, q0.w));
+        } else {
+            const float4 q2 = cp[3 * j + 2];
+            h = ffma2(pack2(q2.x, q2.y), s, pack2(q1.z, q1.w));
+            h = ffma2(h, s, pack2(q1.x, q1.y));
+            h = ffma2(h, s, pack2(q0.z, q0.w));
+        }
+        gsum = ffma2(h, s, gsum);
+        gsum = fadd2(gsum, pack2(q0.x, q0.y));
+        float lo, hi;
+        unpack2(gsum, lo, hi);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
+        pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -678,20 +1225,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sI = base + SmemBwd::kI;
     const uint32_t sJ = base + SmemBwd::kJ;
-    const uint32_t sCA = base + SmemBwd::kCA;
-    const uint32_t sCB = base + SmemBwd::kCB;
-    const float4* gCA = reinterpret_cast<const float4*>(gen + SmemBwd::kCA);
-    const float4* gCB = reinterpret_cast<const float4*>(gen + SmemBwd::kCB);
+    const uint32_t sCP = base + SmemBwd::kCP;
+    const float4* gCP = reinterpret_cast<const float4*>(gen + SmemBwd::kCP);
     int2* sRange = reinterpret_cast<int2*>(gen + SmemBwd::kRange);
     const uint32_t bar = base + SmemBwd::kBar;
     constexpr int kSlots = SmemBwd::kSlots, kStages = SmemBwd::kStages;
-    const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104,
-                   b_dfull = bar + 128, b_dempty = bar + 136, b_ifull = bar + 144, b_iempty = bar + 152;
+    const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104, b_sfree = bar + 128,
+                   b_dfull = bar + 152, b_dempty = bar + 160, b_ifull = bar + 168, b_iempty = bar + 176;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemBwd::kTmem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kProducerWarp) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
-    if (threadIdx.x == kMmaWarp * 32) {
+    if (threadIdx.x == kIssuerWarp0 * 32) {
         for (int s = 0; s < kSlots; ++s) {
             mbar_init(b_full + 8 * s, 1);
             mbar_init(b_empty + 8 * s, 1);
@@ -699,6 +1244,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(b_tfull + 8 * s, 1);
             mbar_init(b_pfull + 8 * s, 4);      // the 4 warps of one epilogue group
+            mbar_init(b_sfree + 8 * s, 1);
         }
         mbar_init(b_dfull, 1);
         mbar_init(b_dempty, 8);
@@ -706,12 +1252,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         mbar_init(b_iempty, 1);
         mbar_fence_init();
     }
-    {
-        // only the label ranges are needed here; reuse the helper with a scratch count array
-        // placed over the (not yet used) first colB slot
-        int* scratch_nv = reinterpret_cast<int*>(gen + SmemBwd::kCB);
-        compute_block_info(p.y, p.nJ, sRange, scratch_nv);
+    for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
+        const int4 q = p.binfo[j];
+        sRange[j] = make_int2(q.x, q.y);
     }
+    const int deg = (kMode == DCL_MODE_PIXEL) ? p.iscal[3] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -720,7 +1265,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
 
     if (warp == kProducerWarp) {
         if (lane == 0) {
-            TileIter<false> iter(p, p.partD, sRange);
+            TileIter<false> iter(p, p.partD, nullptr);
             int I, J, curI = -1, it = 0, seg = 0;
             bool last;
             while (iter.next(I, J, last)) {
@@ -736,82 +1281,98 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 trace_stamp(p, 0, it, 0);
                 mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
                 trace_stamp(p, 0, it, 1);
-                mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes + 4096);
+                if (kMode == DCL_MODE_PIXEL) {
+                    mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes + SmemBwd::kCoefBytes);
+                    tma_bulk_g2s(sCP + slot * SmemBwd::kCoefBytes,
+                                 p.coefP + static_cast<size_t>(J) * 64 * kCoefPairFloats, SmemBwd::kCoefBytes,
+                                 b_full + 8 * slot);
+                } else {
+                    mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes);
+                }
                 tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(J) * kTileBytes,
                              kTileBytes, b_full + 8 * slot);
-                tma_bulk_g2s(sCA + slot * 2048, p.colA + static_cast<size_t>(J) * 128, 2048,
-                             b_full + 8 * slot);
-                tma_bulk_g2s(sCB + slot * 2048, p.colB + static_cast<size_t>(J) * 128, 2048,
-                             b_full + 8 * slot);
                 ++it;
             }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kIssuerWarp0) {
         if (lane == 0) {
-            TileIter<false> iter(p, p.partD, sRange);
+            // ------------------------------------------------------------------ issuer 0: S = F_I F_J^T
+            TileIter<false> iter(p, p.partD, nullptr);
             const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-            const uint32_t idesc_d = umma_idesc_bf16(128, 128, 0, 1);   // B = F_J, MN-major
+            uint64_t dI[8], dJk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dI[k] = ftile_desc_kmajor(sI, k);
+                dJk[k] = ftile_desc_kmajor(sJ, k);
+            }
             int I, J, curI = -1, it = 0, seg = 0;
             bool last;
-            // Issue order S(0) S(1) S(2) dF(0) S(3) dF(1) S(4) ...: S runs two tiles ahead of the
-            // G.F_J product, so while one epilogue group turns S(it) into G(it) the other group's
-            // S(it+1) is already complete and S(it+2) is in flight.  Stage it%3 is reused by
-            // S(it+3), which is issued after dF(it) (in-order tensor pipe => G(it) is consumed).
-            struct Pending { bool first, last; int seg; };
-            Pending pend[2] = {{false, false, 0}, {false, false, 0}};
-            int n_issued_dF = 0;
-            auto issue_dF = [&](int pit) {
-                const Pending& q = pend[pit & 1];
-                const int pslot = pit % kSlots, pst = pit % kStages;
-                trace_stamp(p, 1, pit, 2);
-                mbar_wait(b_pfull + 8 * pst, (pit / kStages) & 1);
-                trace_stamp(p, 1, pit, 3);
-                if (q.first && q.seg > 0) mbar_wait(b_dempty, (q.seg - 1) & 1);
-                tc_fence_after();
-                if (!(p.debug & 4)) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_ts(tD, tmem + pst * 128 + k * 8, ftile_desc_mnmajor(sJ + pslot * kTileBytes, k),
-                            idesc_d, (!q.first) || k > 0);
-                }
-                tc_commit(b_empty + 8 * pslot);
-                if (q.last) tc_commit(b_dfull);
-            };
             while (iter.next(I, J, last)) {
-                const bool first = (I != curI);
-                if (first) {
+                if (I != curI) {
                     mbar_wait(b_ifull, seg & 1);
                     curI = I;
+                    ++seg;
                 }
                 const int slot = it % kSlots, st = it % kStages;
                 trace_stamp(p, 1, it, 0);
                 mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
                 trace_stamp(p, 1, it, 1);
+                mbar_wait(b_sfree + 8 * st, ((it / kStages) & 1) ^ 1);     // G(it-3) consumed
+                trace_stamp(p, 1, it, 2);
                 tc_fence_after();
+                const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
                 if (!(p.debug & 2)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_ss(tmem + st * 128, ftile_desc_kmajor(sI, k),
-                            ftile_desc_kmajor(sJ + slot * kTileBytes, k), idesc_s, k > 0);
+                    for (int k = 0; k < 8; ++k) umma_ss(tmem + st * 128, dI[k], dJk[k] + soff, idesc_s, k > 0);
                 }
                 tc_commit(b_tfull + 8 * st);
                 if (last) tc_commit(b_iempty);
-                if (it >= 2) { issue_dF(it - 2); n_issued_dF = it - 1; }
-                pend[it & 1] = Pending{first, last, seg};
-                if (last) ++seg;
+                trace_stamp(p, 1, it, 3);
                 ++it;
             }
-            for (int pit = n_issued_dF; pit < it; ++pit) issue_dF(pit);
+        }
+    } else if (warp == kIssuerWarp0 + 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ issuer 1: dF_I += G F_J
+            TileIter<false> iter(p, p.partD, nullptr);
+            const uint32_t idesc_d = umma_idesc_bf16(128, 128, 0, 1);   // B = F_J, MN-major
+            uint64_t dJm[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dJm[k] = ftile_desc_mnmajor(sJ, k);
+            int I, J, curI = -1, it = 0, seg = 0;
+            bool last;
+            while (iter.next(I, J, last)) {
+                const bool first = (I != curI);
+                curI = I;
+                const int slot = it % kSlots, st = it % kStages;
+                trace_stamp(p, 2, it, 0);
+                mbar_wait(b_pfull + 8 * st, (it / kStages) & 1);
+                trace_stamp(p, 2, it, 1);
+                if (first && seg > 0) mbar_wait(b_dempty, (seg - 1) & 1);
+                tc_fence_after();
+                const uint64_t poff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
+                if (!(p.debug & 4)) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_ts(tD, tmem + st * 128 + k * 8, dJm[k] + poff, idesc_d, (!first) || k > 0);
+                }
+                tc_commit(b_empty + 8 * slot);
+                tc_commit(b_sfree + 8 * st);
+                if (last) { tc_commit(b_dfull); ++seg; }
+                trace_stamp(p, 2, it, 2);
+                ++it;
+            }
         }
     } else {
         const int g = warp >> 2;                     // group g handles tiles with (it & 1) == g
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        TileIter<false> iter(p, p.partD, sRange);
+        TileIter<false> iter(p, p.partD, nullptr);
         int I, J, curI = -1, it = 0, seg = 0;
         bool last;
         float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = make_float4(0.f, 1.f, 0.f, 0.f);
+        f32x2 rr[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
         int yi = -1, gi = -1;
         int2 rI = make_int2(INT_MAX, -1);
         while (iter.next(I, J, last)) {
@@ -822,47 +1383,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 rB = p.colB[gi];
                 yi = __float_as_int(rB.z);
                 rI = sRange[p.rb0 + I];
+                if (kMode == DCL_MODE_PIXEL) {
+                    const float4 c0 = *reinterpret_cast<const float4*>(p.coefR + static_cast<size_t>(gi) * 8);
+                    const float c4 = p.coefR[static_cast<size_t>(gi) * 8 + 4];
+                    rr[0] = pack2(c0.x, c0.x); rr[1] = pack2(c0.y, c0.y); rr[2] = pack2(c0.z, c0.z);
+                    rr[3] = pack2(c0.w, c0.w); rr[4] = pack2(c4, c4);
+                }
             }
             if ((it & 1) == g) {
                 const int slot = it % kSlots, st = it % kStages;
-                if (threadIdx.x == g * 128) trace_stamp(p, 2, it, 0);
-                mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
+                if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 0);
+                mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);       // column polynomials have landed
                 mbar_wait(b_tfull + 8 * st, (it / kStages) & 1);
-                if (threadIdx.x == g * 128) trace_stamp(p, 2, it, 1);
+                if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 1);
                 tc_fence_after();
-                const float4* cA = gCA + slot * 128;
-                const float4* cB = gCB + slot * 128;
+                const float4* cp = gCP + slot * (SmemBwd::kCoefBytes / 16);
+                const float4* cA = p.colA + static_cast<size_t>(J) * 128;
+                const float4* cB = p.colB + static_cast<size_t>(J) * 128;
                 const int col0 = J * 128;
                 const uint32_t tS = tmem + st * 128 + lane_off;
                 // fast tile: every pair is a plain "denominator" pair in both directions (no
                 // positives, no self pair); padding needs no mask because padded F rows are zero
-                const bool fast = !ranges_overlap(rI, sRange[J]) &&
-                                  (kMode == DCL_MODE_PIXEL || (p.rb0 + I) != J);
+                const bool fast = kMode == DCL_MODE_PIXEL && !ranges_overlap(rI, sRange[J]);
                 if (p.debug & 1) {
                     // diagnostics: no G is produced
                 } else if (fast) {
-                    for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float gg[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const float s = __uint_as_float(v[j + u]);
-                                const float4 ck = cA[c0 + j + u];
-                                const float ti = fmaf(s, rA.x, rA.y);
-                                const float tk = fmaf(s, ck.x, ck.y);
-                                float acc = ti * rA.z;
-                                acc = fmaf(tk, ck.z, acc);
-                                acc = fmaf(DCL_EX2_BWD(ti, j + u), rA.w, acc);
-                                acc = fmaf(DCL_EX2_BWD(tk, j + u + 4), ck.w, acc);
-                                gg[u] = acc;
-                            }
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(gg[0], gg[1]);
-                            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-                        }
-                        tmem_st16(tS + (c0 >> 1), pk);
-                    });
+                    if (deg == 2) {
+                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                            uint32_t pk[16];
+                            bwd_chunk<2>(v, rr, cp + (c0 >> 1) * 3, pk);
+                            tmem_st16(tS + (c0 >> 1), pk);
+                        });
+                    } else if (deg == 3) {
+                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                            uint32_t pk[16];
+                            bwd_chunk<3>(v, rr, cp + (c0 >> 1) * 3, pk);
+                            tmem_st16(tS + (c0 >> 1), pk);
+                        });
+                    } else {
+                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                            uint32_t pk[16];
+                            bwd_chunk<4>(v, rr, cp + (c0 >> 1) * 3, pk);
+                            tmem_st16(tS + (c0 >> 1), pk);
+                        });
+                    }
                 } else {
                     for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
                         uint32_t pk[16];
@@ -872,8 +1436,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
                                 const float s = __uint_as_float(v[j + u]);
-                                const float4 ck = cA[c0 + j + u];
-                                const float4 dk = cB[c0 + j + u];
+                                const float4 ck = __ldg(cA + c0 + j + u);
+                                const float4 dk = __ldg(cB + c0 + j + u);
                                 const int yk = __float_as_int(dk.z);
                                 const float ti = fmaf(s, rA.x, rA.y);
                                 const float tk = fmaf(s, ck.x, ck.y);
@@ -908,7 +1472,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_pfull + 8 * st);
-                if (threadIdx.x == g * 128) trace_stamp(p, 2, it, 2);
+                if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 2);
             }
             ++it;
             if (last) {
@@ -952,13 +1516,30 @@ __global__ void __launch_bounds__(256) k_reduce_dF(const Params p, float* __rest
     *reinterpret_cast<float4*>(dF + static_cast<size_t>(row) * 128 + lane * 4) = acc;
 }
 
+// block info only (legacy forward and the backward entry point, which do not run k_gram)
+__global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
+    __shared__ int si[12];
+    __shared__ float sf[8];
+    const int J = blockIdx.x, t = threadIdx.x;
+    const int yv = p.y[J * 128 + t];
+    const float c = p.sqnorm ? p.sqnorm[J * 128 + t] : 0.f;
+    const BlockStat b = block_stat(yv, c, true, si, sf);
+    if (t == 0) {
+        p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
+        p.bnorm[J] = make_float2(b.cx, b.cn);
+        if (J == 0) p.iscal[3] = 2;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Layout {
     Part partS, partD;
-    int nP, maxsegS, maxsegD, splitc;
-    size_t off_pA, off_pB, off_pC, off_pD, off_bl, off_ticket, bytes;
+    int nP, maxsegS, maxsegD, splitc, gramP, ctas;
+    size_t off_binfo, off_bnorm, off_pA, off_pB, off_gram, off_fsum, off_cmaxp, off_ref, off_Mc, off_mu, off_scal,
+        off_iscal, off_rowq, off_rowc, off_pF, off_pF2, off_uflag, off_ulist, off_rowS, off_rowD, off_pC, off_bl,
+        off_ticket, off_coefR, off_coefP, off_pD, bytes;
 };
 
 static int g_debug_flags = 0;
@@ -977,18 +1558,42 @@ static void make_part(Part& part, int& maxseg, int nU, int nJ, int ctas) {
 static Layout make_layout(int nI, int nJ) {
     Layout L;
     const int ctas = sm_count();
+    L.ctas = ctas;
     L.nP = (nI + 1) / 2;
     make_part(L.partS, L.maxsegS, L.nP, nJ, ctas);
     make_part(L.partD, L.maxsegD, nI, nJ, ctas);
     int sc = (ctas + L.nP - 1) / L.nP;
     L.splitc = sc < 1 ? 1 : (sc > 8 ? 8 : sc);
+    L.gramP = nJ < ctas ? nJ : ctas;
+    const size_t rows = static_cast<size_t>(nI) * 128, allrows = static_cast<size_t>(nJ) * 128;
     size_t o = 0;
-    L.off_pA = o;     o = align_up(o + sizeof(float4) * static_cast<size_t>(nI) * L.maxsegS * 128, 256);
-    L.off_pB = o;     o = align_up(o + sizeof(float2) * static_cast<size_t>(nI) * L.maxsegS * 128, 256);
-    L.off_pC = o;     o = align_up(o + sizeof(float4) * static_cast<size_t>(nI) * L.splitc * 128, 256);
-    L.off_bl = o;     o = align_up(o + sizeof(float) * nI, 256);
-    L.off_ticket = o; o = align_up(o + sizeof(unsigned int), 256);
-    L.off_pD = o;     o = align_up(o + sizeof(float) * static_cast<size_t>(nI) * L.maxsegD * 128 * 128, 256);
+    auto take = [&](size_t& off, size_t bytes) { off = o; o = align_up(o + bytes, 256); };
+    take(L.off_binfo, sizeof(int4) * nJ);
+    take(L.off_bnorm, sizeof(float2) * nJ);
+    take(L.off_pA, sizeof(float4) * rows * L.maxsegS);        // legacy A partials; the v3 pass-1 partials (pF) share it
+    take(L.off_pB, sizeof(float2) * rows * L.maxsegS);
+    take(L.off_gram, sizeof(float) * 16384 * static_cast<size_t>(L.gramP));
+    take(L.off_fsum, sizeof(float) * 128 * L.gramP);
+    take(L.off_cmaxp, sizeof(float) * L.gramP);
+    take(L.off_ref, sizeof(float) * 128);
+    take(L.off_Mc, sizeof(float) * 16384);
+    take(L.off_mu, sizeof(float) * 128);
+    take(L.off_scal, sizeof(float) * 8);
+    take(L.off_iscal, sizeof(int) * 8);
+    take(L.off_rowq, sizeof(float2) * rows);
+    take(L.off_rowc, sizeof(float) * 8 * rows);
+    L.off_pF = L.off_pA;
+    take(L.off_pF2, sizeof(float4) * 256 * static_cast<size_t>(ctas + L.nP + 2));
+    take(L.off_uflag, sizeof(int) * L.nP);
+    take(L.off_ulist, sizeof(int) * L.nP);
+    take(L.off_rowS, sizeof(float4) * rows);
+    take(L.off_rowD, sizeof(float4) * rows);
+    take(L.off_pC, sizeof(float4) * rows * L.splitc);
+    take(L.off_bl, sizeof(float) * nI);
+    take(L.off_ticket, sizeof(unsigned int) * 4);
+    take(L.off_coefR, sizeof(float) * 8 * allrows);
+    take(L.off_coefP, sizeof(float) * kCoefPairFloats * (allrows / 2));
+    take(L.off_pD, sizeof(float) * rows * L.maxsegD * 128);
     L.bytes = o;
     return L;
 }
@@ -1000,17 +1605,38 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.tiles = static_cast<const uint8_t*>(tiles);
     p.y = y;
     p.sqnorm = sqnorm;
-    p.nJ = nJ; p.rb0 = rb0; p.nI = nI; p.nP = L.nP; p.n_valid = n_valid; p.mode = mode;
+    p.nJ = nJ; p.rb0 = rb0; p.nI = nI; p.nP = L.nP; p.n_valid = n_valid; p.mode = mode; p.ctas = L.ctas;
     p.T = T; p.Tb = Tb;
     p.partS = L.partS;
     p.partD = L.partD;
     p.maxsegS = L.maxsegS;
     p.maxsegD = L.maxsegD;
     p.splitc = L.splitc;
+    p.gramP = L.gramP;
+    p.binfo = reinterpret_cast<int4*>(w + L.off_binfo);
+    p.bnorm = reinterpret_cast<float2*>(w + L.off_bnorm);
     p.pA = reinterpret_cast<float4*>(w + L.off_pA);
     p.pB = reinterpret_cast<float2*>(w + L.off_pB);
+    p.gram_part = reinterpret_cast<float*>(w + L.off_gram);
+    p.fsum_part = reinterpret_cast<float*>(w + L.off_fsum);
+    p.cmax_part = reinterpret_cast<float*>(w + L.off_cmaxp);
+    p.ref = reinterpret_cast<float*>(w + L.off_ref);
+    p.Mc = reinterpret_cast<float*>(w + L.off_Mc);
+    p.mu = reinterpret_cast<float*>(w + L.off_mu);
+    p.scal = reinterpret_cast<float*>(w + L.off_scal);
+    p.iscal = reinterpret_cast<int*>(w + L.off_iscal);
+    p.rowq = reinterpret_cast<float2*>(w + L.off_rowq);
+    p.rowc = reinterpret_cast<float*>(w + L.off_rowc);
+    p.pF = reinterpret_cast<float4*>(w + L.off_pF);
+    p.pF2 = reinterpret_cast<float4*>(w + L.off_pF2);
+    p.unit_flag = reinterpret_cast<int*>(w + L.off_uflag);
+    p.unit_list = reinterpret_cast<int*>(w + L.off_ulist);
+    p.rowS = reinterpret_cast<float4*>(w + L.off_rowS);
+    p.rowD = reinterpret_cast<float4*>(w + L.off_rowD);
     p.pC = reinterpret_cast<float4*>(w + L.off_pC);
     p.pD = reinterpret_cast<float*>(w + L.off_pD);
+    p.coefR = reinterpret_cast<float*>(w + L.off_coefR);
+    p.coefP = reinterpret_cast<float*>(w + L.off_coefP);
     p.blockloss = reinterpret_cast<float*>(w + L.off_bl);
     p.ticket = reinterpret_cast<unsigned int*>(w + L.off_ticket);
     p.debug = g_debug_flags;
@@ -1024,8 +1650,46 @@ static int set_smem(K kernel, int bytes) {
     return 0;
 }
 
+constexpr int kGramSmem = 128 * kGramLd * 4;
+constexpr int kRowstatSmem = 2 * 128 * kGramLd * 4;
+
+// v3 pixel forward: closed-form row norms, one fused sweep (+ a list-mode re-sweep that exits at once when the
+// speculation held everywhere), sweep C, finalize
+static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (int e = set_smem(k_gram, kGramSmem)) return e;
+        if (int e = set_smem(k_rowstats, kRowstatSmem)) return e;
+        if (int e = set_smem(k_sweep<SWEEP_F, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
+        if (int e = set_smem(k_sweep<SWEEP_C, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
+        configured = true;
+    }
+    k_gram<<<L.gramP, 256, kGramSmem, st>>>(p);
+    DCL_LAUNCH_CHECK("k_gram");
+    k_gram_reduce<<<64, 256, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_gram_reduce");
+    k_rowstats<<<p.nI, 256, kRowstatSmem, st>>>(p);
+    DCL_LAUNCH_CHECK("k_rowstats");
+    p.list_mode = 0;
+    k_sweep<SWEEP_F, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
+    DCL_LAUNCH_CHECK("k_sweep<F>");
+    k_check<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_check");
+    p.list_mode = 1;
+    k_sweep<SWEEP_F, DCL_MODE_PIXEL><<<L.ctas, kThreads, SmemSweep::kBytes, st>>>(p);
+    DCL_LAUNCH_CHECK("k_sweep<F2>");
+    p.list_mode = 0;
+    k_combine_F<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine_F");
+    k_sweep<SWEEP_C, DCL_MODE_PIXEL><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
+    DCL_LAUNCH_CHECK("k_sweep<C>");
+    k_finalize<DCL_MODE_PIXEL><<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_finalize");
+    return 0;
+}
+
 template <int kMode>
-static int run_fwd(Params p, const Layout& L, cudaStream_t st) {
+static int run_fwd_legacy(Params p, const Layout& L, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (int e = set_smem(k_sweep<SWEEP_A, kMode>, SmemSweep::kBytes)) return e;
@@ -1033,10 +1697,16 @@ static int run_fwd(Params p, const Layout& L, cudaStream_t st) {
         if (int e = set_smem(k_sweep<SWEEP_C, kMode>, SmemSweep::kBytes)) return e;
         configured = true;
     }
+    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_blockinfo");
     k_sweep<SWEEP_A, kMode><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<A>");
+    k_combine_A<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine_A");
     k_sweep<SWEEP_B, kMode><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<B>");
+    k_combine_B<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine_B");
     k_sweep<SWEEP_C, kMode><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<C>");
     k_finalize<kMode><<<p.nI, 128, 0, st>>>(p);
@@ -1051,6 +1721,12 @@ static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
         if (int e = set_smem(k_backward<kMode>, SmemBwd::kBytes)) return e;
         configured = true;
     }
+    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_blockinfo");
+    if (kMode == DCL_MODE_PIXEL) {
+        k_bwd_prep<<<p.nJ, 128, 0, st>>>(p);
+        DCL_LAUNCH_CHECK("k_bwd_prep");
+    }
     k_backward<kMode><<<L.partD.G, kThreads, SmemBwd::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_backward");
     k_reduce_dF<<<(p.nI * 128 + 7) / 8, 256, 0, st>>>(p, dF);
@@ -1062,17 +1738,24 @@ static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
 
 using namespace dcl;
 
-// Diagnostics only: component-isolation switches for profiling (results are invalid when non-zero).
+// Diagnostics only: component-isolation switches for profiling (results are invalid when bits 0..2 are set).
+// Bit 3 (8) selects the legacy three-sweep forward for the pixel term.
 extern "C" int dcl_debug_flags(int flags) {
     const int old = g_debug_flags;
     g_debug_flags = flags;
     return old;
 }
 
-// Diagnostics only: device buffer of 3*32*4 int64 that CTA 0 of k_backward fills with clock64 stamps.
+// Diagnostics only: device buffer of 5*32*8 int64 that CTA 0 of the pipelined kernels fills with clock64 stamps.
 extern "C" int dcl_debug_trace(void* device_buffer) {
     g_trace = static_cast<long long*>(device_buffer);
     return 0;
+}
+
+// kernels launched by one forward (backward != 0: one backward) call for `mode` with the current debug flags
+extern "C" int dcl_contrast_launches(int mode, int backward) {
+    if (backward) return mode == DCL_MODE_PIXEL ? 4 : 3;
+    return (mode == DCL_MODE_PIXEL && !(g_debug_flags & 8)) ? 9 : 7;
 }
 
 extern "C" size_t dcl_contrast_workspace_bytes(int nI, int nJ) {
@@ -1115,8 +1798,10 @@ extern "C" int dcl_contrast_fwd(const void* tiles, const int32_t* y, const float
     p.colB = reinterpret_cast<float4*>(colB);
     p.rowloss = rowloss;
     p.loss_sum = loss_sum;
-    return mode == DCL_MODE_PIXEL ? run_fwd<DCL_MODE_PIXEL>(p, L, as_stream(stream))
-                                  : run_fwd<DCL_MODE_SUPCON>(p, L, as_stream(stream));
+    if (mode == DCL_MODE_PIXEL)
+        return (g_debug_flags & 8) ? run_fwd_legacy<DCL_MODE_PIXEL>(p, L, as_stream(stream))
+                                   : run_fwd_v3(p, L, as_stream(stream));
+    return run_fwd_legacy<DCL_MODE_SUPCON>(p, L, as_stream(stream));
 }
 
 extern "C" int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB,

@@ -279,7 +279,7 @@ def contrast_forward(tiles, y, sqnorm, nJ, rb0, nI, n_valid, mode, T, Tb, colA=N
     with _Timed("contrast_fwd"):
         _lib.call("dcl_contrast_fwd", _p(tiles), _p(y), _p(sqnorm), nJ, rb0, nI, n_valid, mode, float(T),
                   float(Tb), _p(ws), nbytes, _p(colA), _p(colB), _p(rowloss), _p(loss_sum), _stream())
-    _count(_lib.FWD_LAUNCHES)
+    _count(_lib.contrast_launches(mode, 0))
     return colA, colB, rowloss, loss_sum
 
 
@@ -291,7 +291,7 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
     with _Timed("contrast_bwd"):
         _lib.call("dcl_contrast_bwd", _p(tiles), _p(y), _p(colA), _p(colB), nJ, rb0, nI, mode, _p(ws), nbytes,
                   _p(dF), _stream())
-    _count(_lib.BWD_LAUNCHES)
+    _count(_lib.contrast_launches(mode, 1))
     return dF
 
 

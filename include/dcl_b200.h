@@ -47,12 +47,15 @@ const char* dcl_last_error(void);
 /* 0 iff the current device can run the kernels (compute capability 10.x). */
 int dcl_check_device(void);
 /* Diagnostics only: profiling switches for the contrast kernels (1 = skip epilogue math, 2 = skip
- * the S = F_I F_J^T MMAs, 4 = skip the dF MMAs).  Results are invalid while non-zero.  Returns the
- * previous value. */
+ * the S = F_I F_J^T MMAs, 4 = skip the dF MMAs: results are invalid while any of these is set;
+ * 8 = run the pixel term's forward through the legacy three-sweep path, results stay valid).
+ * Returns the previous value. */
 int dcl_debug_flags(int flags);
-/* Diagnostics only: device buffer (3*32*4 int64, or NULL to disable) that CTA 0 of the backward kernel
- * fills with per-role clock64 stamps of its first 32 tiles. */
+/* Diagnostics only: device buffer (5*32*8 int64, or NULL to disable) that CTA 0 of the pipelined
+ * kernels fills with per-role clock64 stamps of its first 32 tiles. */
 int dcl_debug_trace(void* device_buffer);
+/* Number of kernels one dcl_contrast_fwd (backward == 0) or dcl_contrast_bwd call launches for `mode`. */
+int dcl_contrast_launches(int mode, int backward);
 
 /* ---------------------------------------------------------------- sampler front end
  * Replaces loss.py:396-408 (argmax over classes, nearest down-sampling of labels) and the
@@ -106,7 +109,8 @@ int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int 
  *   y      [nJ*128] i32 labels, -1 = padding        sqnorm [nJ*128]
  *   n_valid : number of valid rows over the WHOLE contrast set (the reference's N)
  *   colA, colB [nJ*128] float4 out (rows of the local blocks only are written): per-row
- *            constants consumed by dcl_contrast_bwd; all-gather them before a sharded backward
+ *            constants consumed by dcl_contrast_bwd - (a, b, p, q) and (wn, Den, label bits, logit range L);
+ *            all-gather them before a sharded backward
  *   rowloss [nJ*128] f32 out (local rows): per-row loss term, 0 for padding
  *   loss_sum [1] f32 out: sum of rowloss over the local rows (caller divides by n_valid)
  *   workspace: dcl_contrast_workspace_bytes(nI, nJ) bytes

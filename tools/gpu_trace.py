@@ -14,12 +14,12 @@ nJ = n // 128
 colA, colB, rl, ls = L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
 for _ in range(2):
     L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
-buf = torch.zeros(3 * 32 * 4, dtype=torch.int64, device="cuda")
+buf = torch.zeros(5 * 32 * 8, dtype=torch.int64, device="cuda")
 lib.dcl_debug_trace(buf.data_ptr())
 L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
 torch.cuda.synchronize()
 lib.dcl_debug_trace(None)
-t = buf.cpu().view(3, 32, 4)
+t = buf.cpu().view(5, 32, 8)
 t0 = int(t[t > 0].min())
 print("tile | producer: wait_empty got_empty | mma: wait_full got_full wait_pfull got_pfull | epilogue: start got_tfull done   (clk since first stamp)")
 for it in range(24):

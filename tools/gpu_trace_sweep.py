@@ -16,15 +16,18 @@ tiles, sq = L.pack_rows(Z, n)
 nJ = n // 128
 for _ in range(2):
     L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
-buf = torch.zeros(3 * 32 * 4, dtype=torch.int64, device="cuda")
+lib.dcl_debug_flags(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+buf = torch.zeros(5 * 32 * 8, dtype=torch.int64, device="cuda")
 lib.dcl_debug_trace(buf.data_ptr())
 L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
 torch.cuda.synchronize()
 lib.dcl_debug_trace(None)
-t = buf.cpu().view(3, 32, 4)
+t = buf.cpu().view(5, 32, 8)
 base = int(t[:, 2:, :][t[:, 2:, :] > 0].min())
-print("sweep B (tiles >= 2 keep B's stamps; C only overwrites tile 0/1)")
-print("tile | producer: wait_empty got_empty | mma: wait_full got_full got_tempty issued | epilogue(g0,w0): start got_tfull done")
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+print(f"sweep B, n={n} (tiles >= 2 keep B's stamps)")
+print("tile | prod: wait_e got_e | mma: wait_full got_full got_te0 commit0 got_te1 issued | g0: start got_y got_tfull done | g1: start got_y got_tfull done")
 for it in range(2, 26):
     r = lambda role, ev: (int(t[role, it, ev]) - base) if int(t[role, it, ev]) else -1
-    print(f"{it:4d} | {r(0,0):7d} {r(0,1):7d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} {r(1,3):7d} | {r(2,0):7d} {r(2,1):7d} {r(2,2):7d}")
+    print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(1,0):6d} {r(1,1):6d} {r(1,2):6d} {r(1,4):6d} {r(1,5):6d} {r(1,3):6d} | "
+          f"{r(2,0):6d} {r(2,3):6d} {r(2,1):6d} {r(2,2):6d} | {r(3,0):6d} {r(3,3):6d} {r(3,1):6d} {r(3,2):6d}")
