@@ -9,12 +9,13 @@
 // Two forward pipelines share the kernels below:
 //   * pixel term ("v3", the hot path).  The row norm needs no N^2 pass:
 //         sum_k (s_ik - m)^2 = f_i^T Mc f_i + n (f_i.mu - m)^2,   Mc = centred Gram matrix (k_gram, k_rowstats)
-//     and the row max of a (near-)normalised embedding is its own diagonal c_i = |f_i|^2, so ONE fused sweep
-//     (SWEEP_F) evaluates E = e^{l} with the speculated m_i = c_i, accumulates Den_i and sum E s, and verifies the
-//     speculation (any s_ik > c_i (1 + 2^-8) flags the row; a tile whose Cauchy-Schwarz bound cannot exceed it
-//     skips the check).  Flagged row pairs are re-swept once with their exact maximum (list mode).  e^{l} on the
-//     row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a per-row economised Chebyshev polynomial of
-//     degree 2..4 in s, evaluated with packed FFMA2 - no MUFU in the sweep.
+//     and e^{l} on the row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a per-row economised
+//     Chebyshev polynomial of degree n = 2..4 in s, so  Den_i = sum_neg E = sum_j d_j P_j  and  sum_neg E s =
+//     sum_j d_j P_{j+1}  with the power sums P_j = sum_neg s^j.  P_0..P_2 over all columns are closed forms of the
+//     Gram statistics; ONE sweep (SWEEP_P) therefore only has to produce the exact row maximum and
+//     sum s^3 (.. s^{n+1}) on the tiles that hold no same-class pair (packed FFMA2, no MUFU, no per-row
+//     constants), and full masked sums on the block-diagonal tiles.  kappa_i, the polynomial and Den_i follow per
+//     row afterwards (k_combine_P).
 //   * image term and the diagnostic legacy path: sweep A (max, sums), sweep B (Den), as in round 1.
 //   Both continue with sweep C (tiles that can hold positives), finalize, and the fused backward
 //         G_ik = dS_ik + dS_ki = rp_i(s_ik) + rp_k(s_ik)   on pairs of different classes,
@@ -47,7 +48,6 @@ constexpr int kTmemCols = 512;
 constexpr int kProducerWarp = 8;
 constexpr int kIssuerWarp0 = 9;       // issuer g is warp 9 + g
 constexpr int kMaxBlocks = 1024;      // column blocks whose info is cached in shared memory
-constexpr float kSpecTol = 1.0f / 256.0f;   // speculation holds while no s_ik exceeds c_i (1 + tol)
 constexpr int kGramLd = 132;          // padded row length (floats) of the Gram kernels' shared tiles
 constexpr int kCoefPairFloats = 12;   // backward column coefficients of one column pair: 3 x float4
 
@@ -91,15 +91,10 @@ struct Params {
     float* Mc;               // [128*128] centred Gram
     float* mu;               // [128]
     float* scal;             // [0] cmax over all rows
-    int* iscal;              // [0] fwd poly degree pass 1, [1] degree pass 2, [2] flagged unit count, [3] bwd degree
+    int* iscal;              // [0] forward polynomial degree (bound over the local rows), [3] backward degree
     int gramP;
     float2* rowq;            // [nI*128] (f^T Mc f, f.mu)
-    float* rowc;             // [nI*128][8] (d0..d4 of E(s), threshold c(1+tol), m, L)
-    float4* pF;              // [nI][maxsegS][128] pass-1 partials (sum E, sum E s, max s, -)
-    float4* pF2;             // [ctas + nP + 2][2][128] pass-2 partials, slot = first_cta(u) + u + seg
-    int* unit_flag;          // [nP]
-    int* unit_list;          // [nP]
-    int list_mode;           // SWEEP_F pass 2: units come from unit_list[0 .. iscal[2])
+    float4* pF;              // [nI][maxsegS][3][128] power-sum partials: (max s, Q3, Q4, Q5) (V0, V1, V2, N0) (N1, N2, -, -)
     // per-row state shared by sweep C / finalize
     float4* rowS;            // [nI*128] (a, b, kappa, m)   t = a s + b = l log2(e)
     float4* rowD;            // [nI*128] (Den, Bt = sum_den E t, L, 0)
@@ -112,7 +107,7 @@ struct Params {
     float* rowloss;          // [nJ*128]
     float* blockloss;        // [nI]
     float* loss_sum;
-    unsigned int* ticket;    // last-block counters: [0] finalize, [1] k_check
+    unsigned int* ticket;    // last-block counter of k_finalize
     long long* trace;        // diagnostics only (dcl_debug_trace)
     int debug;               // diagnostics only (dcl_debug_flags)
 };
@@ -201,6 +196,17 @@ __device__ __forceinline__ void for_each_chunk(uint32_t taddr, Fn&& fn) {
     } else {
         fn(32, vb);
     }
+}
+
+// One lane of a fully converged warp.  The single-lane pipeline roles run with ALL lanes executing the (warp-uniform)
+// control flow and only the asynchronous instructions predicated on this: ptxas then keeps descriptors, barrier
+// addresses and loop state in uniform registers.  Under a divergent `if (lane == 0)` every tcgen05.mma / bulk copy
+// is preceded by a ~16-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY uniformisation loop, which made MMA *issue*
+// (~110 clk per MMA next to busy epilogue warps) the bottleneck of the first versions.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // diagnostics: stamp (role, tile, event) for CTA 0's first 32 tiles; roles: 0 producer, 1/2 issuers, 3/4 epilogue groups
@@ -443,29 +449,30 @@ __global__ void __launch_bounds__(256) k_gram_reduce(const Params p) {
             for (int q = 0; q < p.gramP; ++q) cm = fmaxf(cm, p.cmax_part[q]);
             p.scal[0] = cm;
             p.iscal[0] = 2;
-            p.iscal[1] = 2;
-            p.iscal[2] = 0;
             p.ticket[0] = 0u;
             p.ticket[1] = 0u;
         }
     }
 }
 
-// writes one row's forward polynomial block: (d0..d4, threshold, m, L)
-__device__ __forceinline__ int write_rowc(const Params& p, int lrow, double kappa, double m, double L, float thr) {
-    double d[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
-    int deg = 2;
-    if (kappa > 0.0) {
-        deg = poly_degree_for(L);
-        exp_poly_in_s(kappa, m, L, deg, d);
+// Upper bound of the logit range L(m) = kappa(m) (m + b) over every possible row maximum m >= c (the sweep that
+// finds m runs after the polynomial degree must be known):  g(m) = (m + b) / sqrt(qf + n (m - fm)^2) peaks at
+// m* = fm + qf / (n (fm + b)).
+__device__ __forceinline__ double logit_range_bound(double qf, double fm, double c, double cmax, int n_valid) {
+    const double n = n_valid, b = sqrt(c * cmax);
+    auto g = [&](double m) {
+        const double e = m - fm, v = qf + n * e * e;
+        return v > 0.0 ? (m + b) / sqrt(v) : 1.0;
+    };
+    double best = g(c);
+    if (fm + b > 0.0) {
+        const double ms = fm + (qf > 0.0 ? qf : 0.0) / (n * (fm + b));
+        if (ms > c) best = fmax(best, g(ms));
     }
-    float4* out = reinterpret_cast<float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
-    out[0] = make_float4(static_cast<float>(d[0]), static_cast<float>(d[1]), static_cast<float>(d[2]), static_cast<float>(d[3]));
-    out[1] = make_float4(static_cast<float>(d[4]), thr, static_cast<float>(m), static_cast<float>(L));
-    return deg;
+    return fmin(1.0, best * (1.0 + 1e-6));
 }
 
-// per local row block: qf_i = f_i^T Mc f_i, fm_i = f_i . mu, then kappa / polynomial with the speculated m_i = c_i
+// per local row block: qf_i = f_i^T Mc f_i, fm_i = f_i . mu, and the polynomial degree the row may need
 __global__ void __launch_bounds__(256) k_rowstats(const Params p) {
     extern __shared__ float gsm[];
     float* X = gsm;                          // F^T : [d][i]
@@ -504,34 +511,22 @@ __global__ void __launch_bounds__(256) k_rowstats(const Params p) {
         float fm = 0.f;
         for (int d = 0; d < 128; ++d) fm = fmaf(X[d * kGramLd + tid], smu[d], fm);
         p.rowq[lrow] = make_float2(sqf[tid], fm);
-        int deg = 2;
         if (sy[tid] >= 0) {
             const double c = p.sqnorm[gi];
-            double kappa, L;
-            row_scale(sqf[tid], fm, c, c, p.scal[0], p.n_valid, p.T, kappa, L);
-            deg = write_rowc(p, lrow, kappa, c, L, static_cast<float>(c) * (1.0f + kSpecTol));
-            p.rowS[lrow] = make_float4(static_cast<float>(kappa * kLog2e), static_cast<float>(-c * kappa * kLog2e),
-                                       static_cast<float>(kappa), static_cast<float>(c));
-        } else {
-            float4* out = reinterpret_cast<float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
-            out[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            out[1] = make_float4(0.f, FLT_MAX, 0.f, 0.f);
-            p.rowS[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int deg = poly_degree_for(logit_range_bound(sqf[tid], fm, c, p.scal[0], p.n_valid));
+            if (deg > 2) atomicMax(&p.iscal[0], deg);
         }
-        if (deg > 2) atomicMax(&p.iscal[0], deg);
     }
-    if (tid == 0 && (I & 1) == 0) p.unit_flag[I >> 1] = 0;
 }
 
 // =============================================================================================
 // shared-memory carve-up (bytes from a 1024-aligned base)
 // =============================================================================================
 struct SmemSweep {
-    static constexpr int kI = 0;                          // 2 row-block tiles
-    static constexpr int kJ = 2 * kTileBytes;             // 4 slots
-    static constexpr int kInfo = 6 * kTileBytes;          // int4[kMaxBlocks]
-    static constexpr int kNorm = kInfo + 16 * kMaxBlocks; // float2[kMaxBlocks]
-    static constexpr int kBar = kNorm + 8 * kMaxBlocks;   // full[4] empty[4] tfull[4] tempty[4] ifull iempty
+    static constexpr int kSlots = 6;                      // F_J ring (the row blocks live in TMEM)
+    static constexpr int kJ = 0;
+    static constexpr int kInfo = kSlots * kTileBytes;     // int4[kMaxBlocks]
+    static constexpr int kBar = kInfo + 16 * kMaxBlocks;  // full[6] empty[6] tfull[3] tempty[3] afull[2] turn[2]
     static constexpr int kTmem = kBar + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;      // + alignment slack
 };
@@ -548,10 +543,10 @@ struct SmemBwd {
     static constexpr int kBytes = kTmem + 16 + 1024;
 };
 
-enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2, SWEEP_F = 3 };
+enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2, SWEEP_P = 3 };
 
 // Tile sequence of one CTA: (row unit U, column block J).  Flat mode: contiguous range of the flattened U-major
-// list (in list mode the units are positions in unit_list).  Relevant mode (sweep C): CTA = (pair, split s) walks
+// list.  Relevant mode (sweep C): CTA = (pair, split s) walks
 // the column blocks whose label range overlaps either row block of the pair and keeps every splitc-th one.  All
 // warp roles run an identical copy of this iterator, which keeps their barrier phases in step.
 template <bool kRelevantOnly>
@@ -613,137 +608,164 @@ struct TileIter {
 };
 
 // ---------------------------------------------------------------------------------------------
-// SWEEP_F fast-tile body: E = poly(s) for 32 columns (16 packed pairs); accE += E, accS += E s; optional row max
-template <int kDeg, bool kCheck>
-__device__ __forceinline__ void fsweep_chunk(const uint32_t (&v)[32], const f32x2 (&dd)[5], f32x2 (&accE)[4],
-                                             f32x2 (&accS)[4], float& mx) {
+// SWEEP_P fast-tile body for 32 columns (16 packed pairs): row max and the power sums s^3 .. s^{deg+1}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+template <int kDeg>
+__device__ __forceinline__ void psweep_chunk(const uint32_t (&v)[32], f32x2 (&q3)[4], f32x2 (&q4)[4], f32x2 (&q5)[4],
+                                             float (&mx)[4]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
-        f32x2 e = ffma2(dd[kDeg], s, dd[kDeg - 1]);
-#pragma unroll
-        for (int d = kDeg - 2; d >= 0; --d) e = ffma2(e, s, dd[d]);
-        accE[j & 3] = fadd2(accE[j & 3], e);
-        accS[j & 3] = ffma2(e, s, accS[j & 3]);
-        if (kCheck) mx = fmaxf(mx, fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+        const f32x2 s2 = fmul2(s, s);
+        q3[j & 3] = ffma2(s2, s, q3[j & 3]);
+        if (kDeg >= 3) q4[j & 3] = ffma2(s2, s2, q4[j & 3]);
+        if (kDeg >= 4) q5[j & 3] = ffma2(fmul2(s2, s), s2, q5[j & 3]);
+        mx[j & 3] = fmaxf(mx[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
     }
 }
 
 // =============================================================================================
-// Sweeps A / B / C / F
+// Sweeps A / B / C / P
 // =============================================================================================
 template <int kSweep, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sI = base + SmemSweep::kI;
     const uint32_t sJ = base + SmemSweep::kJ;
     int4* sInfo = reinterpret_cast<int4*>(gen + SmemSweep::kInfo);
-    float2* sNorm = reinterpret_cast<float2*>(gen + SmemSweep::kNorm);
     const uint32_t bar = base + SmemSweep::kBar;
-    // tfull / tempty are per (stage, group): index st * 2 + g
-    const uint32_t b_full = bar, b_empty = bar + 32, b_tfull = bar + 64, b_tempty = bar + 96,
-                   b_ifull = bar + 128, b_iempty = bar + 136;
+    constexpr int kSlots = SmemSweep::kSlots;
+    // tfull / tempty are per accumulator buffer (job % 3); afull per row block of the pair; turn per issuer
+    const uint32_t b_full = bar, b_empty = bar + 48, b_tfull = bar + 96, b_tempty = bar + 120,
+                   b_afull = bar + 144, b_turn = bar + 160, b_aseen = bar + 176;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemSweep::kTmem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (warp == kProducerWarp) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
     if (threadIdx.x == kIssuerWarp0 * 32) {
-        for (int s = 0; s < 4; ++s) {
+        for (int s = 0; s < kSlots; ++s) {
             mbar_init(b_full + 8 * s, 1);
-            mbar_init(b_empty + 8 * s, 2);      // one commit per issuer
+            mbar_init(b_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 3; ++s) {
             mbar_init(b_tfull + 8 * s, 1);
             mbar_init(b_tempty + 8 * s, 4);     // the 4 warps of one epilogue group
         }
-        mbar_init(b_ifull, 1);
-        mbar_init(b_iempty, 2);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(b_afull + 8 * s, 4);
+            mbar_init(b_turn + 8 * s, 1);
+        }
+        mbar_init(b_aseen, 2);                  // both issuers have observed the current row blocks
         mbar_fence_init();
     }
-    for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
-        sInfo[j] = p.binfo[j];
-        sNorm[j] = p.bnorm[j];
-    }
-    // list mode (SWEEP_F pass 2): the unit count lives in device memory
-    const bool list_mode = (kSweep == SWEEP_F) && p.list_mode;
-    Part part = p.partS;
-    if (list_mode) {
-        part.total = static_cast<long long>(p.iscal[2]) * p.nJ;
-        part.G = gridDim.x;
-    }
-    const int deg = (kSweep == SWEEP_F) ? (list_mode ? max(p.iscal[0], p.iscal[1]) : p.iscal[0]) : 0;
+    for (int j = threadIdx.x; j < p.nJ; j += kThreads) sInfo[j] = p.binfo[j];
+    const Part& part = p.partS;
+    const int deg = (kSweep == SWEEP_P) ? p.iscal[0] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    auto unit_of = [&](int U) { return list_mode ? p.unit_list[U] : U; };
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // TMEM map: row block g of the pair as the bf16 A operand at columns [64 g, 64 g + 64); three 128-column fp32
+    // accumulator buffers at 128, 256, 384.  Job j = 2 * tile + g uses buffer j % 3.
+    const uint32_t tAcc = tmem + 128;
 
     if (warp == kProducerWarp) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ TMA producer
-            TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
-            int U, J, curU = -1, it = 0, seg = 0;
-            bool last;
-            while (iter.next(U, J, last)) {
-                if (U != curU) {
-                    const int Ua = unit_of(U);
-                    const bool two = 2 * Ua + 1 < p.nI;
-                    mbar_wait(b_iempty, (seg & 1) ^ 1);
-                    mbar_arrive_expect_tx(b_ifull, two ? 2 * kTileBytes : kTileBytes);
-                    tma_bulk_g2s(sI, p.tiles + static_cast<size_t>(p.rb0 + 2 * Ua) * kTileBytes,
-                                 two ? 2 * kTileBytes : kTileBytes, b_ifull);   // the pair is contiguous
-                    curU = U;
-                    ++seg;
-                }
-                const int slot = it & 3;
-                trace_stamp(p, 0, it, 0);
-                mbar_wait(b_empty + 8 * slot, ((it >> 2) & 1) ^ 1);
-                trace_stamp(p, 0, it, 1);
+        // ---------------------------------------------------------------------- TMA producer (column blocks only)
+        TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
+        int U, J, it = 0;
+        bool last;
+        while (iter.next(U, J, last)) {
+            const int slot = it % kSlots;
+            if (lane == 0) trace_stamp(p, 0, it, 0);
+            mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
+            if (lane == 0) trace_stamp(p, 0, it, 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes);
                 tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(J) * kTileBytes,
                              kTileBytes, b_full + 8 * slot);
-                ++it;
             }
+            __syncwarp();
+            ++it;
         }
     } else if (warp >= kIssuerWarp0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer of group g
-            const int g = warp - kIssuerWarp0;
+        {
+            // ------------------------------------------------------------------ MMA issuer s (whole warp, see elect_one)
+            // tcgen05.mma issue blocks its thread while the tensor pipe drains and every barrier wait costs
+            // 150-200 clocks, so two issuers alternate bursts: issuer s owns the tiles with it % 2 == s (16 MMAs:
+            // both row blocks of the pair) and does its waits for the next burst while the other one's burst
+            // executes.  The turn is handed over two MMAs before the end of a burst (bursts touch different
+            // accumulators, so their tails may interleave).  A comes from TMEM (TS form): with both operands in
+            // shared memory a 128x128x16 MMA needs the full 128 B/clk of shared-memory bandwidth and the TMA
+            // writes of the next tiles push it to ~110 clk per MMA (profiles/r01f_*).
+            const int s = warp - kIssuerWarp0;
             TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
             const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
-            // descriptors are built once; a slot only shifts the 16-byte-granular start address
-            uint64_t dI[8], dJ0[8];
+            uint64_t dJ0[8];                         // built once; a slot only shifts the start address
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                dI[k] = ftile_desc_kmajor(sI + g * kTileBytes, k);
-                dJ0[k] = ftile_desc_kmajor(sJ, k);
-            }
-            int U, J, curU = -1, it = 0, seg = 0;
-            bool last, have = false;
+            for (int k = 0; k < 8; ++k) dJ0[k] = ftile_desc_kmajor(sJ, k);
+            int U, J, curU = -1, it = 0, seg = 0, turn = 0;
+            bool last, two = false;
             while (iter.next(U, J, last)) {
                 if (U != curU) {
-                    mbar_wait(b_ifull, seg & 1);
-                    have = 2 * unit_of(U) + g < p.nI;
+                    // BOTH issuers wait for every unit's row blocks (a waiter that skipped a phase would alias
+                    // the 1-bit parity) and acknowledge, so the epilogue never runs two phases ahead of one
+                    two = 2 * U + 1 < p.nI;
                     curU = U;
+                    mbar_wait(b_afull, seg & 1);
+                    mbar_wait(b_afull + 8, seg & 1);
+                    if (elect_one()) mbar_arrive(b_aseen);
+                    __syncwarp();
                     ++seg;
                 }
-                const int slot = it & 3, st = it & 1;
-                trace_stamp(p, 1 + g, it, 0);
-                mbar_wait(b_full + 8 * slot, (it >> 2) & 1);
-                trace_stamp(p, 1 + g, it, 1);
-                mbar_wait(b_tempty + 8 * (st * 2 + g), ((it >> 1) & 1) ^ 1);
-                trace_stamp(p, 1 + g, it, 2);
-                tc_fence_after();
-                const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
-                if (have && !(p.debug & 2)) {
+                if ((it & 1) == s) {
+                    const int slot = it % kSlots;
+                    const int j0 = 2 * it, j1 = 2 * it + 1;
+                    const int b0 = j0 % 3, b1 = j1 % 3;
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 0);
+                    mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 1);
+                    mbar_wait(b_tempty + 8 * b0, ((j0 / 3) & 1) ^ 1);
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 2);
+                    mbar_wait(b_turn + 8 * s, (turn & 1) ^ (s == 0 ? 1 : 0));
+                    ++turn;
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 4);
+                    tc_fence_after();
+                    const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
+                    const bool run = !(p.debug & 2);
+                    if (elect_one()) {
+                        if (run) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_ss(tmem + (st * 2 + g) * 128, dI[k], dJ0[k] + soff, idesc, k > 0);
+                            for (int k = 0; k < 8; ++k) umma_ts(tAcc + b0 * 128, tmem + k * 8, dJ0[k] + soff, idesc, k > 0);
+                        }
+                        tc_commit(b_tfull + 8 * b0);
+                    }
+                    __syncwarp();
+                    // the second buffer was released by the job three before it (same tile parity, other group):
+                    // waiting for it only now lets that epilogue overlap the MMAs above
+                    mbar_wait(b_tempty + 8 * b1, ((j1 / 3) & 1) ^ 1);
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 5);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (run && two) {
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, k > 0);
+                        }
+                        mbar_arrive(b_turn + 8 * (s ^ 1));
+                        if (run && two) {
+#pragma unroll
+                            for (int k = 6; k < 8; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, true);
+                        }
+                        tc_commit(b_tfull + 8 * b1);
+                        tc_commit(b_empty + 8 * slot);
+                    }
+                    __syncwarp();
+                    if (lane == 0) trace_stamp(p, 1 + s, it, 3);
                 }
-                tc_commit(b_tfull + 8 * (st * 2 + g));
-                tc_commit(b_empty + 8 * slot);
-                if (kSweep != SWEEP_C && last) tc_commit(b_iempty);
-                trace_stamp(p, 1 + g, it, 3);
                 ++it;
             }
         }
@@ -757,22 +779,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         int U, J, curU = -1, it = 0;
         bool last, valid = false;
         float acc0[4], acc1[4], acc2[4], acc3[4];
-        f32x2 accE[4], accS[4], dd[5];
-        float dsc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f, mx = -FLT_MAX, chk_lim = 0.f;
-        int yi = -1, gi = -1, Iloc = 0, lrow = 0;
+        f32x2 q3[4], q4[4], q5[4];                         // SWEEP_P: packed sums of s^3, s^4, s^5
+        float mx4[4];
+        float mV0 = 0.f, mV1 = 0.f, mV2 = 0.f, mN0 = 0.f, mN1 = 0.f, mN2 = 0.f;   // SWEEP_P masked-tile sums
+        float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f;
+        int yi = -1, gi = -1, Iloc = 0, lrow = 0, nunits = 0;
         int2 rI = make_int2(INT_MAX, -1);
-#pragma unroll
-        for (int d = 0; d < 5; ++d) dd[d] = 0ull;
 
         auto reset = [&]() {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 acc0[u] = (kSweep == SWEEP_A) ? -FLT_MAX : 0.f;
                 acc1[u] = acc2[u] = acc3[u] = 0.f;
-                accE[u] = accS[u] = 0ull;
+                q3[u] = q4[u] = q5[u] = 0ull;
+                mx4[u] = -FLT_MAX;
             }
-            mx = -FLT_MAX;
+            mV0 = mV1 = mV2 = mN0 = mN1 = mN2 = 0.f;
         };
         auto flush = [&]() {
             if (!valid) return;
@@ -786,16 +808,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 p.pB[(static_cast<size_t>(Iloc) * p.maxsegS + seg) * 128 + r] =
                     make_float2((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
                                 (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]));
-            } else if (kSweep == SWEEP_F) {
-                const float se = (sum2(accE[0]) + sum2(accE[1])) + (sum2(accE[2]) + sum2(accE[3])) +
-                                 ((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]));
-                const float ss = (sum2(accS[0]) + sum2(accS[1])) + (sum2(accS[2]) + sum2(accS[3])) +
-                                 ((acc1[0] + acc1[1]) + (acc1[2] + acc1[3]));
-                const float4 o = make_float4(se, ss, mx, 0.f);
-                if (list_mode)
-                    p.pF2[(static_cast<size_t>(part.first_cta(curU) + curU + seg) * 2 + g) * 128 + r] = o;
-                else
-                    p.pF[(static_cast<size_t>(Iloc) * p.maxsegS + seg) * 128 + r] = o;
+            } else if (kSweep == SWEEP_P) {
+                float4* o = p.pF + ((static_cast<size_t>(Iloc) * p.maxsegS + seg) * 3) * 128 + r;
+                o[0] = make_float4(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])),
+                                   (sum2(q3[0]) + sum2(q3[1])) + (sum2(q3[2]) + sum2(q3[3])) + ((acc0[0] + acc0[1]) + (acc0[2] + acc0[3])),
+                                   (sum2(q4[0]) + sum2(q4[1])) + (sum2(q4[2]) + sum2(q4[3])) + ((acc1[0] + acc1[1]) + (acc1[2] + acc1[3])),
+                                   (sum2(q5[0]) + sum2(q5[1])) + (sum2(q5[2]) + sum2(q5[3])) + ((acc2[0] + acc2[1]) + (acc2[2] + acc2[3])));
+                o[128] = make_float4(mV0, mV1, mV2, mN0);
+                o[256] = make_float4(mN1, mN2, 0.f, 0.f);
             } else {
                 p.pC[(static_cast<size_t>(Iloc) * p.splitc + (blockIdx.x % p.splitc)) * 128 + r] =
                     make_float4((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
@@ -806,8 +826,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         };
         auto begin_segment = [&](int nU) {
             curU = nU;
-            Iloc = 2 * unit_of(nU) + g;
+            Iloc = 2 * nU + g;
             valid = Iloc < p.nI;
+            // Row block -> TMEM as the A operand (bf16 pairs, channel order).  Every MMA that read the previous
+            // block has completed: this group has consumed the accumulators of all its earlier jobs.
+            if (valid) {
+                const uint8_t* trow = p.tiles + static_cast<size_t>(p.rb0 + Iloc) * kTileBytes + r * 128;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 2; ++c4) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int c = c4 * 4 + cc;
+                            const uint4 x = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes + ((c ^ (r & 7)) << 4)));
+                            w[cc * 4 + 0] = x.x; w[cc * 4 + 1] = x.y; w[cc * 4 + 2] = x.z; w[cc * 4 + 3] = x.w;
+                        }
+                        tmem_st16(tmem + lane_off + g * 64 + h * 32 + c4 * 16, w);
+                    }
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            if (nunits > 0) mbar_wait(b_aseen, (nunits - 1) & 1);   // both issuers are past the previous unit's wait
+            ++nunits;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_afull + 8 * g);
             if (!valid) return;
             lrow = Iloc * 128 + r;
             gi = (p.rb0 + Iloc) * 128 + r;
@@ -816,15 +861,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             rI = make_int2(bi.x, bi.y);
             if (kSweep == SWEEP_A) {
                 cshift = p.sqnorm[gi];
-            } else if (kSweep == SWEEP_F) {
-                const float4 c0 = *reinterpret_cast<const float4*>(p.rowc + static_cast<size_t>(lrow) * 8);
-                const float4 c1 = *reinterpret_cast<const float4*>(p.rowc + static_cast<size_t>(lrow) * 8 + 4);
-                dsc[0] = c0.x; dsc[1] = c0.y; dsc[2] = c0.z; dsc[3] = c0.w; dsc[4] = c1.x;
-#pragma unroll
-                for (int d = 0; d < 5; ++d) dd[d] = pack2(dsc[d], dsc[d]);
-                // a tile needs the max check unless max_k c_k <= min_i c_i (1 + tol)^2  (Cauchy-Schwarz)
-                chk_lim = sNorm[p.rb0 + Iloc].y * ((1.0f + kSpecTol) * (1.0f + kSpecTol) * (1.0f - 1e-6f));
-                if (list_mode) chk_lim = FLT_MAX;         // pass 2 runs with the exact maximum
+            } else if (kSweep == SWEEP_P) {
+                // no per-row constants: the sweep only needs the row's label
             } else {
                 const float4 rs = p.rowS[lrow];
                 ra = rs.x;
@@ -840,50 +878,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 if (curU >= 0) flush();
                 begin_segment(U);
             }
-            const int st = it & 1;
+            const int job = 2 * it + g, buf = job % 3;
             if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 0);
-            mbar_wait(b_tfull + 8 * (st * 2 + g), (it >> 1) & 1);
+            mbar_wait(b_tfull + 8 * buf, (job / 3) & 1);
             if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 1);
             tc_fence_after();
             const int col0 = J * 128;
             const int4 bj = sInfo[J];
             const int2 rJ = make_int2(bj.x, bj.y);
             const bool all_valid = bj.z == 128;
-            const uint32_t taddr = tmem + (st * 2 + g) * 128 + lane_off;
+            const uint32_t taddr = tAcc + buf * 128 + lane_off;
             const int32_t* yJ = p.y + col0;
 
             if (!valid || (p.debug & 1)) {
                 // odd tail: this group has no row block; just release the stage
-            } else if (kSweep == SWEEP_F) {
+            } else if (kSweep == SWEEP_P) {
                 const bool fast = all_valid && !ranges_overlap(rI, rJ);
-                const bool chk = sNorm[J].x > chk_lim;
                 if (fast) {
-                    if (deg == 2) {
-                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<2, false>(v, dd, accE, accS, mx); });
-                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<2, true>(v, dd, accE, accS, mx); });
-                    } else if (deg == 3) {
-                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<3, false>(v, dd, accE, accS, mx); });
-                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<3, true>(v, dd, accE, accS, mx); });
-                    } else {
-                        if (!chk) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<4, false>(v, dd, accE, accS, mx); });
-                        else      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { fsweep_chunk<4, true>(v, dd, accE, accS, mx); });
-                    }
+                    if (deg == 2)      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<2>(v, q3, q4, q5, mx4); });
+                    else if (deg == 3) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<3>(v, q3, q4, q5, mx4); });
+                    else               for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<4>(v, q3, q4, q5, mx4); });
                 } else {
-                    // masked tile: negatives feed the sums, every valid column feeds the max
+                    // masked tile: every valid column feeds the max and V0..V2 (to be removed from the closed-form
+                    // totals), the negatives feed N0..N2 and the higher power sums
                     for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float s = __uint_as_float(v[j]);
                             const int yj = __ldg(yJ + c0 + j);
-                            float e = fmaf(dsc[4], s, dsc[3]);
-                            e = fmaf(e, s, dsc[2]);
-                            e = fmaf(e, s, dsc[1]);
-                            e = fmaf(e, s, dsc[0]);
+                            const float s2 = s * s;
                             if (yj >= 0) {
-                                mx = fmaxf(mx, s);
+                                mx4[j & 3] = fmaxf(mx4[j & 3], s);
+                                mV0 += 1.f;
+                                mV1 += s;
+                                mV2 += s2;
                                 if (yj != yi) {
-                                    acc0[j & 3] += e;
-                                    acc1[j & 3] = fmaf(e, s, acc1[j & 3]);
+                                    mN0 += 1.f;
+                                    mN1 += s;
+                                    mN2 += s2;
+                                    acc0[j & 3] = fmaf(s2, s, acc0[j & 3]);
+                                    acc1[j & 3] = fmaf(s2, s2, acc1[j & 3]);
+                                    acc2[j & 3] = fmaf(s2 * s, s2, acc2[j & 3]);
                                 }
                             }
                         }
@@ -971,7 +1006,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_tempty + 8 * (st * 2 + g));
+            if (lane == 0) mbar_arrive(b_tempty + 8 * buf);
             if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 2);
             ++it;
         }
@@ -1018,72 +1053,49 @@ __global__ void __launch_bounds__(128) k_combine_B(const Params p) {
 }
 
 // =============================================================================================
-// v3: verify the speculated maxima, build the list of row pairs to re-sweep, combine the partials
+// v3: per row, power sums + exact maximum -> kappa, the exponential polynomial, Den and Bt
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_check(const Params p) {
+__global__ void __launch_bounds__(128) k_combine_P(const Params p) {
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
     const int ns = p.partS.nseg(I >> 1);
     float mx = -FLT_MAX;
-    for (int s = 0; s < ns; ++s) mx = fmaxf(mx, p.pF[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r].z);
-    const float thr = p.rowc[static_cast<size_t>(lrow) * 8 + 5];
-    const bool flagged = p.y[gi] >= 0 && mx > thr;
-    if (flagged) {
-        // exact maximum known (the violating tiles were all checked): redo the row's scale and polynomial
-        const float2 q = p.rowq[lrow];
-        const double c = p.sqnorm[gi], m = mx;
-        double kappa, L;
-        row_scale(q.x, q.y, m, c, p.scal[0], p.n_valid, p.T, kappa, L);
-        const int deg = write_rowc(p, lrow, kappa, m, L, FLT_MAX);
-        p.rowS[lrow] = make_float4(static_cast<float>(kappa * kLog2e), static_cast<float>(-m * kappa * kLog2e),
-                                   static_cast<float>(kappa), static_cast<float>(m));
-        if (deg > 2) atomicMax(&p.iscal[1], deg);
-        p.unit_flag[I >> 1] = 1;          // same value from every flagged row
+    double Q[3] = {0.0, 0.0, 0.0}, V[3] = {0.0, 0.0, 0.0}, Nn[3] = {0.0, 0.0, 0.0};
+    for (int s = 0; s < ns; ++s) {
+        const float4* o = p.pF + ((static_cast<size_t>(I) * p.maxsegS + s) * 3) * 128 + r;
+        const float4 a = o[0], b = o[128], c = o[256];
+        mx = fmaxf(mx, a.x);
+        Q[0] += a.y; Q[1] += a.z; Q[2] += a.w;
+        V[0] += b.x; V[1] += b.y; V[2] += b.z;
+        Nn[0] += b.w; Nn[1] += c.x; Nn[2] += c.y;
     }
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (r == 0) is_last = atomicAdd(p.ticket + 1, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (is_last && r == 0) {
-        __threadfence();
-        const volatile int* fl = p.unit_flag;
-        int n = 0;
-        for (int u = 0; u < p.nP; ++u)
-            if (fl[u]) p.unit_list[n++] = u;
-        p.iscal[2] = n;
+    if (p.y[gi] < 0) {
+        p.rowS[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.rowD[lrow] = make_float4(1.f, 0.f, 0.f, 0.f);
+        return;
     }
-}
-
-__global__ void __launch_bounds__(128) k_combine_F(const Params p) {
-    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
-    const int U = I >> 1, g = I & 1;
+    const float2 q = p.rowq[lrow];
+    const double qf = q.x, fm = q.y, n = p.n_valid, m = mx, c = p.sqnorm[gi];
+    double kappa, L;
+    row_scale(qf, fm, m, c, p.scal[0], p.n_valid, p.T, kappa, L);
+    double d[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
+    if (kappa > 0.0) {
+        int deg = poly_degree_for(L);
+        const int swept = p.iscal[0];             // the sweep produced power sums up to s^{swept+1}
+        if (deg > swept) deg = swept;             // cannot happen: logit_range_bound() covers every m >= c
+        exp_poly_in_s(kappa, m, L, deg, d);
+    }
+    // power sums over the negatives: closed-form totals minus the masked tiles' columns, plus their negatives
+    double P[6];
+    P[0] = (n - V[0]) + Nn[0];
+    P[1] = (n * fm - V[1]) + Nn[1];
+    P[2] = (qf + n * fm * fm - V[2]) + Nn[2];
+    P[3] = Q[0]; P[4] = Q[1]; P[5] = Q[2];
     double se = 0.0, ss = 0.0;
-    if (p.unit_flag[U]) {
-        // position of the unit in the list = number of flagged units before it
-        int pos = 0;
-        for (int u = 0; u < U; ++u) pos += p.unit_flag[u] != 0;
-        Part part = p.partS;
-        part.total = static_cast<long long>(p.iscal[2]) * p.nJ;
-        part.G = p.ctas;
-        const int fc = part.first_cta(pos), ns = part.nseg(pos);
-        for (int s = 0; s < ns; ++s) {
-            const float4 v = p.pF2[(static_cast<size_t>(fc + pos + s) * 2 + g) * 128 + r];
-            se += v.x;
-            ss += v.y;
-        }
-    } else {
-        const int ns = p.partS.nseg(U);
-        for (int s = 0; s < ns; ++s) {
-            const float4 v = p.pF[(static_cast<size_t>(I) * p.maxsegS + s) * 128 + r];
-            se += v.x;
-            ss += v.y;
-        }
-    }
-    const float4 rs = p.rowS[lrow];                 // (a, b, kappa, m)
-    const float L = p.rowc[static_cast<size_t>(lrow) * 8 + 7];
+    for (int j = 0; j < 5; ++j) { se += d[j] * P[j]; ss += d[j] * P[j + 1]; }
+    const double a = kappa * static_cast<double>(kLog2e);
+    p.rowS[lrow] = make_float4(static_cast<float>(a), static_cast<float>(-m * a), static_cast<float>(kappa), static_cast<float>(m));
     // Bt = sum_den E t = log2(e) kappa (sum E s - m sum E)
-    const double bt = static_cast<double>(rs.x) * (ss - static_cast<double>(rs.w) * se);
-    p.rowD[lrow] = make_float4(static_cast<float>(se), static_cast<float>(bt), L, 0.f);
+    p.rowD[lrow] = make_float4(static_cast<float>(se), static_cast<float>(a * (ss - m * se)), static_cast<float>(L), 0.f);
 }
 
 // =============================================================================================
@@ -1233,7 +1245,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104, b_sfree = bar + 128,
                    b_dfull = bar + 152, b_dempty = bar + 160, b_ifull = bar + 168, b_iempty = bar + 176;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemBwd::kTmem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (warp == kProducerWarp) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
     if (threadIdx.x == kIssuerWarp0 * 32) {
@@ -1260,27 +1272,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tD = tmem + 384;          // dF accumulator; S/G stage st lives at tmem + st*128
 
     if (warp == kProducerWarp) {
-        if (lane == 0) {
-            TileIter<false> iter(p, p.partD, nullptr);
-            int I, J, curI = -1, it = 0, seg = 0;
-            bool last;
-            while (iter.next(I, J, last)) {
-                if (I != curI) {
-                    mbar_wait(b_iempty, (seg & 1) ^ 1);
+        // whole warp runs the (uniform) control flow; the bulk copies are issued by one elected lane (see elect_one)
+        TileIter<false> iter(p, p.partD, nullptr);
+        int I, J, curI = -1, it = 0, seg = 0;
+        bool last;
+        while (iter.next(I, J, last)) {
+            if (I != curI) {
+                mbar_wait(b_iempty, (seg & 1) ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(b_ifull, kTileBytes);
-                    tma_bulk_g2s(sI, p.tiles + static_cast<size_t>(p.rb0 + I) * kTileBytes, kTileBytes,
-                                 b_ifull);
-                    curI = I;
-                    ++seg;
+                    tma_bulk_g2s(sI, p.tiles + static_cast<size_t>(p.rb0 + I) * kTileBytes, kTileBytes, b_ifull);
                 }
-                const int slot = it % kSlots;
-                trace_stamp(p, 0, it, 0);
-                mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
-                trace_stamp(p, 0, it, 1);
+                __syncwarp();
+                curI = I;
+                ++seg;
+            }
+            const int slot = it % kSlots;
+            if (lane == 0) trace_stamp(p, 0, it, 0);
+            mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
+            if (lane == 0) trace_stamp(p, 0, it, 1);
+            if (elect_one()) {
                 if (kMode == DCL_MODE_PIXEL) {
                     mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes + SmemBwd::kCoefBytes);
                     tma_bulk_g2s(sCP + slot * SmemBwd::kCoefBytes,
@@ -1291,11 +1306,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 }
                 tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(J) * kTileBytes,
                              kTileBytes, b_full + 8 * slot);
-                ++it;
             }
+            __syncwarp();
+            ++it;
         }
     } else if (warp == kIssuerWarp0) {
-        if (lane == 0) {
+        {
             // ------------------------------------------------------------------ issuer 0: S = F_I F_J^T
             TileIter<false> iter(p, p.partD, nullptr);
             const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
@@ -1314,25 +1330,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                     ++seg;
                 }
                 const int slot = it % kSlots, st = it % kStages;
-                trace_stamp(p, 1, it, 0);
+                if (lane == 0) trace_stamp(p, 1, it, 0);
                 mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
-                trace_stamp(p, 1, it, 1);
+                if (lane == 0) trace_stamp(p, 1, it, 1);
                 mbar_wait(b_sfree + 8 * st, ((it / kStages) & 1) ^ 1);     // G(it-3) consumed
-                trace_stamp(p, 1, it, 2);
+                if (lane == 0) trace_stamp(p, 1, it, 2);
                 tc_fence_after();
                 const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
-                if (!(p.debug & 2)) {
+                if (elect_one()) {
+                    if (!(p.debug & 2)) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) umma_ss(tmem + st * 128, dI[k], dJk[k] + soff, idesc_s, k > 0);
+                        for (int k = 0; k < 8; ++k) umma_ss(tmem + st * 128, dI[k], dJk[k] + soff, idesc_s, k > 0);
+                    }
+                    tc_commit(b_tfull + 8 * st);
+                    if (last) tc_commit(b_iempty);
                 }
-                tc_commit(b_tfull + 8 * st);
-                if (last) tc_commit(b_iempty);
-                trace_stamp(p, 1, it, 3);
+                __syncwarp();
+                if (lane == 0) trace_stamp(p, 1, it, 3);
                 ++it;
             }
         }
     } else if (warp == kIssuerWarp0 + 1) {
-        if (lane == 0) {
+        {
             // ------------------------------------------------------------------ issuer 1: dF_I += G F_J
             TileIter<false> iter(p, p.partD, nullptr);
             const uint32_t idesc_d = umma_idesc_bf16(128, 128, 0, 1);   // B = F_J, MN-major
@@ -1345,21 +1364,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 const bool first = (I != curI);
                 curI = I;
                 const int slot = it % kSlots, st = it % kStages;
-                trace_stamp(p, 2, it, 0);
+                if (lane == 0) trace_stamp(p, 2, it, 0);
                 mbar_wait(b_pfull + 8 * st, (it / kStages) & 1);
-                trace_stamp(p, 2, it, 1);
+                if (lane == 0) trace_stamp(p, 2, it, 1);
                 if (first && seg > 0) mbar_wait(b_dempty, (seg - 1) & 1);
                 tc_fence_after();
                 const uint64_t poff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
-                if (!(p.debug & 4)) {
+                if (elect_one()) {
+                    if (!(p.debug & 4)) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_ts(tD, tmem + st * 128 + k * 8, dJm[k] + poff, idesc_d, (!first) || k > 0);
+                        for (int k = 0; k < 8; ++k)
+                            umma_ts(tD, tmem + st * 128 + k * 8, dJm[k] + poff, idesc_d, (!first) || k > 0);
+                    }
+                    tc_commit(b_empty + 8 * slot);
+                    tc_commit(b_sfree + 8 * st);
+                    if (last) tc_commit(b_dfull);
                 }
-                tc_commit(b_empty + 8 * slot);
-                tc_commit(b_sfree + 8 * st);
-                if (last) { tc_commit(b_dfull); ++seg; }
-                trace_stamp(p, 2, it, 2);
+                __syncwarp();
+                if (last) ++seg;
+                if (lane == 0) trace_stamp(p, 2, it, 2);
                 ++it;
             }
         }
@@ -1538,7 +1561,7 @@ struct Layout {
     Part partS, partD;
     int nP, maxsegS, maxsegD, splitc, gramP, ctas;
     size_t off_binfo, off_bnorm, off_pA, off_pB, off_gram, off_fsum, off_cmaxp, off_ref, off_Mc, off_mu, off_scal,
-        off_iscal, off_rowq, off_rowc, off_pF, off_pF2, off_uflag, off_ulist, off_rowS, off_rowD, off_pC, off_bl,
+        off_iscal, off_rowq, off_pF, off_rowS, off_rowD, off_pC, off_bl,
         off_ticket, off_coefR, off_coefP, off_pD, bytes;
 };
 
@@ -1570,7 +1593,7 @@ static Layout make_layout(int nI, int nJ) {
     auto take = [&](size_t& off, size_t bytes) { off = o; o = align_up(o + bytes, 256); };
     take(L.off_binfo, sizeof(int4) * nJ);
     take(L.off_bnorm, sizeof(float2) * nJ);
-    take(L.off_pA, sizeof(float4) * rows * L.maxsegS);        // legacy A partials; the v3 pass-1 partials (pF) share it
+    take(L.off_pA, sizeof(float4) * rows * L.maxsegS * 3);    // legacy A partials; the v3 power-sum partials (pF) share it
     take(L.off_pB, sizeof(float2) * rows * L.maxsegS);
     take(L.off_gram, sizeof(float) * 16384 * static_cast<size_t>(L.gramP));
     take(L.off_fsum, sizeof(float) * 128 * L.gramP);
@@ -1581,11 +1604,7 @@ static Layout make_layout(int nI, int nJ) {
     take(L.off_scal, sizeof(float) * 8);
     take(L.off_iscal, sizeof(int) * 8);
     take(L.off_rowq, sizeof(float2) * rows);
-    take(L.off_rowc, sizeof(float) * 8 * rows);
     L.off_pF = L.off_pA;
-    take(L.off_pF2, sizeof(float4) * 256 * static_cast<size_t>(ctas + L.nP + 2));
-    take(L.off_uflag, sizeof(int) * L.nP);
-    take(L.off_ulist, sizeof(int) * L.nP);
     take(L.off_rowS, sizeof(float4) * rows);
     take(L.off_rowD, sizeof(float4) * rows);
     take(L.off_pC, sizeof(float4) * rows * L.splitc);
@@ -1626,11 +1645,7 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.scal = reinterpret_cast<float*>(w + L.off_scal);
     p.iscal = reinterpret_cast<int*>(w + L.off_iscal);
     p.rowq = reinterpret_cast<float2*>(w + L.off_rowq);
-    p.rowc = reinterpret_cast<float*>(w + L.off_rowc);
     p.pF = reinterpret_cast<float4*>(w + L.off_pF);
-    p.pF2 = reinterpret_cast<float4*>(w + L.off_pF2);
-    p.unit_flag = reinterpret_cast<int*>(w + L.off_uflag);
-    p.unit_list = reinterpret_cast<int*>(w + L.off_ulist);
     p.rowS = reinterpret_cast<float4*>(w + L.off_rowS);
     p.rowD = reinterpret_cast<float4*>(w + L.off_rowD);
     p.pC = reinterpret_cast<float4*>(w + L.off_pC);
@@ -1653,14 +1668,13 @@ static int set_smem(K kernel, int bytes) {
 constexpr int kGramSmem = 128 * kGramLd * 4;
 constexpr int kRowstatSmem = 2 * 128 * kGramLd * 4;
 
-// v3 pixel forward: closed-form row norms, one fused sweep (+ a list-mode re-sweep that exits at once when the
-// speculation held everywhere), sweep C, finalize
+// v3 pixel forward: closed-form row norms, one power-sum sweep, per-row combination, sweep C, finalize
 static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (int e = set_smem(k_gram, kGramSmem)) return e;
         if (int e = set_smem(k_rowstats, kRowstatSmem)) return e;
-        if (int e = set_smem(k_sweep<SWEEP_F, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
+        if (int e = set_smem(k_sweep<SWEEP_P, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
         if (int e = set_smem(k_sweep<SWEEP_C, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
         configured = true;
     }
@@ -1670,17 +1684,10 @@ static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
     DCL_LAUNCH_CHECK("k_gram_reduce");
     k_rowstats<<<p.nI, 256, kRowstatSmem, st>>>(p);
     DCL_LAUNCH_CHECK("k_rowstats");
-    p.list_mode = 0;
-    k_sweep<SWEEP_F, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<F>");
-    k_check<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_check");
-    p.list_mode = 1;
-    k_sweep<SWEEP_F, DCL_MODE_PIXEL><<<L.ctas, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<F2>");
-    p.list_mode = 0;
-    k_combine_F<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine_F");
+    k_sweep<SWEEP_P, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
+    DCL_LAUNCH_CHECK("k_sweep<P>");
+    k_combine_P<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine_P");
     k_sweep<SWEEP_C, DCL_MODE_PIXEL><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<C>");
     k_finalize<DCL_MODE_PIXEL><<<p.nI, 128, 0, st>>>(p);
@@ -1755,7 +1762,7 @@ extern "C" int dcl_debug_trace(void* device_buffer) {
 // kernels launched by one forward (backward != 0: one backward) call for `mode` with the current debug flags
 extern "C" int dcl_contrast_launches(int mode, int backward) {
     if (backward) return mode == DCL_MODE_PIXEL ? 4 : 3;
-    return (mode == DCL_MODE_PIXEL && !(g_debug_flags & 8)) ? 9 : 7;
+    return 7;
 }
 
 extern "C" size_t dcl_contrast_workspace_bytes(int nI, int nJ) {

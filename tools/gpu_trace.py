@@ -14,6 +14,7 @@ nJ = n // 128
 colA, colB, rl, ls = L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
 for _ in range(2):
     L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
+lib.dcl_debug_flags(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 buf = torch.zeros(5 * 32 * 8, dtype=torch.int64, device="cuda")
 lib.dcl_debug_trace(buf.data_ptr())
 L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
@@ -21,7 +22,8 @@ torch.cuda.synchronize()
 lib.dcl_debug_trace(None)
 t = buf.cpu().view(5, 32, 8)
 t0 = int(t[t > 0].min())
-print("tile | producer: wait_empty got_empty | mma: wait_full got_full wait_pfull got_pfull | epilogue: start got_tfull done   (clk since first stamp)")
-for it in range(24):
+print("tile | prod: wait_e got_e | issS: wait_full got_full got_sfree issued | issD: wait_pfull got_pfull issued | g0: start got_tfull done | g1: start got_tfull done")
+for it in range(28):
     r = lambda role, ev: (int(t[role, it, ev]) - t0) if int(t[role, it, ev]) else -1
-    print(f"{it:4d} | {r(0,0):7d} {r(0,1):7d} | {r(1,0):7d} {r(1,1):7d} {r(1,2):7d} {r(1,3):7d} | {r(2,0):7d} {r(2,1):7d} {r(2,2):7d}")
+    print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(1,0):6d} {r(1,1):6d} {r(1,2):6d} {r(1,3):6d} | {r(2,0):6d} {r(2,1):6d} {r(2,2):6d} | "
+          f"{r(3,0):6d} {r(3,1):6d} {r(3,2):6d} | {r(4,0):6d} {r(4,1):6d} {r(4,2):6d}")
