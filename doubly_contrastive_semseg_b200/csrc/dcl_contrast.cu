@@ -35,6 +35,7 @@
 // that crosses a row-unit boundary flushes a deterministic partial ("segment") instead of using atomics, so results
 // are bit-reproducible.
 #include <cfloat>
+#include <type_traits>
 #include <cuda_bf16.h>
 #include "dcl_common.cuh"
 #include "dcl_ptx.cuh"
@@ -102,8 +103,10 @@ struct Params {
     float* pD;               // [nI][maxsegD][128][128] dF partials
     float4* colA;            // [nJ*128] (a, b, p, q)
     float4* colB;            // [nJ*128] (wn, Den, y bits, L)
-    float* coefR;            // [nJ*128][8] backward row polynomial rp (r0..r4, 0, 0, 0)
-    float* coefP;            // [nJ*64][12] the same, pair-interleaved for the column side
+    float* coefR;            // [nJ*128][16] backward row polynomials (n0..n4 - - - p0..p4 - - -), see k_bwd_prep
+    float* coefP;            // [nJ*64][12] different-class polynomial, pair-interleaved for the column side (+ labels)
+    float* coefPP;           // [nJ*64][12] same-class polynomial, pair-interleaved
+    float* bden;             // [nJ] smallest Den of each block's valid rows
     float* rowloss;          // [nJ*128]
     float* blockloss;        // [nI]
     float* loss_sum;
@@ -209,6 +212,20 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// The same walk as a real loop (one chunk body in the instruction stream instead of four): the pipelined kernels
+// hold several alternative epilogue bodies, and unrolled they overflow the instruction cache.  The TMEM load
+// latency of a chunk is covered by the other epilogue warp of the scheduler.
+template <class Fn>
+__device__ __forceinline__ void for_each_chunk_loop(uint32_t taddr, Fn&& fn) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait_on(v);
+        fn(c0, v);
+    }
+}
+
 // diagnostics: stamp (role, tile, event) for CTA 0's first 32 tiles; roles: 0 producer, 1/2 issuers, 3/4 epilogue groups
 __device__ __forceinline__ void trace_stamp(const Params& p, int role, int it, int ev) {
     if (p.trace && blockIdx.x == 0 && it < 32) p.trace[(role * 32 + it) * 8 + ev] = clock64();
@@ -219,10 +236,11 @@ __device__ __forceinline__ bool ranges_overlap(int2 a, int2 b) { return a.x <= b
 // =============================================================================================
 // Per-row exponential polynomial.  For l = kappa (s - m) in [-L, 0]:
 //   e^l = e^{-r} e^z,  z = l + r in [-r, r],  r = L/2,   e^z ~ truncated Chebyshev series (modified Bessel I_k(r)),
-// re-expanded in s.  Truncation error ~ 2 I_{deg+1}(r): deg 2 for L <= 1/8 (1.1e-5), 3 for L <= 1/2 (2e-5), else 4
+// re-expanded in s.  Truncation error ~ 2 I_{deg+1}(r): deg 1 for L <= 0.03 (5.6e-5: the logits of a few thousand
+// anchors span so little that exp is linear to that accuracy), 2 for L <= 1/8 (1.1e-5), 3 for L <= 1/2 (2e-5), else 4
 // (1.6e-5 at L = 1).
 // =============================================================================================
-__device__ __forceinline__ int poly_degree_for(double L) { return L <= 0.125 ? 2 : (L <= 0.5 ? 3 : 4); }
+__device__ __forceinline__ int poly_degree_for(double L) { return L <= 0.03 ? 1 : (L <= 0.125 ? 2 : (L <= 0.5 ? 3 : 4)); }
 
 __device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, double (&d)[5]) {
     double r = 0.5 * L;
@@ -242,9 +260,9 @@ __device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, 
     }
     // Chebyshev -> monomials in x = z / r
     double cx[5] = {0, 0, 0, 0, 0};
-    cx[0] = a[0] - a[2];
+    cx[0] = a[0];
     cx[1] = a[1];
-    cx[2] = 2.0 * a[2];
+    if (deg >= 2) { cx[0] -= a[2]; cx[2] = 2.0 * a[2]; }
     if (deg >= 3) { cx[1] -= 3.0 * a[3]; cx[3] = 4.0 * a[3]; }
     if (deg >= 4) { cx[0] += a[4]; cx[2] -= 8.0 * a[4]; cx[4] = 8.0 * a[4]; }
     const double er = exp(-r);
@@ -448,7 +466,7 @@ __global__ void __launch_bounds__(256) k_gram_reduce(const Params p) {
             float cm = 0.f;
             for (int q = 0; q < p.gramP; ++q) cm = fmaxf(cm, p.cmax_part[q]);
             p.scal[0] = cm;
-            p.iscal[0] = 2;
+            p.iscal[0] = 1;
             p.ticket[0] = 0u;
             p.ticket[1] = 0u;
         }
@@ -514,7 +532,7 @@ __global__ void __launch_bounds__(256) k_rowstats(const Params p) {
         if (sy[tid] >= 0) {
             const double c = p.sqnorm[gi];
             const int deg = poly_degree_for(logit_range_bound(sqf[tid], fm, c, p.scal[0], p.n_valid));
-            if (deg > 2) atomicMax(&p.iscal[0], deg);
+            if (deg > 1) atomicMax(&p.iscal[0], deg);
         }
     }
 }
@@ -609,6 +627,7 @@ struct TileIter {
 
 // ---------------------------------------------------------------------------------------------
 // SWEEP_P fast-tile body for 32 columns (16 packed pairs): row max and the power sums s^3 .. s^{deg+1}
+// (degree 1 needs none: P_0..P_2 are closed forms)
 __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -619,11 +638,13 @@ __device__ __forceinline__ void psweep_chunk(const uint32_t (&v)[32], f32x2 (&q3
                                              float (&mx)[4]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
-        const f32x2 s2 = fmul2(s, s);
-        q3[j & 3] = ffma2(s2, s, q3[j & 3]);
-        if (kDeg >= 3) q4[j & 3] = ffma2(s2, s2, q4[j & 3]);
-        if (kDeg >= 4) q5[j & 3] = ffma2(fmul2(s2, s), s2, q5[j & 3]);
+        if (kDeg >= 2) {
+            const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
+            const f32x2 s2 = fmul2(s, s);
+            q3[j & 3] = ffma2(s2, s, q3[j & 3]);
+            if (kDeg >= 3) q4[j & 3] = ffma2(s2, s2, q4[j & 3]);
+            if (kDeg >= 4) q5[j & 3] = ffma2(fmul2(s2, s), s2, q5[j & 3]);
+        }
         mx[j & 3] = fmaxf(mx[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
     }
 }
@@ -895,13 +916,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             } else if (kSweep == SWEEP_P) {
                 const bool fast = all_valid && !ranges_overlap(rI, rJ);
                 if (fast) {
-                    if (deg == 2)      for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<2>(v, q3, q4, q5, mx4); });
-                    else if (deg == 3) for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<3>(v, q3, q4, q5, mx4); });
-                    else               for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<4>(v, q3, q4, q5, mx4); });
+                    if (deg == 1)      for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<1>(v, q3, q4, q5, mx4); });
+                    else if (deg == 2) for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<2>(v, q3, q4, q5, mx4); });
+                    else if (deg == 3) for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<3>(v, q3, q4, q5, mx4); });
+                    else               for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<4>(v, q3, q4, q5, mx4); });
                 } else {
                     // masked tile: every valid column feeds the max and V0..V2 (to be removed from the closed-form
                     // totals), the negatives feed N0..N2 and the higher power sums
-                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                    for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float s = __uint_as_float(v[j]);
@@ -926,7 +948,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 }
             } else if (kSweep == SWEEP_A) {
                 if (all_valid) {
-                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                    for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float x = __uint_as_float(v[j]) - cshift;
@@ -936,7 +958,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         }
                     });
                 } else {
-                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                    for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float x = __uint_as_float(v[j]) - cshift;
@@ -952,7 +974,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 const bool fast = all_valid && (kMode == DCL_MODE_PIXEL ? !ranges_overlap(rI, rJ)
                                                                         : (p.rb0 + Iloc) != J);
                 if (fast) {
-                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                    for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float t = fmaf(__uint_as_float(v[j]), ra, rb);
@@ -962,7 +984,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         }
                     });
                 } else {
-                    for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                    for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float t = fmaf(__uint_as_float(v[j]), ra, rb);
@@ -978,7 +1000,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     });
                 }
             } else if (ranges_overlap(rI, rJ)) {
-                for_each_chunk<4>(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int yj = __ldg(yJ + c0 + j);
@@ -1168,15 +1190,22 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
 // =============================================================================================
 // Backward
 // =============================================================================================
-// per row (all nJ*128 of them): the polynomial rp(s) = q E(s) + p (a s + b), in row order (coefR) and
-// pair-interleaved for the column side (coefP: [c0k c0k' c1k c1k'] [c2k c2k' c3k c3k'] [c4k c4k' 0 0])
+// Per row (all nJ*128 of them) two polynomials in s = s_ik, in row order (coefR: n0..n4 - - - p0..p4 - - -) and
+// pair-interleaved for the column side (coefP / coefPP: [c0k c0k' c1k c1k'] [c2k c2k' c3k c3k'] [c4k c4k' * *]):
+//   pairs of different classes:  rpN(s) = q E(s) + p (a s + b)
+//   pairs of the same class   :  rpP(s) = p (a s + b) + wn / (E + Den) ~ p (a s + b) + wn/Den - (wn/Den^2) E(s)
+// (first-order series in E/Den <= 1/Den; tiles use it only where every Den >= kMinDenSeries, see bden).  The two
+// spare floats of a coefP pair block hold the labels of its two columns.
+constexpr float kMinDenSeries = 64.0f;      // series error (E/Den)^2 <= 2.5e-4 of the positive-pair term
 __global__ void __launch_bounds__(128) k_bwd_prep(const Params p) {
     const int row = blockIdx.x * 128 + threadIdx.x;
     const float4 cA = p.colA[row];
     const float4 cB = p.colB[row];
-    double d[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    int deg = 2;
-    if (__float_as_int(cB.z) >= 0) {
+    const int yv = __float_as_int(cB.z);
+    double dn[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, dp[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int deg = 1;
+    float den = FLT_MAX;
+    if (yv >= 0) {
         const double a = cA.x, b = cA.y;
         double e[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
         if (a > 0.0) {
@@ -1184,47 +1213,101 @@ __global__ void __launch_bounds__(128) k_bwd_prep(const Params p) {
             deg = poly_degree_for(L);
             exp_poly_in_s(kappa, m, L, deg, e);
         }
-        for (int j = 0; j < 5; ++j) d[j] = static_cast<double>(cA.w) * e[j];
-        d[1] += static_cast<double>(cA.z) * a;
-        d[0] += static_cast<double>(cA.z) * b;
+        den = cB.y;
+        const double wn = cB.x, D = cB.y;
+        const double qP = D >= 1.0 ? -wn / (D * D) : 0.0, cP = D >= 1.0 ? wn / D : 0.0;
+        for (int j = 0; j < 5; ++j) { dn[j] = static_cast<double>(cA.w) * e[j]; dp[j] = qP * e[j]; }
+        dn[1] += static_cast<double>(cA.z) * a;
+        dn[0] += static_cast<double>(cA.z) * b;
+        dp[1] += static_cast<double>(cA.z) * a;
+        dp[0] += static_cast<double>(cA.z) * b + cP;
     }
-    float4* o = reinterpret_cast<float4*>(p.coefR + static_cast<size_t>(row) * 8);
-    o[0] = make_float4(static_cast<float>(d[0]), static_cast<float>(d[1]), static_cast<float>(d[2]), static_cast<float>(d[3]));
-    o[1] = make_float4(static_cast<float>(d[4]), 0.f, 0.f, 0.f);
-    float* cp = p.coefP + static_cast<size_t>(row >> 1) * kCoefPairFloats + (row & 1);
+    float4* o = reinterpret_cast<float4*>(p.coefR + static_cast<size_t>(row) * 16);
+    o[0] = make_float4(static_cast<float>(dn[0]), static_cast<float>(dn[1]), static_cast<float>(dn[2]), static_cast<float>(dn[3]));
+    o[1] = make_float4(static_cast<float>(dn[4]), 0.f, 0.f, 0.f);
+    o[2] = make_float4(static_cast<float>(dp[0]), static_cast<float>(dp[1]), static_cast<float>(dp[2]), static_cast<float>(dp[3]));
+    o[3] = make_float4(static_cast<float>(dp[4]), 0.f, 0.f, 0.f);
+    float* cn = p.coefP + static_cast<size_t>(row >> 1) * kCoefPairFloats + (row & 1);
+    float* cq = p.coefPP + static_cast<size_t>(row >> 1) * kCoefPairFloats + (row & 1);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) cp[2 * j] = static_cast<float>(d[j]);
-    cp[10] = 0.f;
-    if (deg > 2) atomicMax(&p.iscal[3], deg);
+    for (int j = 0; j < 5; ++j) { cn[2 * j] = static_cast<float>(dn[j]); cq[2 * j] = static_cast<float>(dp[j]); }
+    cn[10] = __int_as_float(yv);
+    cq[10] = 0.f;
+    if (deg > 1) atomicMax(&p.iscal[3], deg);
+    // smallest Den of the block's valid rows
+    for (int o2 = 16; o2 > 0; o2 >>= 1) den = fminf(den, __shfl_xor_sync(0xffffffffu, den, o2));
+    __shared__ float sden[4];
+    if ((threadIdx.x & 31) == 0) sden[threadIdx.x >> 5] = den;
+    __syncthreads();
+    if (threadIdx.x == 0) p.bden[blockIdx.x] = fminf(fminf(sden[0], sden[1]), fminf(sden[2], sden[3]));
 }
 
-// G for 32 columns of a fast tile: rp_i(s) + rp_k(s), packed bf16 into pk[16]
+// one column pair of a Horner chain on the column coefficients: h = ((c4 s + c3) s + c2) s + c1 (degree-dependent)
+template <int kDeg>
+__device__ __forceinline__ f32x2 col_horner(const float4* __restrict__ cp, const float4& q0, f32x2 s) {
+    if (kDeg == 1) return pack2(q0.z, q0.w);
+    const float4 q1 = cp[1];
+    if (kDeg == 2) return ffma2(pack2(q1.x, q1.y), s, pack2(q0.z, q0.w));
+    if (kDeg == 3) {
+        f32x2 h = ffma2(pack2(q1.z, q1.w), s, pack2(q1.x, q1.y));
+        return ffma2(h, s, pack2(q0.z, q0.w));
+    }
+    const float4 q2 = cp[2];
+    f32x2 h = ffma2(pack2(q2.x, q2.y), s, pack2(q1.z, q1.w));
+    h = ffma2(h, s, pack2(q1.x, q1.y));
+    return ffma2(h, s, pack2(q0.z, q0.w));
+}
+template <int kDeg>
+__device__ __forceinline__ f32x2 row_horner(const f32x2 (&rr)[5], f32x2 s) {
+    if (kDeg == 1) return ffma2(rr[1], s, rr[0]);
+    f32x2 g = ffma2(rr[kDeg], s, rr[kDeg - 1]);
+#pragma unroll
+    for (int d = kDeg - 2; d >= 0; --d) g = ffma2(g, s, rr[d]);
+    return g;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) {
+    float lo, hi;
+    unpack2(v, lo, hi);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&b2);
+}
+
+// G for 32 columns of a tile without same-class pairs: rpN_i(s) + rpN_k(s), packed bf16 into pk[16]
 template <int kDeg>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], const f32x2 (&rr)[5], const float4* __restrict__ cp,
                                           uint32_t (&pk)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
-        const float4 q0 = cp[3 * j], q1 = cp[3 * j + 1];
-        f32x2 gsum = ffma2(rr[kDeg], s, rr[kDeg - 1]);
+        const float4 q0 = cp[3 * j];
+        f32x2 g = ffma2(col_horner<kDeg>(cp + 3 * j, q0, s), s, row_horner<kDeg>(rr, s));
+        g = fadd2(g, pack2(q0.x, q0.y));
+        pk[j] = pack_bf16x2(g);
+    }
+}
+// The same for a tile that mixes classes: both polynomials, selected per element by label equality.  `cq` points
+// at the same-class column polynomials in global memory (L1-resident: every row of the tile reads the same words).
+template <int kDeg>
+__device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const f32x2 (&rn)[5], const f32x2 (&rq)[5],
+                                                 const float4* __restrict__ cp, const float4* __restrict__ cq, int yi,
+                                                 uint32_t (&pk)[16]) {
 #pragma unroll
-        for (int d = kDeg - 2; d >= 0; --d) gsum = ffma2(gsum, s, rr[d]);
-        f32x2 h;
-        if (kDeg == 2) {
-            h = ffma2(pack2(q1.x, q1.y), s, pack2(q0.z, q0.w));
-        } else if (kDeg == 3) {
-            h = ffma2(pack2(q1.z, q1.w), s, pack2(q1.x, q1.y));
-            h = ffma2(h, s, pack2(q0.z, q0.w));
-        } else {
-            const float4 q2 = cp[3 * j + 2];
-            h = ffma2(pack2(q2.x, q2.y), s, pack2(q1.z, q1.w));
-            h = ffma2(h, s, pack2(q1.x, q1.y));
-            h = ffma2(h, s, pack2(q0.z, q0.w));
-        }
-        gsum = ffma2(h, s, gsum);
-        gsum = fadd2(gsum, pack2(q0.x, q0.y));
-        float lo, hi;
-        unpack2(gsum, lo, hi);
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
+        const float4 n0 = cp[3 * j], n2 = cp[3 * j + 2];
+        f32x2 gn = ffma2(col_horner<kDeg>(cp + 3 * j, n0, s), s, row_horner<kDeg>(rn, s));
+        gn = fadd2(gn, pack2(n0.x, n0.y));
+        float4 u[3];
+        u[0] = __ldg(cq + 3 * j);
+        if (kDeg >= 2) u[1] = __ldg(cq + 3 * j + 1);
+        if (kDeg >= 4) u[2] = __ldg(cq + 3 * j + 2);
+        f32x2 gp = ffma2(col_horner<kDeg>(u, u[0], s), s, row_horner<kDeg>(rq, s));
+        gp = fadd2(gp, pack2(u[0].x, u[0].y));
+        float nl, nh, pl, ph;
+        unpack2(gn, nl, nh);
+        unpack2(gp, pl, ph);
+        const float lo = (__float_as_int(n2.z) == yi) ? pl : nl;
+        const float hi = (__float_as_int(n2.w) == yi) ? ph : nh;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
         pk[j] = *reinterpret_cast<uint32_t*>(&b2);
     }
@@ -1395,9 +1478,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         int I, J, curI = -1, it = 0, seg = 0;
         bool last;
         float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = make_float4(0.f, 1.f, 0.f, 0.f);
-        f32x2 rr[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+        f32x2 rn[5] = {0ull, 0ull, 0ull, 0ull, 0ull}, rq[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
         int yi = -1, gi = -1;
         int2 rI = make_int2(INT_MAX, -1);
+        float denI = 0.f;
         while (iter.next(I, J, last)) {
             if (I != curI) {
                 curI = I;
@@ -1407,10 +1491,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 yi = __float_as_int(rB.z);
                 rI = sRange[p.rb0 + I];
                 if (kMode == DCL_MODE_PIXEL) {
-                    const float4 c0 = *reinterpret_cast<const float4*>(p.coefR + static_cast<size_t>(gi) * 8);
-                    const float c4 = p.coefR[static_cast<size_t>(gi) * 8 + 4];
-                    rr[0] = pack2(c0.x, c0.x); rr[1] = pack2(c0.y, c0.y); rr[2] = pack2(c0.z, c0.z);
-                    rr[3] = pack2(c0.w, c0.w); rr[4] = pack2(c4, c4);
+                    const float4* cr = reinterpret_cast<const float4*>(p.coefR + static_cast<size_t>(gi) * 16);
+                    const float4 n0 = cr[0], n1 = cr[1], q0 = cr[2], q1 = cr[3];
+                    rn[0] = pack2(n0.x, n0.x); rn[1] = pack2(n0.y, n0.y); rn[2] = pack2(n0.z, n0.z);
+                    rn[3] = pack2(n0.w, n0.w); rn[4] = pack2(n1.x, n1.x);
+                    rq[0] = pack2(q0.x, q0.x); rq[1] = pack2(q0.y, q0.y); rq[2] = pack2(q0.z, q0.z);
+                    rq[3] = pack2(q0.w, q0.w); rq[4] = pack2(q1.x, q1.x);
+                    denI = p.bden[p.rb0 + I];
                 }
             }
             if ((it & 1) == g) {
@@ -1421,37 +1508,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 1);
                 tc_fence_after();
                 const float4* cp = gCP + slot * (SmemBwd::kCoefBytes / 16);
-                const float4* cA = p.colA + static_cast<size_t>(J) * 128;
-                const float4* cB = p.colB + static_cast<size_t>(J) * 128;
                 const int col0 = J * 128;
                 const uint32_t tS = tmem + st * 128 + lane_off;
-                // fast tile: every pair is a plain "denominator" pair in both directions (no
-                // positives, no self pair); padding needs no mask because padded F rows are zero
-                const bool fast = kMode == DCL_MODE_PIXEL && !ranges_overlap(rI, sRange[J]);
+                // Tile classes (pixel term): no same-class pair -> one polynomial per side; mixed classes away from
+                // the diagonal and every Den large -> two polynomials selected per element; otherwise (diagonal
+                // tile, tiny denominators, image term) the exact masked form.  Padding needs no mask: padded F
+                // rows are zero and padded columns carry zero coefficients.
+                const bool overlap = ranges_overlap(rI, sRange[J]);
+                const bool fast = kMode == DCL_MODE_PIXEL && !overlap;
+                const bool series = kMode == DCL_MODE_PIXEL && overlap && (p.rb0 + I) != J &&
+                                    fminf(denI, p.bden[J]) >= kMinDenSeries;
                 if (p.debug & 1) {
                     // diagnostics: no G is produced
                 } else if (fast) {
-                    if (deg == 2) {
-                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                    auto body = [&](auto degc) {
+                        for_each_chunk_loop(tS, [&](int c0, const uint32_t (&v)[32]) {
                             uint32_t pk[16];
-                            bwd_chunk<2>(v, rr, cp + (c0 >> 1) * 3, pk);
+                            bwd_chunk<decltype(degc)::value>(v, rn, cp + (c0 >> 1) * 3, pk);
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
-                    } else if (deg == 3) {
-                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                    };
+                    if (deg == 1) body(std::integral_constant<int, 1>{});
+                    else if (deg == 2) body(std::integral_constant<int, 2>{});
+                    else if (deg == 3) body(std::integral_constant<int, 3>{});
+                    else body(std::integral_constant<int, 4>{});
+                } else if (series) {
+                    const float4* cq = reinterpret_cast<const float4*>(p.coefPP) + static_cast<size_t>(J) * 64 * 3;
+                    auto body = [&](auto degc) {
+                        for_each_chunk_loop(tS, [&](int c0, const uint32_t (&v)[32]) {
                             uint32_t pk[16];
-                            bwd_chunk<3>(v, rr, cp + (c0 >> 1) * 3, pk);
+                            bwd_chunk_masked<decltype(degc)::value>(v, rn, rq, cp + (c0 >> 1) * 3, cq + (c0 >> 1) * 3, yi, pk);
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
-                    } else {
-                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
-                            uint32_t pk[16];
-                            bwd_chunk<4>(v, rr, cp + (c0 >> 1) * 3, pk);
-                            tmem_st16(tS + (c0 >> 1), pk);
-                        });
-                    }
+                    };
+                    if (deg == 1) body(std::integral_constant<int, 1>{});
+                    else if (deg == 2) body(std::integral_constant<int, 2>{});
+                    else if (deg == 3) body(std::integral_constant<int, 3>{});
+                    else body(std::integral_constant<int, 4>{});
                 } else {
-                    for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                    const float4* cA = p.colA + static_cast<size_t>(J) * 128;
+                    const float4* cB = p.colB + static_cast<size_t>(J) * 128;
+                    for_each_chunk_loop(tS, [&](int c0, const uint32_t (&v)[32]) {
                         uint32_t pk[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
@@ -1550,7 +1647,7 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
     if (t == 0) {
         p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
         p.bnorm[J] = make_float2(b.cx, b.cn);
-        if (J == 0) p.iscal[3] = 2;
+        if (J == 0) p.iscal[3] = 1;
     }
 }
 
@@ -1562,7 +1659,7 @@ struct Layout {
     int nP, maxsegS, maxsegD, splitc, gramP, ctas;
     size_t off_binfo, off_bnorm, off_pA, off_pB, off_gram, off_fsum, off_cmaxp, off_ref, off_Mc, off_mu, off_scal,
         off_iscal, off_rowq, off_pF, off_rowS, off_rowD, off_pC, off_bl,
-        off_ticket, off_coefR, off_coefP, off_pD, bytes;
+        off_ticket, off_coefR, off_coefP, off_coefPP, off_bden, off_pD, bytes;
 };
 
 static int g_debug_flags = 0;
@@ -1610,8 +1707,10 @@ static Layout make_layout(int nI, int nJ) {
     take(L.off_pC, sizeof(float4) * rows * L.splitc);
     take(L.off_bl, sizeof(float) * nI);
     take(L.off_ticket, sizeof(unsigned int) * 4);
-    take(L.off_coefR, sizeof(float) * 8 * allrows);
+    take(L.off_coefR, sizeof(float) * 16 * allrows);
     take(L.off_coefP, sizeof(float) * kCoefPairFloats * (allrows / 2));
+    take(L.off_coefPP, sizeof(float) * kCoefPairFloats * (allrows / 2));
+    take(L.off_bden, sizeof(float) * nJ);
     take(L.off_pD, sizeof(float) * rows * L.maxsegD * 128);
     L.bytes = o;
     return L;
@@ -1652,6 +1751,8 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.pD = reinterpret_cast<float*>(w + L.off_pD);
     p.coefR = reinterpret_cast<float*>(w + L.off_coefR);
     p.coefP = reinterpret_cast<float*>(w + L.off_coefP);
+    p.coefPP = reinterpret_cast<float*>(w + L.off_coefPP);
+    p.bden = reinterpret_cast<float*>(w + L.off_bden);
     p.blockloss = reinterpret_cast<float*>(w + L.off_bl);
     p.ticket = reinterpret_cast<unsigned int*>(w + L.off_ticket);
     p.debug = g_debug_flags;
