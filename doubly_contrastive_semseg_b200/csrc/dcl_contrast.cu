@@ -7,15 +7,15 @@
 //   loss = mean_i [ -(T/T_b) mean_{j in pos(i)} lp_ij ];  dS_ik = kappa_i (g_ik - l_ik R_i);  dF = (dS + dS^T) F
 //
 // Two forward pipelines share the kernels below:
-//   * pixel term ("v3", the hot path).  The row norm needs no N^2 pass:
-//         sum_k (s_ik - m)^2 = f_i^T Mc f_i + n (f_i.mu - m)^2,   Mc = centred Gram matrix (k_gram, k_rowstats)
-//     and e^{l} on the row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a per-row economised
-//     Chebyshev polynomial of degree n = 2..4 in s, so  Den_i = sum_neg E = sum_j d_j P_j  and  sum_neg E s =
-//     sum_j d_j P_{j+1}  with the power sums P_j = sum_neg s^j.  P_0..P_2 over all columns are closed forms of the
-//     Gram statistics; ONE sweep (SWEEP_P) therefore only has to produce the exact row maximum and
-//     sum s^3 (.. s^{n+1}) on the tiles that hold no same-class pair (packed FFMA2, no MUFU, no per-row
-//     constants), and full masked sums on the block-diagonal tiles.  kappa_i, the polynomial and Den_i follow per
-//     row afterwards (k_combine_P).
+//   * pixel term ("v3", the hot path).  e^{l} on a row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a
+//     per-row economised Chebyshev polynomial of degree n = 1..4, so  Den_i = sum_neg E = sum_j e_j P_j  and
+//     sum_neg E x = sum_j e_j P_{j+1}  with the shifted power sums P_j = sum_neg x^j, x = s - c_i (c_i = |f_i|^2, the
+//     diagonal: the shift keeps every sum well conditioned).  ONE sweep (SWEEP_P) produces, per row, the exact
+//     maximum and P_0..P_2 of the different-class columns plus Q_0..Q_2 of the same-class columns (packed FFMA2, no
+//     MUFU, no per-row constants but c_i); kappa_i comes from P + Q, and with n = 1 (a few thousand anchors or
+//     more) everything else follows per row (k_combine1/2).  Rows whose range needs n > 1 trigger a second sweep
+//     (SWEEP_H: x^3..x^{n+1}) that otherwise exits at once; the positive-pair terms use a first-order series in
+//     E/Den and fall back to the exact sweep C only when some row has fewer than ~170 negatives.
 //   * image term and the diagnostic legacy path: sweep A (max, sums), sweep B (Den), as in round 1.
 //   Both continue with sweep C (tiles that can hold positives), finalize, and the fused backward
 //         G_ik = dS_ik + dS_ki = rp_i(s_ik) + rp_k(s_ik)   on pairs of different classes,
@@ -49,7 +49,6 @@ constexpr int kTmemCols = 512;
 constexpr int kProducerWarp = 8;
 constexpr int kIssuerWarp0 = 9;       // issuer g is warp 9 + g
 constexpr int kMaxBlocks = 1024;      // column blocks whose info is cached in shared memory
-constexpr int kGramLd = 132;          // padded row length (floats) of the Gram kernels' shared tiles
 constexpr int kCoefPairFloats = 12;   // backward column coefficients of one column pair: 3 x float4
 
 // ---------------------------------------------------------------------------------------------
@@ -73,6 +72,7 @@ struct Params {
     const int32_t* y;        // [nJ*128]
     const float* sqnorm;     // [nJ*128]
     int nJ, rb0, nI, nP, n_valid, mode, ctas;
+    int use_series;          // v3 forward: positive-pair sums come from the series unless iscal[4] says otherwise
     float T, Tb;
     Part partS;              // sweeps: units = pairs of row blocks
     Part partD;              // backward: units = row blocks
@@ -84,18 +84,13 @@ struct Params {
     // legacy sweeps A / B
     float4* pA;              // [nI][maxsegS][128] (max(s-c), S1, S2, -)
     float2* pB;              // [nI][maxsegS][128] (Den, Bt)
-    // v3 closed-form statistics
-    float* gram_part;        // [P][128*128] partial Gram matrices of (f - ref)
-    float* fsum_part;        // [P][128]
-    float* cmax_part;        // [P]
-    float* ref;              // [128] reference vector (mean of the first block)
-    float* Mc;               // [128*128] centred Gram
-    float* mu;               // [128]
-    float* scal;             // [0] cmax over all rows
-    int* iscal;              // [0] forward polynomial degree (bound over the local rows), [3] backward degree
-    int gramP;
-    float2* rowq;            // [nI*128] (f^T Mc f, f.mu)
-    float4* pF;              // [nI][maxsegS][3][128] power-sum partials: (max s, Q3, Q4, Q5) (V0, V1, V2, N0) (N1, N2, -, -)
+    // v3 power-sum forward
+    int* iscal;              // [0] largest polynomial degree of the local rows, [3] the same for the backward (all rows),
+                             // [4] != 0: some row has too few negatives for the positive-pair series (sweep C runs)
+    float4* pF;              // [nI][maxsegS][2][128] sweep P partials: (max x, P0, P1, P2) (Q0, Q1, Q2, -)
+    float4* pH;              // [nI][maxsegS][2][128] sweep H partials: (P3, P4, P5, -) (Q3, Q4, Q5, -)
+    float* rowM;             // [nI*128][8] (P0, P1, P2, Q0, Q1, Q2, d = max x, L)
+    float4* rowPos;          // [nI*128] positive-pair sums from the series: (P, sum lp, sum inv, sum inv*l)
     // per-row state shared by sweep C / finalize
     float4* rowS;            // [nI*128] (a, b, kappa, m)   t = a s + b = l log2(e)
     float4* rowD;            // [nI*128] (Den, Bt = sum_den E t, L, 0)
@@ -281,12 +276,9 @@ __device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, 
     }
 }
 
-// kappa and logit-range bound of a row from its closed-form norm.  A row whose every s_ik equals the maximum to
-// 1e-6 relative (all embeddings identical) has l = 0 in the reference (0 / eps); it is mapped to kappa = 0.
-__device__ __forceinline__ void row_scale(double qf, double fm, double m, double c, double cmax, int n_valid, float T,
-                                          double& kappa, double& L) {
-    const double e = fm - m;
-    double nrm2 = qf + static_cast<double>(n_valid) * e * e;
+// kappa and logit-range bound of a row from its squared norm sum_k (s_ik - m)^2.  A row whose every s_ik equals the
+// maximum to 1e-6 relative (all embeddings identical) has l = 0 in the reference (0 / eps); it is mapped to kappa = 0.
+__device__ __forceinline__ void row_scale(double nrm2, double m, double c, double cmax, float T, double& kappa, double& L) {
     if (!(nrm2 > 0.0)) nrm2 = 0.0;
     const double nrm = sqrt(nrm2);
     if (nrm <= 1e-6 * fabs(m) || nrm <= static_cast<double>(T) * 1e-12) {
@@ -301,56 +293,8 @@ __device__ __forceinline__ void row_scale(double qf, double fm, double m, double
 }
 
 // =============================================================================================
-// Closed-form statistics: block info, Gram matrix of (f - ref), per-row quadratic forms
+// Block info
 // =============================================================================================
-// register-tiled outer-product accumulation  acc[u][v] += sum_k X[k][rm(ty,u)] Y[k][rm(tx,v)]
-// with rm(t, u) = (u < 4 ? 4t + u : 64 + 4t + u - 4)  (conflict-free float4 reads)
-__device__ __forceinline__ int rmap(int t, int u) { return u < 4 ? 4 * t + u : 64 + 4 * t + (u - 4); }
-__device__ __forceinline__ void outer_accumulate(const float* __restrict__ X, const float* __restrict__ Y, int ty, int tx,
-                                                 float (&acc)[8][8]) {
-#pragma unroll 4
-    for (int k = 0; k < 128; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(X + k * kGramLd + 4 * ty);
-        const float4 a1 = *reinterpret_cast<const float4*>(X + k * kGramLd + 64 + 4 * ty);
-        const float4 b0 = *reinterpret_cast<const float4*>(Y + k * kGramLd + 4 * tx);
-        const float4 b1 = *reinterpret_cast<const float4*>(Y + k * kGramLd + 64 + 4 * tx);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int v = 0; v < 8; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
-    }
-}
-
-// F-tile image (global) -> fp32 shared tile; kTranspose: dst[d][r] else dst[r][d]; rows with y < 0 become zero;
-// `sub` (may be null) is subtracted from valid rows
-template <bool kTranspose>
-__device__ __forceinline__ void load_tile_f32(const uint8_t* __restrict__ tile, const int* __restrict__ yrow,
-                                              const float* __restrict__ sub, float* __restrict__ dst) {
-    for (int q = threadIdx.x; q < 2048; q += blockDim.x) {
-        const int hpanel = q >> 10, r = (q & 1023) >> 3, cs = q & 7;
-        const int c = cs ^ (r & 7);
-        const int d0 = hpanel * 64 + c * 8;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tile) + q);
-        const bool valid = yrow[r] >= 0;
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-            if (sub) { lo -= sub[d0 + 2 * e]; hi -= sub[d0 + 2 * e + 1]; }
-            if (!valid) { lo = 0.f; hi = 0.f; }
-            if (kTranspose) {
-                dst[(d0 + 2 * e) * kGramLd + r] = lo;
-                dst[(d0 + 2 * e + 1) * kGramLd + r] = hi;
-            } else {
-                dst[r * kGramLd + d0 + 2 * e] = lo;
-                dst[r * kGramLd + d0 + 2 * e + 1] = hi;
-            }
-        }
-    }
-}
-
 // (ymin, ymax, nvalid) and (cmax, cmin) of one 128-row block; threads 0..127 hold one row each, the result is valid
 // in thread 0 after the second barrier.  Must be called by all threads of the CTA (it uses __syncthreads).
 struct BlockStat {
@@ -382,161 +326,6 @@ __device__ __forceinline__ BlockStat block_stat(int yv, float c, bool participat
     return b;
 }
 
-// one CTA per strided set of column blocks: block info for its blocks + partial Gram of (f - ref)
-__global__ void __launch_bounds__(256) k_gram(const Params p) {
-    extern __shared__ float gsm[];
-    float* G = gsm;                         // [128][kGramLd]
-    __shared__ float sref[128];
-    __shared__ int sy[128];
-    __shared__ int si[12];
-    __shared__ float sf[8];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    // reference vector = mean of block 0's valid rows (every CTA derives the same one)
-    if (tid < 128) sy[tid] = p.y[tid];
-    __syncthreads();
-    load_tile_f32<false>(p.tiles, sy, nullptr, G);
-    __syncthreads();
-    if (tid < 128) {
-        float s = 0.f;
-        int nv = 0;
-        for (int r = 0; r < 128; ++r) { s += G[r * kGramLd + tid]; nv += sy[r] >= 0; }
-        sref[tid] = nv > 0 ? s / nv : 0.f;
-        if (blockIdx.x == 0) p.ref[tid] = sref[tid];
-    }
-    float acc[8][8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
-    float fs = 0.f, cmx = 0.f;
-    for (int J = blockIdx.x; J < p.nJ; J += gridDim.x) {
-        __syncthreads();                     // readers of sy / G from the previous block are done
-        float c = 0.f;
-        int yv = -1;
-        if (tid < 128) {
-            yv = p.y[J * 128 + tid];
-            sy[tid] = yv;
-            c = p.sqnorm[J * 128 + tid];
-        }
-        const BlockStat b = block_stat(yv, c, tid < 128, si, sf);
-        if (tid == 0) {
-            p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
-            p.bnorm[J] = make_float2(b.cx, b.cn);
-            cmx = fmaxf(cmx, b.cx);
-        }
-        load_tile_f32<false>(p.tiles + static_cast<size_t>(J) * kTileBytes, sy, sref, G);
-        __syncthreads();
-        outer_accumulate(G, G, ty, tx, acc);
-        if (tid < 128) {
-            float s = 0.f;
-            for (int r = 0; r < 128; ++r) s += G[r * kGramLd + tid];
-            fs += s;
-        }
-    }
-    float* gp = p.gram_part + static_cast<size_t>(blockIdx.x) * 128 * 128;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int a = rmap(ty, u);
-        *reinterpret_cast<float4*>(gp + a * 128 + 4 * tx) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
-        *reinterpret_cast<float4*>(gp + a * 128 + 64 + 4 * tx) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
-    }
-    if (tid < 128) p.fsum_part[blockIdx.x * 128 + tid] = fs;
-    if (tid == 0) p.cmax_part[blockIdx.x] = cmx;
-}
-
-// Mc = sum_p Gram_p - n delta delta^T,  mu = ref + delta,  delta = sum_p fsum_p / n   (fp64 combination, fixed order)
-__global__ void __launch_bounds__(256) k_gram_reduce(const Params p) {
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    const int a = e >> 7, b = e & 127;
-    double g = 0.0, da = 0.0, db = 0.0;
-    for (int q = 0; q < p.gramP; ++q) {
-        g += p.gram_part[static_cast<size_t>(q) * 16384 + e];
-        da += p.fsum_part[q * 128 + a];
-        db += p.fsum_part[q * 128 + b];
-    }
-    const double n = p.n_valid;
-    p.Mc[e] = static_cast<float>(g - da * db / n);
-    if (blockIdx.x == 0) {
-        if (threadIdx.x < 128) {
-            double d = 0.0;
-            for (int q = 0; q < p.gramP; ++q) d += p.fsum_part[q * 128 + threadIdx.x];
-            p.mu[threadIdx.x] = static_cast<float>(p.ref[threadIdx.x] + d / n);
-        }
-        if (threadIdx.x == 0) {
-            float cm = 0.f;
-            for (int q = 0; q < p.gramP; ++q) cm = fmaxf(cm, p.cmax_part[q]);
-            p.scal[0] = cm;
-            p.iscal[0] = 1;
-            p.ticket[0] = 0u;
-            p.ticket[1] = 0u;
-        }
-    }
-}
-
-// Upper bound of the logit range L(m) = kappa(m) (m + b) over every possible row maximum m >= c (the sweep that
-// finds m runs after the polynomial degree must be known):  g(m) = (m + b) / sqrt(qf + n (m - fm)^2) peaks at
-// m* = fm + qf / (n (fm + b)).
-__device__ __forceinline__ double logit_range_bound(double qf, double fm, double c, double cmax, int n_valid) {
-    const double n = n_valid, b = sqrt(c * cmax);
-    auto g = [&](double m) {
-        const double e = m - fm, v = qf + n * e * e;
-        return v > 0.0 ? (m + b) / sqrt(v) : 1.0;
-    };
-    double best = g(c);
-    if (fm + b > 0.0) {
-        const double ms = fm + (qf > 0.0 ? qf : 0.0) / (n * (fm + b));
-        if (ms > c) best = fmax(best, g(ms));
-    }
-    return fmin(1.0, best * (1.0 + 1e-6));
-}
-
-// per local row block: qf_i = f_i^T Mc f_i, fm_i = f_i . mu, and the polynomial degree the row may need
-__global__ void __launch_bounds__(256) k_rowstats(const Params p) {
-    extern __shared__ float gsm[];
-    float* X = gsm;                          // F^T : [d][i]
-    float* Y = gsm + 128 * kGramLd;          // Mc  : [d][e]
-    __shared__ int sy[128];
-    __shared__ float smu[128];
-    __shared__ float sqf[128];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const int I = blockIdx.x, gb = p.rb0 + I;
-    if (tid < 128) { sy[tid] = p.y[gb * 128 + tid]; smu[tid] = p.mu[tid]; }
-    for (int q = tid; q < 128 * 32; q += 256) {
-        const int d = q >> 5, c4 = q & 31;
-        *reinterpret_cast<float4*>(Y + d * kGramLd + 4 * c4) = __ldg(reinterpret_cast<const float4*>(p.Mc) + q);
-    }
-    __syncthreads();
-    load_tile_f32<true>(p.tiles + static_cast<size_t>(gb) * kTileBytes, sy, nullptr, X);
-    __syncthreads();
-    float acc[8][8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
-    outer_accumulate(X, Y, ty, tx, acc);      // acc[u][v] = (F Mc)[i = rmap(ty,u)][e = rmap(tx,v)]
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int i = rmap(ty, u);
-        float s = 0.f;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) s = fmaf(acc[u][v], X[rmap(tx, v) * kGramLd + i], s);
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tx == 0) sqf[i] = s;
-    }
-    __syncthreads();
-    if (tid < 128) {
-        const int lrow = I * 128 + tid, gi = gb * 128 + tid;
-        float fm = 0.f;
-        for (int d = 0; d < 128; ++d) fm = fmaf(X[d * kGramLd + tid], smu[d], fm);
-        p.rowq[lrow] = make_float2(sqf[tid], fm);
-        if (sy[tid] >= 0) {
-            const double c = p.sqnorm[gi];
-            const int deg = poly_degree_for(logit_range_bound(sqf[tid], fm, c, p.scal[0], p.n_valid));
-            if (deg > 1) atomicMax(&p.iscal[0], deg);
-        }
-    }
-}
-
 // =============================================================================================
 // shared-memory carve-up (bytes from a 1024-aligned base)
 // =============================================================================================
@@ -544,7 +333,8 @@ struct SmemSweep {
     static constexpr int kSlots = 6;                      // F_J ring (the row blocks live in TMEM)
     static constexpr int kJ = 0;
     static constexpr int kInfo = kSlots * kTileBytes;     // int4[kMaxBlocks]
-    static constexpr int kBar = kInfo + 16 * kMaxBlocks;  // full[6] empty[6] tfull[3] tempty[3] afull[2] turn[2]
+    static constexpr int kLab = kInfo + 16 * kMaxBlocks;  // 8 epilogue warps x 128 labels of the current masked column block
+    static constexpr int kBar = kLab + 8 * 512;           // full[6] empty[6] tfull[3] tempty[3] afull[2] turn[2] aseen
     static constexpr int kTmem = kBar + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;      // + alignment slack
 };
@@ -561,7 +351,7 @@ struct SmemBwd {
     static constexpr int kBytes = kTmem + 16 + 1024;
 };
 
-enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2, SWEEP_P = 3 };
+enum { SWEEP_A = 0, SWEEP_B = 1, SWEEP_C = 2, SWEEP_P = 3, SWEEP_H = 4 };
 
 // Tile sequence of one CTA: (row unit U, column block J).  Flat mode: contiguous range of the flattened U-major
 // list.  Relevant mode (sweep C): CTA = (pair, split s) walks
@@ -626,39 +416,83 @@ struct TileIter {
 };
 
 // ---------------------------------------------------------------------------------------------
-// SWEEP_P fast-tile body for 32 columns (16 packed pairs): row max and the power sums s^3 .. s^{deg+1}
-// (degree 1 needs none: P_0..P_2 are closed forms)
 __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-template <int kDeg>
-__device__ __forceinline__ void psweep_chunk(const uint32_t (&v)[32], f32x2 (&q3)[4], f32x2 (&q4)[4], f32x2 (&q5)[4],
-                                             float (&mx)[4]) {
+// SWEEP_P fast-tile body for 32 columns (16 packed pairs), x = s - c_i: row max, sum x, sum x^2
+__device__ __forceinline__ void psweep_chunk(const uint32_t (&v)[32], f32x2 negc, f32x2 (&x1)[4], f32x2 (&x2)[4], float (&mx)[4]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        if (kDeg >= 2) {
-            const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
-            const f32x2 s2 = fmul2(s, s);
-            q3[j & 3] = ffma2(s2, s, q3[j & 3]);
-            if (kDeg >= 3) q4[j & 3] = ffma2(s2, s2, q4[j & 3]);
-            if (kDeg >= 4) q5[j & 3] = ffma2(fmul2(s2, s), s2, q5[j & 3]);
+        const f32x2 x = fadd2(pack2u(v[2 * j], v[2 * j + 1]), negc);
+        float lo, hi;
+        unpack2(x, lo, hi);
+        mx[j & 3] = fmaxf(mx[j & 3], fmaxf(lo, hi));
+        x1[j & 3] = fadd2(x1[j & 3], x);
+        x2[j & 3] = ffma2(x, x, x2[j & 3]);
+    }
+}
+// SWEEP_P body for a tile that may hold same-class pairs, labels of its 128 columns staged in `wy` (shared):
+// sums over every valid column (a1, a2; the count comes from the block info) and over the different-class ones
+// (n0..n2).  The same-class sums follow as all - different - self.
+template <bool kAllValid>
+__device__ __forceinline__ void psweep_chunk_masked(const uint32_t (&v)[32], const int* __restrict__ wy, int yi, f32x2 negc,
+                                                    f32x2& a0, f32x2& a1, f32x2& a2, f32x2& n0, f32x2& n1, f32x2& n2,
+                                                    float (&mx)[4]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int2 yy = *reinterpret_cast<const int2*>(wy + 2 * j);
+        const f32x2 x = fadd2(pack2u(v[2 * j], v[2 * j + 1]), negc);
+        const f32x2 xx = fmul2(x, x);
+        float lo, hi;
+        unpack2(x, lo, hi);
+        const bool v0 = kAllValid || yy.x >= 0, v1 = kAllValid || yy.y >= 0;
+        const f32x2 wn = pack2((v0 && yy.x != yi) ? 1.f : 0.f, (v1 && yy.y != yi) ? 1.f : 0.f);
+        if (kAllValid) {
+            mx[j & 3] = fmaxf(mx[j & 3], fmaxf(lo, hi));
+            a1 = fadd2(a1, x);
+            a2 = fadd2(a2, xx);
+        } else {
+            const f32x2 wv = pack2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+            mx[j & 3] = fmaxf(mx[j & 3], fmaxf(v0 ? lo : -FLT_MAX, v1 ? hi : -FLT_MAX));
+            a0 = fadd2(a0, wv);
+            a1 = ffma2(wv, x, a1);
+            a2 = ffma2(wv, xx, a2);
         }
-        mx[j & 3] = fmaxf(mx[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+        n0 = fadd2(n0, wn);
+        n1 = ffma2(wn, x, n1);
+        n2 = ffma2(wn, xx, n2);
+    }
+}
+// SWEEP_H fast-tile body: sum x^3 .. x^{deg+1}
+template <int kDeg>
+__device__ __forceinline__ void hsweep_chunk(const uint32_t (&v)[32], f32x2 negc, f32x2 (&h3)[4], f32x2 (&h4)[4], f32x2 (&h5)[4]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 x = fadd2(pack2u(v[2 * j], v[2 * j + 1]), negc);
+        const f32x2 xx = fmul2(x, x);
+        h3[j & 3] = ffma2(xx, x, h3[j & 3]);
+        if (kDeg >= 3) h4[j & 3] = ffma2(xx, xx, h4[j & 3]);
+        if (kDeg >= 4) h5[j & 3] = ffma2(fmul2(xx, x), xx, h5[j & 3]);
     }
 }
 
 // =============================================================================================
-// Sweeps A / B / C / P
+// Sweeps A / B / C / P / H
 // =============================================================================================
 template <int kSweep, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     extern __shared__ uint8_t smem_raw[];
+    // conditional sweeps leave before any set-up when their trigger (written by k_combine1) is clear
+    if (kSweep == SWEEP_H && p.iscal[0] <= 1) return;
+    if (kSweep == SWEEP_C && kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[4] == 0) return;
+    if (threadIdx.x == 0) trace_stamp(p, 0, 0, 7);          // kernel entry
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sJ = base + SmemSweep::kJ;
     int4* sInfo = reinterpret_cast<int4*>(gen + SmemSweep::kInfo);
+    int* sLab = reinterpret_cast<int*>(gen + SmemSweep::kLab);
     const uint32_t bar = base + SmemSweep::kBar;
     constexpr int kSlots = SmemSweep::kSlots;
     // tfull / tempty are per accumulator buffer (job % 3); afull per row block of the pair; turn per issuer
@@ -686,10 +520,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     }
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) sInfo[j] = p.binfo[j];
     const Part& part = p.partS;
-    const int deg = (kSweep == SWEEP_P) ? p.iscal[0] : 0;
+    const int deg = (kSweep == SWEEP_H) ? p.iscal[0] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (threadIdx.x == 0) trace_stamp(p, 0, 2, 7);          // set-up done
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     // TMEM map: row block g of the pair as the bf16 A operand at columns [64 g, 64 g + 64); three 128-column fp32
     // accumulator buffers at 128, 256, 384.  Job j = 2 * tile + g uses buffer j % 3.
@@ -800,9 +635,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         int U, J, curU = -1, it = 0;
         bool last, valid = false;
         float acc0[4], acc1[4], acc2[4], acc3[4];
-        f32x2 q3[4], q4[4], q5[4];                         // SWEEP_P: packed sums of s^3, s^4, s^5
+        f32x2 q3[4], q4[4], q5[4];                         // SWEEP_P: packed sums of x, x^2 (q3, q4); SWEEP_H: x^3, x^4, x^5
         float mx4[4];
-        float mV0 = 0.f, mV1 = 0.f, mV2 = 0.f, mN0 = 0.f, mN1 = 0.f, mN2 = 0.f;   // SWEEP_P masked-tile sums
+        float mQ0 = 0.f, mQ1 = 0.f, mQ2 = 0.f, mN0 = 0.f, mN1 = 0.f, mN2 = 0.f;   // masked-tile sums: positives / negatives
+        f32x2 negc = 0ull;
+        f32x2 mA0 = 0ull, mA1 = 0ull, mA2 = 0ull, mP0 = 0ull, mP1 = 0ull, mP2 = 0ull;   // SWEEP_P masked tiles (packed)
+        int* wy = sLab + warp * 128;
         float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f;
         int yi = -1, gi = -1, Iloc = 0, lrow = 0, nunits = 0;
         int2 rI = make_int2(INT_MAX, -1);
@@ -815,7 +653,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                 q3[u] = q4[u] = q5[u] = 0ull;
                 mx4[u] = -FLT_MAX;
             }
-            mV0 = mV1 = mV2 = mN0 = mN1 = mN2 = 0.f;
+            mQ0 = mQ1 = mQ2 = mN0 = mN1 = mN2 = 0.f;
+            mA0 = mA1 = mA2 = mP0 = mP1 = mP2 = 0ull;
         };
         auto flush = [&]() {
             if (!valid) return;
@@ -830,13 +669,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     make_float2((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
                                 (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]));
             } else if (kSweep == SWEEP_P) {
-                float4* o = p.pF + ((static_cast<size_t>(Iloc) * p.maxsegS + seg) * 3) * 128 + r;
-                o[0] = make_float4(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])),
-                                   (sum2(q3[0]) + sum2(q3[1])) + (sum2(q3[2]) + sum2(q3[3])) + ((acc0[0] + acc0[1]) + (acc0[2] + acc0[3])),
-                                   (sum2(q4[0]) + sum2(q4[1])) + (sum2(q4[2]) + sum2(q4[3])) + ((acc1[0] + acc1[1]) + (acc1[2] + acc1[3])),
-                                   (sum2(q5[0]) + sum2(q5[1])) + (sum2(q5[2]) + sum2(q5[3])) + ((acc2[0] + acc2[1]) + (acc2[2] + acc2[3])));
-                o[128] = make_float4(mV0, mV1, mV2, mN0);
-                o[256] = make_float4(mN1, mN2, 0.f, 0.f);
+                // mN0 counts the 128 columns of every unmasked tile, mQ0 the valid columns of the masked ones (minus the
+                // row's own column); masked tiles: same-class = all valid - different-class
+                const float n0 = sum2(mP0), n1 = sum2(mP1), n2 = sum2(mP2);
+                float4* o = p.pF + ((static_cast<size_t>(Iloc) * p.maxsegS + seg) * 2) * 128 + r;
+                o[0] = make_float4(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), mN0 + n0,
+                                   (sum2(q3[0]) + sum2(q3[1])) + (sum2(q3[2]) + sum2(q3[3])) + n1,
+                                   (sum2(q4[0]) + sum2(q4[1])) + (sum2(q4[2]) + sum2(q4[3])) + n2);
+                o[128] = make_float4((mQ0 + sum2(mA0)) - n0, sum2(mA1) - n1, sum2(mA2) - n2, 0.f);
+            } else if (kSweep == SWEEP_H) {
+                float4* o = p.pH + ((static_cast<size_t>(Iloc) * p.maxsegS + seg) * 2) * 128 + r;
+                o[0] = make_float4((sum2(q3[0]) + sum2(q3[1])) + (sum2(q3[2]) + sum2(q3[3])) + mN0,
+                                   (sum2(q4[0]) + sum2(q4[1])) + (sum2(q4[2]) + sum2(q4[3])) + mN1,
+                                   (sum2(q5[0]) + sum2(q5[1])) + (sum2(q5[2]) + sum2(q5[3])) + mN2, 0.f);
+                o[128] = make_float4(mQ0, mQ1, mQ2, 0.f);
             } else {
                 p.pC[(static_cast<size_t>(Iloc) * p.splitc + (blockIdx.x % p.splitc)) * 128 + r] =
                     make_float4((acc0[0] + acc0[1]) + (acc0[2] + acc0[3]),
@@ -853,19 +699,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             // block has completed: this group has consumed the accumulators of all its earlier jobs.
             if (valid) {
                 const uint8_t* trow = p.tiles + static_cast<size_t>(p.rb0 + Iloc) * kTileBytes + r * 128;
+                gi = (p.rb0 + Iloc) * 128 + r;
+                // all loads first (one round trip), then the four TMEM stores
+                const int yload = __ldg(p.y + gi);
+                const float cload = (kSweep == SWEEP_A || kSweep == SWEEP_P || kSweep == SWEEP_H) ? __ldg(p.sqnorm + gi) : 0.f;
+                uint4 xw[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int c4 = 0; c4 < 2; ++c4) {
-                        uint32_t w[16];
+                    for (int c = 0; c < 8; ++c)
+                        xw[h * 8 + c] = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes + ((c ^ (r & 7)) << 4)));
+                yi = yload;
+                cshift = cload;
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const int c = c4 * 4 + cc;
-                            const uint4 x = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes + ((c ^ (r & 7)) << 4)));
-                            w[cc * 4 + 0] = x.x; w[cc * 4 + 1] = x.y; w[cc * 4 + 2] = x.z; w[cc * 4 + 3] = x.w;
-                        }
-                        tmem_st16(tmem + lane_off + g * 64 + h * 32 + c4 * 16, w);
+                for (int qq = 0; qq < 4; ++qq) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const uint4 x = xw[qq * 4 + cc];
+                        w[cc * 4 + 0] = x.x; w[cc * 4 + 1] = x.y; w[cc * 4 + 2] = x.z; w[cc * 4 + 3] = x.w;
                     }
+                    tmem_st16(tmem + lane_off + g * 64 + qq * 16, w);
                 }
                 tmem_st_wait();
             }
@@ -876,14 +730,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             if (lane == 0) mbar_arrive(b_afull + 8 * g);
             if (!valid) return;
             lrow = Iloc * 128 + r;
-            gi = (p.rb0 + Iloc) * 128 + r;
-            yi = p.y[gi];
             const int4 bi = sInfo[p.rb0 + Iloc];
             rI = make_int2(bi.x, bi.y);
             if (kSweep == SWEEP_A) {
-                cshift = p.sqnorm[gi];
-            } else if (kSweep == SWEEP_P) {
-                // no per-row constants: the sweep only needs the row's label
+                // cshift loaded above
+            } else if (kSweep == SWEEP_P || kSweep == SWEEP_H) {
+                negc = pack2(-cshift, -cshift);         // the only per-row constant: the shift x = s - c_i
             } else {
                 const float4 rs = p.rowS[lrow];
                 ra = rs.x;
@@ -916,31 +768,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             } else if (kSweep == SWEEP_P) {
                 const bool fast = all_valid && !ranges_overlap(rI, rJ);
                 if (fast) {
-                    if (deg == 1)      for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<1>(v, q3, q4, q5, mx4); });
-                    else if (deg == 2) for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<2>(v, q3, q4, q5, mx4); });
-                    else if (deg == 3) for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<3>(v, q3, q4, q5, mx4); });
-                    else               for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<4>(v, q3, q4, q5, mx4); });
+                    for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk(v, negc, q3, q4, mx4); });
+                    mN0 += 128.f;
                 } else {
-                    // masked tile: every valid column feeds the max and V0..V2 (to be removed from the closed-form
-                    // totals), the negatives feed N0..N2 and the higher power sums
+                    // masked tile: stage the column labels once per warp, then packed masked sums
+                    __syncwarp();
+                    reinterpret_cast<int4*>(wy)[lane] = __ldg(reinterpret_cast<const int4*>(yJ) + lane);
+                    __syncwarp();
+                    if (all_valid) {
+                        for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                            psweep_chunk_masked<true>(v, wy + c0, yi, negc, mA0, mA1, mA2, mP0, mP1, mP2, mx4);
+                        });
+                        mQ0 += 128.f;
+                    } else {
+                        for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
+                            psweep_chunk_masked<false>(v, wy + c0, yi, negc, mA0, mA1, mA2, mP0, mP1, mP2, mx4);
+                        });
+                    }
+                    if (J == p.rb0 + Iloc) mQ0 -= 1.f;          // the row's own column (x = 0) is not a positive
+                }
+            } else if (kSweep == SWEEP_H) {
+                const bool fast = all_valid && !ranges_overlap(rI, rJ);
+                if (fast) {
+                    if (deg == 2)      for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { hsweep_chunk<2>(v, negc, q3, q4, q5); });
+                    else if (deg == 3) for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { hsweep_chunk<3>(v, negc, q3, q4, q5); });
+                    else               for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { hsweep_chunk<4>(v, negc, q3, q4, q5); });
+                } else {
                     for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]);
+                            const float x = __uint_as_float(v[j]) - cshift;
                             const int yj = __ldg(yJ + c0 + j);
-                            const float s2 = s * s;
+                            const float xx = x * x, x3 = xx * x;
                             if (yj >= 0) {
-                                mx4[j & 3] = fmaxf(mx4[j & 3], s);
-                                mV0 += 1.f;
-                                mV1 += s;
-                                mV2 += s2;
                                 if (yj != yi) {
-                                    mN0 += 1.f;
-                                    mN1 += s;
-                                    mN2 += s2;
-                                    acc0[j & 3] = fmaf(s2, s, acc0[j & 3]);
-                                    acc1[j & 3] = fmaf(s2, s2, acc1[j & 3]);
-                                    acc2[j & 3] = fmaf(s2 * s, s2, acc2[j & 3]);
+                                    mN0 += x3;
+                                    mN1 = fmaf(xx, xx, mN1);
+                                    mN2 = fmaf(x3, xx, mN2);
+                                } else if (col0 + c0 + j != gi) {
+                                    mQ0 += x3;
+                                    mQ1 = fmaf(xx, xx, mQ1);
+                                    mQ2 = fmaf(x3, xx, mQ2);
                                 }
                             }
                         }
@@ -1036,6 +904,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(p, 0, 1, 7);          // all roles done
     if (warp == kProducerWarp) tmem_dealloc<kTmemCols>(tmem);
 }
 
@@ -1075,49 +944,96 @@ __global__ void __launch_bounds__(128) k_combine_B(const Params p) {
 }
 
 // =============================================================================================
-// v3: per row, power sums + exact maximum -> kappa, the exponential polynomial, Den and Bt
+// v3: per row, shifted power sums + exact maximum -> kappa, logit range, polynomial degree (k_combine1);
+//     polynomial, Den, Bt and the positive-pair sums (k_combine2)
 // =============================================================================================
-__global__ void __launch_bounds__(128) k_combine_P(const Params p) {
+constexpr float kMinNegSeries = 174.0f;     // E >= 1/e, so this many negatives guarantee Den >= kMinDenSeries
+
+__global__ void __launch_bounds__(128) k_combine1(const Params p) {
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
+    // largest |f|^2 of the contrast set (per-block maxima from k_blockinfo)
+    __shared__ float scm[128];
+    float cm = 0.f;
+    for (int j = r; j < p.nJ; j += 128) cm = fmaxf(cm, p.bnorm[j].x);
+    scm[r] = cm;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (r < o) scm[r] = fmaxf(scm[r], scm[r + o]);
+        __syncthreads();
+    }
+    const double cmax = scm[0];
     const int ns = p.partS.nseg(I >> 1);
     float mx = -FLT_MAX;
-    double Q[3] = {0.0, 0.0, 0.0}, V[3] = {0.0, 0.0, 0.0}, Nn[3] = {0.0, 0.0, 0.0};
+    double P[3] = {0.0, 0.0, 0.0}, Q[3] = {0.0, 0.0, 0.0};
     for (int s = 0; s < ns; ++s) {
-        const float4* o = p.pF + ((static_cast<size_t>(I) * p.maxsegS + s) * 3) * 128 + r;
-        const float4 a = o[0], b = o[128], c = o[256];
+        const float4* o = p.pF + ((static_cast<size_t>(I) * p.maxsegS + s) * 2) * 128 + r;
+        const float4 a = o[0], b = o[128];
         mx = fmaxf(mx, a.x);
-        Q[0] += a.y; Q[1] += a.z; Q[2] += a.w;
-        V[0] += b.x; V[1] += b.y; V[2] += b.z;
-        Nn[0] += b.w; Nn[1] += c.x; Nn[2] += c.y;
+        P[0] += a.y; P[1] += a.z; P[2] += a.w;
+        Q[0] += b.x; Q[1] += b.y; Q[2] += b.z;
     }
+    float4* rm = reinterpret_cast<float4*>(p.rowM + static_cast<size_t>(lrow) * 8);
     if (p.y[gi] < 0) {
+        rm[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rm[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         p.rowS[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
-        p.rowD[lrow] = make_float4(1.f, 0.f, 0.f, 0.f);
         return;
     }
-    const float2 q = p.rowq[lrow];
-    const double qf = q.x, fm = q.y, n = p.n_valid, m = mx, c = p.sqnorm[gi];
+    // sum over every valid column of (s - m)^2 = sum (x - d)^2, d = max x (the row itself has x = 0)
+    const double d = mx, n = p.n_valid, c = p.sqnorm[gi], m = c + d;
+    const double nrm2 = (P[2] + Q[2]) - 2.0 * d * (P[1] + Q[1]) + n * d * d;
     double kappa, L;
-    row_scale(qf, fm, m, c, p.scal[0], p.n_valid, p.T, kappa, L);
-    double d[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
-    if (kappa > 0.0) {
-        int deg = poly_degree_for(L);
-        const int swept = p.iscal[0];             // the sweep produced power sums up to s^{swept+1}
-        if (deg > swept) deg = swept;             // cannot happen: logit_range_bound() covers every m >= c
-        exp_poly_in_s(kappa, m, L, deg, d);
-    }
-    // power sums over the negatives: closed-form totals minus the masked tiles' columns, plus their negatives
-    double P[6];
-    P[0] = (n - V[0]) + Nn[0];
-    P[1] = (n * fm - V[1]) + Nn[1];
-    P[2] = (qf + n * fm * fm - V[2]) + Nn[2];
-    P[3] = Q[0]; P[4] = Q[1]; P[5] = Q[2];
-    double se = 0.0, ss = 0.0;
-    for (int j = 0; j < 5; ++j) { se += d[j] * P[j]; ss += d[j] * P[j + 1]; }
+    row_scale(nrm2, m, c, cmax, p.T, kappa, L);
+    const int deg = kappa > 0.0 ? poly_degree_for(L) : 1;
+    if (deg > 1) atomicMax(&p.iscal[0], deg);
+    if (P[0] < kMinNegSeries) p.iscal[4] = 1;       // same value from every such row
+    rm[0] = make_float4(static_cast<float>(P[0]), static_cast<float>(P[1]), static_cast<float>(P[2]), static_cast<float>(Q[0]));
+    rm[1] = make_float4(static_cast<float>(Q[1]), static_cast<float>(Q[2]), mx, static_cast<float>(L));
     const double a = kappa * static_cast<double>(kLog2e);
     p.rowS[lrow] = make_float4(static_cast<float>(a), static_cast<float>(-m * a), static_cast<float>(kappa), static_cast<float>(m));
-    // Bt = sum_den E t = log2(e) kappa (sum E s - m sum E)
-    p.rowD[lrow] = make_float4(static_cast<float>(se), static_cast<float>(a * (ss - m * se)), static_cast<float>(L), 0.f);
+}
+
+__global__ void __launch_bounds__(128) k_combine2(const Params p) {
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
+    if (p.y[gi] < 0) {
+        p.rowD[lrow] = make_float4(1.f, 0.f, 0.f, 0.f);
+        p.rowPos[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float4* rm = reinterpret_cast<const float4*>(p.rowM + static_cast<size_t>(lrow) * 8);
+    const float4 m0 = rm[0], m1 = rm[1];
+    double P[6] = {m0.x, m0.y, m0.z, 0.0, 0.0, 0.0}, Q[6] = {m0.w, m1.x, m1.y, 0.0, 0.0, 0.0};
+    const double d = m1.z, L = m1.w;
+    if (p.iscal[0] > 1) {
+        const int ns = p.partS.nseg(I >> 1);
+        for (int s = 0; s < ns; ++s) {
+            const float4* o = p.pH + ((static_cast<size_t>(I) * p.maxsegS + s) * 2) * 128 + r;
+            const float4 a = o[0], b = o[128];
+            P[3] += a.x; P[4] += a.y; P[5] += a.z;
+            Q[3] += b.x; Q[4] += b.y; Q[5] += b.z;
+        }
+    }
+    const float4 rs = p.rowS[lrow];                 // (a, b, kappa, m)
+    const double kappa = rs.z, a = rs.x;
+    // E as a polynomial in x = s - c:  l = kappa (x - d)
+    double e[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
+    if (kappa > 0.0) exp_poly_in_s(kappa, d, L, poly_degree_for(L), e);
+    double den = 0.0, sex = 0.0, pe = 0.0, pex = 0.0;
+    for (int j = 0; j < 5; ++j) {
+        den += e[j] * P[j]; sex += e[j] * P[j + 1];
+        pe += e[j] * Q[j];  pex += e[j] * Q[j + 1];
+    }
+    // Bt = sum_neg E t,  t = log2(e) kappa (x - d)
+    p.rowD[lrow] = make_float4(static_cast<float>(den), static_cast<float>(a * (sex - d * den)), static_cast<float>(L), 0.f);
+    // positive pairs, first-order series in E/Den (second-order term with sum E^2 ~ (sum E)^2 / P):
+    //   lp = l - log(E + Den) ~ l - log Den - E/Den + E^2/(2 Den^2),   1/(E + Den) ~ 1/Den - E/Den^2 + E^2/Den^3
+    const double Pn = Q[0], sl = kappa * (Q[1] - d * Q[0]), sel = kappa * (pex - d * pe);
+    const double pe2 = Pn > 0.0 ? pe * pe / Pn : 0.0;
+    const double id = 1.0 / den;
+    const double SL = sl - Pn * log(den) - pe * id + 0.5 * pe2 * id * id;
+    const double SI = Pn * id - pe * id * id + pe2 * id * id * id;
+    const double SIL = sl * id - sel * id * id;
+    p.rowPos[lrow] = make_float4(static_cast<float>(Pn), static_cast<float>(SL), static_cast<float>(SI), static_cast<float>(SIL));
 }
 
 // =============================================================================================
@@ -1137,9 +1053,14 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
         const float4 db = p.rowD[lrow];
         const float kappa = rs.z;
         float P = 0.f, SL = 0.f, SI = 0.f, SIL = 0.f;
-        for (int s = 0; s < p.splitc; ++s) {
-            float4 v = p.pC[(static_cast<size_t>(I) * p.splitc + s) * 128 + r];
-            P += v.x; SL += v.y; SI += v.z; SIL += v.w;
+        if (kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[4] == 0) {
+            const float4 v = p.rowPos[lrow];          // series sums from k_combine2 (sweep C did not run)
+            P = v.x; SL = v.y; SI = v.z; SIL = v.w;
+        } else {
+            for (int s = 0; s < p.splitc; ++s) {
+                float4 v = p.pC[(static_cast<size_t>(I) * p.splitc + s) * 128 + r];
+                P += v.x; SL += v.y; SI += v.z; SIL += v.w;
+            }
         }
         const float ratio = p.T / p.Tb;
         const float c = ratio / static_cast<float>(p.n_valid);
@@ -1287,10 +1208,12 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], const f32x2 (
 }
 // The same for a tile that mixes classes: both polynomials, selected per element by label equality.  `cq` points
 // at the same-class column polynomials in global memory (L1-resident: every row of the tile reads the same words).
+// `self` is the tile-local column of the row's own pair (0..31 inside this chunk, anything else = none): that
+// element is neither a denominator nor a positive pair, only the linear term survives: 2 p (a s + b) = fma(s, l1, l0).
 template <int kDeg>
 __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const f32x2 (&rn)[5], const f32x2 (&rq)[5],
                                                  const float4* __restrict__ cp, const float4* __restrict__ cq, int yi,
-                                                 uint32_t (&pk)[16]) {
+                                                 int self, float l1, float l0, uint32_t (&pk)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const f32x2 s = pack2u(v[2 * j], v[2 * j + 1]);
@@ -1306,8 +1229,10 @@ __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const 
         float nl, nh, pl, ph;
         unpack2(gn, nl, nh);
         unpack2(gp, pl, ph);
-        const float lo = (__float_as_int(n2.z) == yi) ? pl : nl;
-        const float hi = (__float_as_int(n2.w) == yi) ? ph : nh;
+        float lo = (__float_as_int(n2.z) == yi) ? pl : nl;
+        float hi = (__float_as_int(n2.w) == yi) ? ph : nh;
+        if (self == 2 * j) lo = fmaf(__uint_as_float(v[2 * j]), l1, l0);
+        if (self == 2 * j + 1) hi = fmaf(__uint_as_float(v[2 * j + 1]), l1, l0);
         __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
         pk[j] = *reinterpret_cast<uint32_t*>(&b2);
     }
@@ -1510,14 +1435,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 const float4* cp = gCP + slot * (SmemBwd::kCoefBytes / 16);
                 const int col0 = J * 128;
                 const uint32_t tS = tmem + st * 128 + lane_off;
-                // Tile classes (pixel term): no same-class pair -> one polynomial per side; mixed classes away from
-                // the diagonal and every Den large -> two polynomials selected per element; otherwise (diagonal
-                // tile, tiny denominators, image term) the exact masked form.  Padding needs no mask: padded F
+                // Tile classes (pixel term): no same-class pair -> one polynomial per side; mixed classes and every
+                // Den large -> two polynomials selected per element (+ the self pair on the diagonal tile);
+                // otherwise (tiny denominators, image term) the exact masked form.  Padding needs no mask: padded F
                 // rows are zero and padded columns carry zero coefficients.
                 const bool overlap = ranges_overlap(rI, sRange[J]);
                 const bool fast = kMode == DCL_MODE_PIXEL && !overlap;
-                const bool series = kMode == DCL_MODE_PIXEL && overlap && (p.rb0 + I) != J &&
-                                    fminf(denI, p.bden[J]) >= kMinDenSeries;
+                const bool series = kMode == DCL_MODE_PIXEL && overlap && fminf(denI, p.bden[J]) >= kMinDenSeries;
                 if (p.debug & 1) {
                     // diagnostics: no G is produced
                 } else if (fast) {
@@ -1534,10 +1458,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                     else body(std::integral_constant<int, 4>{});
                 } else if (series) {
                     const float4* cq = reinterpret_cast<const float4*>(p.coefPP) + static_cast<size_t>(J) * 64 * 3;
+                    const int selfcol = ((p.rb0 + I) == J) ? r : -1000;
+                    const float l1 = 2.f * rA.z * rA.x, l0 = 2.f * rA.z * rA.y;
                     auto body = [&](auto degc) {
                         for_each_chunk_loop(tS, [&](int c0, const uint32_t (&v)[32]) {
                             uint32_t pk[16];
-                            bwd_chunk_masked<decltype(degc)::value>(v, rn, rq, cp + (c0 >> 1) * 3, cq + (c0 >> 1) * 3, yi, pk);
+                            bwd_chunk_masked<decltype(degc)::value>(v, rn, rq, cp + (c0 >> 1) * 3, cq + (c0 >> 1) * 3, yi,
+                                                                    selfcol - c0, l1, l0, pk);
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
                     };
@@ -1636,7 +1563,7 @@ __global__ void __launch_bounds__(256) k_reduce_dF(const Params p, float* __rest
     *reinterpret_cast<float4*>(dF + static_cast<size_t>(row) * 128 + lane * 4) = acc;
 }
 
-// block info only (legacy forward and the backward entry point, which do not run k_gram)
+// block info (first kernel of every forward / backward call; also resets the device-side scalars)
 __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
     __shared__ int si[12];
     __shared__ float sf[8];
@@ -1647,7 +1574,7 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
     if (t == 0) {
         p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
         p.bnorm[J] = make_float2(b.cx, b.cn);
-        if (J == 0) p.iscal[3] = 1;
+        if (J == 0) { p.iscal[0] = 1; p.iscal[3] = 1; p.iscal[4] = 0; p.ticket[0] = 0u; }
     }
 }
 
@@ -1656,10 +1583,9 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
 // ---------------------------------------------------------------------------------------------
 struct Layout {
     Part partS, partD;
-    int nP, maxsegS, maxsegD, splitc, gramP, ctas;
-    size_t off_binfo, off_bnorm, off_pA, off_pB, off_gram, off_fsum, off_cmaxp, off_ref, off_Mc, off_mu, off_scal,
-        off_iscal, off_rowq, off_pF, off_rowS, off_rowD, off_pC, off_bl,
-        off_ticket, off_coefR, off_coefP, off_coefPP, off_bden, off_pD, bytes;
+    int nP, maxsegS, maxsegD, splitc, ctas;
+    size_t off_binfo, off_bnorm, off_pA, off_pB, off_iscal, off_pF, off_pH, off_rowM, off_rowPos, off_rowS, off_rowD,
+        off_pC, off_bl, off_ticket, off_coefR, off_coefP, off_coefPP, off_bden, off_pD, bytes;
 };
 
 static int g_debug_flags = 0;
@@ -1684,24 +1610,18 @@ static Layout make_layout(int nI, int nJ) {
     make_part(L.partD, L.maxsegD, nI, nJ, ctas);
     int sc = (ctas + L.nP - 1) / L.nP;
     L.splitc = sc < 1 ? 1 : (sc > 8 ? 8 : sc);
-    L.gramP = nJ < ctas ? nJ : ctas;
     const size_t rows = static_cast<size_t>(nI) * 128, allrows = static_cast<size_t>(nJ) * 128;
     size_t o = 0;
     auto take = [&](size_t& off, size_t bytes) { off = o; o = align_up(o + bytes, 256); };
     take(L.off_binfo, sizeof(int4) * nJ);
     take(L.off_bnorm, sizeof(float2) * nJ);
-    take(L.off_pA, sizeof(float4) * rows * L.maxsegS * 3);    // legacy A partials; the v3 power-sum partials (pF) share it
-    take(L.off_pB, sizeof(float2) * rows * L.maxsegS);
-    take(L.off_gram, sizeof(float) * 16384 * static_cast<size_t>(L.gramP));
-    take(L.off_fsum, sizeof(float) * 128 * L.gramP);
-    take(L.off_cmaxp, sizeof(float) * L.gramP);
-    take(L.off_ref, sizeof(float) * 128);
-    take(L.off_Mc, sizeof(float) * 16384);
-    take(L.off_mu, sizeof(float) * 128);
-    take(L.off_scal, sizeof(float) * 8);
+    take(L.off_pA, sizeof(float4) * rows * L.maxsegS * 2);    // legacy A partials; the v3 sweep-P partials (pF) share it
+    take(L.off_pB, sizeof(float4) * rows * L.maxsegS * 2);    // legacy B partials; the v3 sweep-H partials (pH) share it
     take(L.off_iscal, sizeof(int) * 8);
-    take(L.off_rowq, sizeof(float2) * rows);
     L.off_pF = L.off_pA;
+    L.off_pH = L.off_pB;
+    take(L.off_rowM, sizeof(float) * 8 * rows);
+    take(L.off_rowPos, sizeof(float4) * rows);
     take(L.off_rowS, sizeof(float4) * rows);
     take(L.off_rowD, sizeof(float4) * rows);
     take(L.off_pC, sizeof(float4) * rows * L.splitc);
@@ -1730,21 +1650,15 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.maxsegS = L.maxsegS;
     p.maxsegD = L.maxsegD;
     p.splitc = L.splitc;
-    p.gramP = L.gramP;
     p.binfo = reinterpret_cast<int4*>(w + L.off_binfo);
     p.bnorm = reinterpret_cast<float2*>(w + L.off_bnorm);
     p.pA = reinterpret_cast<float4*>(w + L.off_pA);
     p.pB = reinterpret_cast<float2*>(w + L.off_pB);
-    p.gram_part = reinterpret_cast<float*>(w + L.off_gram);
-    p.fsum_part = reinterpret_cast<float*>(w + L.off_fsum);
-    p.cmax_part = reinterpret_cast<float*>(w + L.off_cmaxp);
-    p.ref = reinterpret_cast<float*>(w + L.off_ref);
-    p.Mc = reinterpret_cast<float*>(w + L.off_Mc);
-    p.mu = reinterpret_cast<float*>(w + L.off_mu);
-    p.scal = reinterpret_cast<float*>(w + L.off_scal);
     p.iscal = reinterpret_cast<int*>(w + L.off_iscal);
-    p.rowq = reinterpret_cast<float2*>(w + L.off_rowq);
     p.pF = reinterpret_cast<float4*>(w + L.off_pF);
+    p.pH = reinterpret_cast<float4*>(w + L.off_pH);
+    p.rowM = reinterpret_cast<float*>(w + L.off_rowM);
+    p.rowPos = reinterpret_cast<float4*>(w + L.off_rowPos);
     p.rowS = reinterpret_cast<float4*>(w + L.off_rowS);
     p.rowD = reinterpret_cast<float4*>(w + L.off_rowD);
     p.pC = reinterpret_cast<float4*>(w + L.off_pC);
@@ -1766,29 +1680,27 @@ static int set_smem(K kernel, int bytes) {
     return 0;
 }
 
-constexpr int kGramSmem = 128 * kGramLd * 4;
-constexpr int kRowstatSmem = 2 * 128 * kGramLd * 4;
-
-// v3 pixel forward: closed-form row norms, one power-sum sweep, per-row combination, sweep C, finalize
+// v3 pixel forward: block info, one power-sum sweep, per-row combination; the higher-moment sweep and the exact
+// positive-pair sweep C are launched too but leave at once unless k_combine1 raised their triggers
 static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (int e = set_smem(k_gram, kGramSmem)) return e;
-        if (int e = set_smem(k_rowstats, kRowstatSmem)) return e;
         if (int e = set_smem(k_sweep<SWEEP_P, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
+        if (int e = set_smem(k_sweep<SWEEP_H, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
         if (int e = set_smem(k_sweep<SWEEP_C, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
         configured = true;
     }
-    k_gram<<<L.gramP, 256, kGramSmem, st>>>(p);
-    DCL_LAUNCH_CHECK("k_gram");
-    k_gram_reduce<<<64, 256, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_gram_reduce");
-    k_rowstats<<<p.nI, 256, kRowstatSmem, st>>>(p);
-    DCL_LAUNCH_CHECK("k_rowstats");
+    p.use_series = 1;
+    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_blockinfo");
     k_sweep<SWEEP_P, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<P>");
-    k_combine_P<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine_P");
+    k_combine1<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine1");
+    k_sweep<SWEEP_H, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
+    DCL_LAUNCH_CHECK("k_sweep<H>");
+    k_combine2<<<p.nI, 128, 0, st>>>(p);
+    DCL_LAUNCH_CHECK("k_combine2");
     k_sweep<SWEEP_C, DCL_MODE_PIXEL><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
     DCL_LAUNCH_CHECK("k_sweep<C>");
     k_finalize<DCL_MODE_PIXEL><<<p.nI, 128, 0, st>>>(p);

@@ -21,10 +21,11 @@ L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
 torch.cuda.synchronize()
 lib.dcl_debug_trace(None)
 t = buf.cpu().view(5, 32, 8)
-base = int(t[:, 4:, :][t[:, 4:, :] > 0].min())
+base = int(t[0, 0, 7])
+print("kernel entry 0, set-up done", int(t[0, 2, 7]) - base, ", all roles done", int(t[0, 1, 7]) - base)
 print(f"forward sweep, n={n}")
 print("tile | prod: wait_e got_e | issuer(it%2): wait_full got_full got_te0 got_turn got_te1 issued | g0: start got_tfull done | g1: start got_tfull done")
-for it in range(4, 30):
+for it in range(0, 30):
     r = lambda role, ev: (int(t[role, it, ev]) - base) if int(t[role, it, ev]) else -1
     i = 1 + (it & 1)
     print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(i,0):6d} {r(i,1):6d} {r(i,2):6d} {r(i,4):6d} {r(i,5):6d} {r(i,3):6d} | "
