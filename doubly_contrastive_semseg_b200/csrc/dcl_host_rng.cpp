@@ -25,16 +25,32 @@ struct Mt {
     uint32_t next;
 };
 
-inline uint32_t mix(uint32_t u, uint32_t v) {
+inline __attribute__((always_inline)) uint32_t mix(uint32_t u, uint32_t v) {
     uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-    return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+    return (y >> 1) ^ ((0u - (v & 1u)) & 0x9908b0dfu);       // branch-free: vectorises
 }
 
-void twist(Mt& m) {
-    uint32_t* s = m.s;
+// State regeneration.  Nearly all of the sampler's host time is spent here (one regeneration per 624 draws, and
+// every pixel of the batch is one draw), so the loops are written to vectorise: element i reads i+1 and i+397
+// (not yet rewritten) in the first loop and i-227 (rewritten 227 iterations earlier) in the second, i.e. no
+// dependence closer than the vector width.
+inline __attribute__((always_inline)) void twist_body(uint32_t* __restrict__ s) {
+#pragma GCC ivdep
     for (int i = 0; i < kN - kM; ++i) s[i] = s[i + kM] ^ mix(s[i], s[i + 1]);
+    // split the second range so that the vectorised part never reads an element written inside the same vector
+#pragma GCC ivdep
     for (int i = kN - kM; i < kN - 1; ++i) s[i] = s[i + kM - kN] ^ mix(s[i], s[i + 1]);
     s[kN - 1] = s[kM - 1] ^ mix(s[kN - 1], s[0]);
+}
+__attribute__((target("avx512f"))) void twist_avx512(uint32_t* s) { twist_body(s); }
+__attribute__((target("avx2"))) void twist_avx2(uint32_t* s) { twist_body(s); }
+void twist_generic(uint32_t* s) { twist_body(s); }
+
+void twist(Mt& m) {
+    static const int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    if (isa == 2) twist_avx512(m.s);
+    else if (isa == 1) twist_avx2(m.s);
+    else twist_generic(m.s);
     m.left = kN;
     m.next = 0;
 }
@@ -67,30 +83,31 @@ inline void skip(Mt& m, int64_t cnt) {
     }
 }
 
-// tiny open-addressing map for the sparse Fisher-Yates state (only touched positions are stored)
+// Sparse Fisher-Yates state: positions [0, k) live in a dense array, the (at most k) touched positions >= k in a
+// small open-addressing map with key and value side by side.
 struct Sparse {
-    std::vector<int64_t> key, val;
-    uint64_t mask;
-    void reset(int k) {
+    struct Slot { int32_t key, val; };
+    std::vector<Slot> tab;
+    std::vector<uint32_t> used;        // slots filled by the current permutation (cleared on reset)
+    std::vector<int32_t> front;
+    uint32_t mask = 0;
+    void reset(int64_t k) {
         size_t cap = 16;
-        while (cap < static_cast<size_t>(4 * k + 4)) cap <<= 1;
-        key.assign(cap, -1);
-        val.resize(cap);
-        mask = cap - 1;
+        while (cap < static_cast<size_t>(2 * k + 4)) cap <<= 1;
+        if (tab.size() != cap) {
+            tab.assign(cap, Slot{-1, 0});
+            mask = static_cast<uint32_t>(cap - 1);
+        } else {
+            for (uint32_t h : used) tab[h].key = -1;
+        }
+        used.clear();
+        front.resize(static_cast<size_t>(k));
+        for (int64_t i = 0; i < k; ++i) front[i] = static_cast<int32_t>(i);
     }
-    size_t slot(int64_t k) const {
-        size_t h = (static_cast<uint64_t>(k) * 0x9E3779B97F4A7C15ull) & mask;
-        while (key[h] != -1 && key[h] != k) h = (h + 1) & mask;
+    uint32_t slot(int32_t k) const {
+        uint32_t h = (static_cast<uint32_t>(k) * 0x9E3779B1u >> 12) & mask;
+        while (tab[h].key != -1 && tab[h].key != k) h = (h + 1) & mask;
         return h;
-    }
-    int64_t get(int64_t k) const {
-        size_t h = slot(k);
-        return key[h] == k ? val[h] : k;
-    }
-    void set(int64_t k, int64_t v) {
-        size_t h = slot(k);
-        key[h] = k;
-        val[h] = v;
     }
 };
 
@@ -100,33 +117,38 @@ void randperm_prefix(Mt& m, int64_t n, int64_t k, int64_t* out, Sparse& sp) {
         return;
     }
     if (k > n) k = n;
-    sp.reset(static_cast<int>(k));
+    sp.reset(k);
     int64_t drawn = 0;
     for (int64_t i = 0; i < k; ++i) {
         int64_t j = i;
         if (i < n - 1) {
-            j = i + static_cast<int64_t>(draw(m) % static_cast<uint64_t>(n - i));
+            j = i + static_cast<int64_t>(draw(m) % static_cast<uint32_t>(n - i));   // n < 2^31: 32-bit modulo, same value
             ++drawn;
         }
-        const int64_t vi = sp.get(i), vj = sp.get(j);
-        sp.set(i, vj);
-        sp.set(j, vi);
-        out[i] = vj;
+        const int32_t vi = sp.front[i];
+        if (j < k) {
+            out[i] = sp.front[j];
+            sp.front[j] = vi;
+        } else {
+            const uint32_t h = sp.slot(static_cast<int32_t>(j));
+            Sparse::Slot& t = sp.tab[h];
+            if (t.key == static_cast<int32_t>(j)) {
+                out[i] = t.val;
+            } else {
+                out[i] = j;
+                t.key = static_cast<int32_t>(j);
+                sp.used.push_back(h);
+            }
+            t.val = vi;
+        }
     }
     skip(m, (n - 1) - drawn);
 }
 
-}  // namespace
-
-extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int n_view,
-                                     const int64_t* num_hard, const int64_t* num_easy,
-                                     const int64_t* keep_hard, int64_t* ranks) {
+int load_state(void* torch_rng_state, size_t state_bytes, Mt& m) {
     if (!torch_rng_state || state_bytes < 24 + 8 * static_cast<size_t>(kN))
         return dcl::fail(DCL_ERR_ARG, "rng state buffer too small (%zu bytes)", state_bytes);
-    if (A < 0 || n_view < 0 || (A > 0 && (!num_hard || !num_easy || !keep_hard || !ranks)))
-        return dcl::fail(DCL_ERR_ARG, "bad argument");
-    uint8_t* raw = static_cast<uint8_t*>(torch_rng_state);
-    Mt m;
+    const uint8_t* raw = static_cast<const uint8_t*>(torch_rng_state);
     int32_t left;
     uint64_t next;
     std::memcpy(&left, raw + 8, 4);
@@ -137,6 +159,114 @@ extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, 
     m.next = static_cast<uint32_t>(next);
     if (m.left < 0 || m.left > kN || m.next > static_cast<uint32_t>(kN))
         return dcl::fail(DCL_ERR_ARG, "unexpected generator state (left=%d next=%u)", m.left, m.next);
+    return 0;
+}
+void store_state(void* torch_rng_state, const Mt& m) {
+    uint8_t* raw = static_cast<uint8_t*>(torch_rng_state);
+    const int32_t left = m.left;
+    const uint64_t next = m.next;
+    std::memcpy(raw + 8, &left, 4);
+    std::memcpy(raw + 16, &next, 8);
+    uint64_t* sw = reinterpret_cast<uint64_t*>(raw + 24);
+    for (int i = 0; i < kN; ++i) sw[i] = m.s[i];
+}
+
+}  // namespace
+
+// Whole host side of the sampler in one call (loss.py:264-337 minus the tensor indexing): class list, n_view,
+// split rule, the randperm draws and the class-sorted device row layout.
+//   counts [B][256][2] i32 : pixels per (image, label, hard|easy) from dcl_sample_classify
+//   info out [4] i32      : A, n_view, n (valid rows), n_pad
+//   anchor arrays out     : image, cls, num_hard, num_easy, keep_hard [A <= B*256] i64; ranks [A*n_view] i64
+//   row arrays out        : req [n_pad*4] i32 (image, label, easy, rank; -1 padding), y [n_pad] i32,
+//                           ref_row [n_pad] i64 (v*A + a in the reference's order), anchor [n_pad] i64
+//   the caller sizes the row arrays for max_samples rounded up to 128 (+128).
+// Returns 0, 1 when no class qualifies (the reference's `return None, None`, loss.py:287-288), 2 when the
+// split rule hits the reference's "this shoud be never touched" branch (info[0..2] = num_hard, num_easy, n_view),
+// or a negative dcl_status.
+extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_samples, int max_views,
+                                  void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                                  int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
+                                  int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor) {
+    if (!counts || !info || B <= 0) return dcl::fail(DCL_ERR_ARG, "bad argument");
+    int A = 0;
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < 256; ++c) {
+            const int64_t nh = counts[(b * 256 + c) * 2], ne = counts[(b * 256 + c) * 2 + 1];
+            if (c == ignore_label || nh + ne <= max_views) continue;          // loss.py:281-282
+            image[A] = b; cls[A] = c; num_hard[A] = nh; num_easy[A] = ne;
+            ++A;
+        }
+    info[0] = A; info[1] = 0; info[2] = 0; info[3] = 0;
+    if (A == 0) return 1;
+    int n_view = max_samples / A;                                              // loss.py:290-291
+    if (n_view > max_views) n_view = max_views;
+    info[1] = n_view;
+    const double half = n_view / 2.0;                                          // true division, loss.py:314
+    for (int a = 0; a < A; ++a) {
+        const int64_t nh = num_hard[a], ne = num_easy[a];
+        if (nh >= half && ne >= half) keep_hard[a] = n_view / 2;
+        else if (nh >= half) keep_hard[a] = n_view - ne;
+        else if (ne >= half) keep_hard[a] = nh;
+        else {
+            info[0] = static_cast<int32_t>(nh); info[1] = static_cast<int32_t>(ne); info[2] = n_view;
+            return 2;
+        }
+    }
+    if (n_view > 0) {
+        Mt m;
+        if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
+        Sparse sp;
+        for (int a = 0; a < A; ++a) {
+            const int64_t kh = keep_hard[a], ke = n_view - kh;
+            if (kh < 0 || ke < 0 || kh > num_hard[a] || ke > num_easy[a] || num_hard[a] >= 214748364 ||
+                num_easy[a] >= 214748364)
+                return dcl::fail(DCL_ERR_ARG, "anchor %d: keep (%lld,%lld) exceeds counts (%lld,%lld)", a,
+                                 (long long)kh, (long long)ke, (long long)num_hard[a], (long long)num_easy[a]);
+            randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
+            randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
+        }
+        store_state(torch_rng_state, m);
+    }
+    // rows: anchors stably sorted by class (counting sort), views contiguous per anchor
+    const int n = A * n_view;
+    int n_pad = (n + 127) / 128 * 128;
+    if (n_pad < 128) n_pad = 128;
+    info[2] = n; info[3] = n_pad;
+    std::vector<int> start(257, 0), order(A);
+    for (int a = 0; a < A; ++a) ++start[cls[a] + 1];
+    for (int c = 0; c < 256; ++c) start[c + 1] += start[c];
+    for (int a = 0; a < A; ++a) order[start[cls[a]]++] = a;
+    int row = 0;
+    for (int o = 0; o < A; ++o) {
+        const int a = order[o];
+        const int64_t* rk = ranks + static_cast<size_t>(a) * n_view;
+        for (int v = 0; v < n_view; ++v, ++row) {
+            req[row * 4 + 0] = static_cast<int32_t>(image[a]);
+            req[row * 4 + 1] = static_cast<int32_t>(cls[a]);
+            req[row * 4 + 2] = v >= keep_hard[a];
+            req[row * 4 + 3] = static_cast<int32_t>(rk[v]);
+            y[row] = static_cast<int32_t>(cls[a]);
+            ref_row[row] = static_cast<int64_t>(v) * A + a;
+            anchor[row] = a;
+        }
+    }
+    for (; row < n_pad; ++row) {
+        req[row * 4 + 0] = req[row * 4 + 1] = req[row * 4 + 2] = req[row * 4 + 3] = -1;
+        y[row] = -1;
+        ref_row[row] = -1;
+        anchor[row] = -1;
+    }
+    return 0;
+}
+
+extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int n_view,
+                                     const int64_t* num_hard, const int64_t* num_easy,
+                                     const int64_t* keep_hard, int64_t* ranks) {
+    if (A < 0 || n_view < 0 || (A > 0 && (!num_hard || !num_easy || !keep_hard || !ranks)))
+        return dcl::fail(DCL_ERR_ARG, "bad argument");
+    Mt m;
+    if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
     Sparse sp;
     for (int a = 0; a < A; ++a) {
         const int64_t kh = keep_hard[a], ke = n_view - kh;
@@ -147,11 +277,6 @@ extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, 
         randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
         randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
     }
-    left = m.left;
-    next = m.next;
-    std::memcpy(raw + 8, &left, 4);
-    std::memcpy(raw + 16, &next, 8);
-    uint64_t* sw = reinterpret_cast<uint64_t*>(raw + 24);
-    for (int i = 0; i < kN; ++i) sw[i] = m.s[i];
+    store_state(torch_rng_state, m);
     return 0;
 }

@@ -302,7 +302,7 @@ class _PixelContrastFn(torch.autograd.Function):
     """loss(feats) for a fixed set of sampled anchor pixels; gradient only w.r.t. feats."""
 
     @staticmethod
-    def forward(ctx, feats, pix, y_dev, n_valid, T, Tb):
+    def forward(ctx, feats, pix, y_dev, n_valid, T, Tb, dzero=None):
         B, C, h, w = feats.shape
         n_pad = pix.shape[0]
         tiles, sqnorm = gather_tiles(feats, pix, n_pad)
@@ -311,6 +311,7 @@ class _PixelContrastFn(torch.autograd.Function):
                                                          MODE_PIXEL, T, Tb)
         ctx.save_for_backward(tiles, y_dev, colA, colB, pix)
         ctx.meta = dict(nJ=nJ, rb0=0, nI=nJ, n_local_pad=n_pad, shape=(B, C, h, w))
+        ctx.dzero = dzero          # dense gradient buffer zero-filled while the host planned the sample
         return (loss_sum / n_valid).reshape(())
 
     @staticmethod
@@ -319,12 +320,18 @@ class _PixelContrastFn(torch.autograd.Function):
         m = ctx.meta
         dF = contrast_backward(tiles, y, colA, colB, m["nJ"], m["rb0"], m["nI"], MODE_PIXEL)
         B, C, h, w = m["shape"]
-        dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
         g = grad_out.to(torch.float32).contiguous()
-        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
-                  _stream())
-        _count(2)
-        return dfeats, None, None, None, None, None
+        dfeats, ctx.dzero = ctx.dzero, None
+        if dfeats is None:
+            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
+            _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
+                      _stream())
+            _count(2)
+        else:
+            _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 0,
+                      _stream())
+            _count(1)
+        return dfeats, None, None, None, None, None, None
 
 
 class _ContrastRowsFn(torch.autograd.Function):
@@ -416,6 +423,76 @@ class PixelContrastLoss(nn.Module):
         self.last_pix: Optional[torch.Tensor] = None
 
     # ---- sampling front end ------------------------------------------------------------------
+    def _host_buffers(self, B, dev):
+        """Persistent pinned staging for the one D2H (count table) and the one H2D (row requests) of a step, plus
+        the host arrays dcl_host_plan_rows fills; re-made only when the batch or max_samples grows."""
+        cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
+        key = (B, cap, str(dev))
+        hb = getattr(self, "_hb", None)
+        if hb is None or hb["key"] != key:
+            A_cap = B * 256
+            hb = dict(key=key, cap=cap,
+                      counts=torch.empty(B * _BINS, dtype=torch.int32).pin_memory(),
+                      stage=torch.empty(cap * 5, dtype=torch.int32).pin_memory(),       # req [cap*4] | y [cap]
+                      info=np.zeros(4, dtype=np.int32),
+                      anchors=np.empty((5, A_cap), dtype=np.int64),
+                      ranks=np.empty(max(int(self.max_samples), 1), dtype=np.int64),
+                      rows=np.empty((2, cap), dtype=np.int64),
+                      event=torch.cuda.Event())
+            hb["stage_np"] = hb["stage"].numpy()
+            hb["counts_np"] = hb["counts"].numpy()
+            self._hb = hb
+        return hb
+
+    def _sample_fast(self, feats, labels, predict, want_grad):
+        """classify -> (GPU: zero-fill of the gradient buffer) || (host: dcl_host_plan_rows) -> select.
+        Same results as _sample + layout_rows; used when the C replay of torch's generator is verified."""
+        B, C, h, w = feats.shape
+        dev = feats.device
+        hb = self._host_buffers(B, dev)
+        code, chunk, counts = classify(labels, predict, h, w)
+        hb["counts"].copy_(counts.view(-1), non_blocking=True)
+        hb["event"].record()
+        dzero = None
+        if want_grad:
+            dzero = torch.zeros_like(feats)            # runs on the GPU while the host plans below
+            _count(1)
+        hb["event"].synchronize()                      # the one unavoidable sync: the count table
+        st = torch.get_rng_state()
+        sbuf = st.numpy()
+        cap, stage, an, rows, info = hb["cap"], hb["stage_np"], hb["anchors"], hb["rows"], hb["info"]
+        rc = _lib.load().dcl_host_plan_rows(
+            hb["counts_np"].ctypes.data, B, int(self.ignore_label), int(self.max_samples), int(self.max_views),
+            sbuf.ctypes.data, sbuf.nbytes, info.ctypes.data, an[0].ctypes.data, an[1].ctypes.data,
+            an[2].ctypes.data, an[3].ctypes.data, an[4].ctypes.data, hb["ranks"].ctypes.data,
+            stage.ctypes.data, stage[cap * 4:].ctypes.data, rows[0].ctypes.data, rows[1].ctypes.data)
+        if rc == 1:
+            self.last_plan = None
+            return None
+        if rc == 2:
+            print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
+            raise Exception
+        if rc != 0:
+            raise _lib.DclError("dcl_host_plan_rows failed with status %d: %s"
+                                % (rc, _lib.load().dcl_last_error().decode("utf-8", "replace")))
+        torch.set_rng_state(st)
+        A, n_view, n, n_pad = (int(v) for v in info)
+        self.last_plan = AnchorPlan(A, n_view, an[0, :A].copy(), an[1, :A].copy(), an[2, :A].copy(),
+                                    an[3, :A].copy(), an[4, :A].copy(),
+                                    hb["ranks"][: A * n_view].reshape(A, n_view).copy())
+        if n_view <= 0:
+            raise RuntimeError("max_samples // total_classes == 0: no views to sample "
+                               "(the reference fails in torch.cat at loss.py:345)")
+        self.last_layout = RowLayout(n, n_pad, stage[: n_pad * 4].reshape(n_pad, 4).copy(),
+                                     stage[cap * 4: cap * 4 + n_pad].copy(), rows[0, :n_pad].copy(),
+                                     rows[1, :n_pad].copy())
+        packed = hb["stage"].to(dev, non_blocking=True)
+        req_dev = packed[: n_pad * 4]
+        y_dev = packed[cap * 4: cap * 4 + n_pad]
+        pix = select_pixels(code, chunk, B, h * w, req_dev, n_pad)
+        self.last_pix = pix
+        return pix, y_dev, n, dzero
+
     def _sample(self, feats, labels, predict):
         B, C, h, w = feats.shape
         code, chunk, counts = classify(labels, predict, h, w)
@@ -460,6 +537,14 @@ class PixelContrastLoss(nn.Module):
         feats_c = feats.contiguous().to(torch.float32)
         labels_c = labels.contiguous().to(torch.int64)
         predict_c = predict.detach().contiguous().to(torch.float32)
+        if _verify_host_rng():
+            sampled = self._sample_fast(feats_c, labels_c, predict_c,
+                                        feats_c.requires_grad and torch.is_grad_enabled())
+            if sampled is None:
+                return feats_c.sum() * 0.0
+            pix, y_dev, n_valid, dzero = sampled
+            return _PixelContrastFn.apply(feats_c, pix, y_dev, n_valid, self.temperature,
+                                          self.base_temperature, dzero)
         sampled = self.sample(feats_c, labels_c, predict_c)
         if sampled is None:
             return feats_c.sum() * 0.0

@@ -102,6 +102,24 @@ int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int 
                           const int64_t* num_hard, const int64_t* num_easy, const int64_t* keep_hard,
                           int64_t* ranks);
 
+/* Host-side (no GPU work): the whole host half of _hard_anchor_sampling in one call - class list and
+ * n_view (loss.py:278-291), split rule (:314-325), the randperm draws (:327-330, generator advanced
+ * exactly as the reference's calls would) and the class-sorted device row layout that
+ * dcl_sample_select / dcl_gather_tiles consume.
+ *   counts [B][256][2] i32 host (from dcl_sample_classify), torch_rng_state as above
+ *   info [4] out: A (anchors = reference `total_classes`), n_view, n (valid rows), n_pad
+ *   image, cls, num_hard, num_easy, keep_hard [>= B*256] i64 out; ranks [>= max_samples] i64 out
+ *   req [4*n_cap] i32 out (image, label, easy, rank; -1 = padding row), y [n_cap] i32 out,
+ *   ref_row [n_cap] i64 out (row index v*A + a in the reference's ordering), anchor [n_cap] i64 out,
+ *   n_cap >= max_samples rounded up to 128 (and >= 128)
+ * Returns 0; 1 when no class qualifies (reference: `return None, None`, loss.py:287-288); 2 when the
+ * split rule reaches the reference's "this shoud be never touched" branch (info = num_hard, num_easy,
+ * n_view of the offending anchor); negative dcl_status on bad arguments. */
+int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_samples, int max_views,
+                       void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                       int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
+                       int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor);
+
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.
