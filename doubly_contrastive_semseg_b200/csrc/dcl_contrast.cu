@@ -1104,7 +1104,8 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
         float s = 0.f;
         const volatile float* bl = p.blockloss;
         for (int i = 0; i < p.nI; ++i) s += bl[i];
-        *p.loss_sum = s;
+        p.loss_sum[0] = s;
+        p.loss_sum[1] = s / static_cast<float>(p.n_valid);      // the loss itself when the rows are not sharded
     }
 }
 
@@ -1241,6 +1242,7 @@ __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const 
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     extern __shared__ uint8_t smem_raw[];
+    if (threadIdx.x == 0) trace_stamp(p, 0, 0, 7);          // kernel entry
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sI = base + SmemBwd::kI;
@@ -1280,6 +1282,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (threadIdx.x == 0) trace_stamp(p, 0, 2, 7);          // set-up done
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tD = tmem + 384;          // dF accumulator; S/G stage st lives at tmem + st*128
 
@@ -1544,6 +1547,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(p, 0, 1, 7);          // all roles done
     if (warp == kProducerWarp) tmem_dealloc<kTmemCols>(tmem);
 }
 

@@ -12,6 +12,7 @@
 // randperm(n) for n < 2^32/20: r = arange(n); for i < n-1: z = u32() % (n-i); swap(r[i], r[i+z]).
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "dcl_common.cuh"
 
@@ -174,21 +175,15 @@ void store_state(void* torch_rng_state, const Mt& m) {
 }  // namespace
 
 // Whole host side of the sampler in one call (loss.py:264-337 minus the tensor indexing): class list, n_view,
-// split rule, the randperm draws and the class-sorted device row layout.
-//   counts [B][256][2] i32 : pixels per (image, label, hard|easy) from dcl_sample_classify
-//   info out [4] i32      : A, n_view, n (valid rows), n_pad
-//   anchor arrays out     : image, cls, num_hard, num_easy, keep_hard [A <= B*256] i64; ranks [A*n_view] i64
-//   row arrays out        : req [n_pad*4] i32 (image, label, easy, rank; -1 padding), y [n_pad] i32,
-//                           ref_row [n_pad] i64 (v*A + a in the reference's order), anchor [n_pad] i64
-//   the caller sizes the row arrays for max_samples rounded up to 128 (+128).
-// Returns 0, 1 when no class qualifies (the reference's `return None, None`, loss.py:287-288), 2 when the
-// split rule hits the reference's "this shoud be never touched" branch (info[0..2] = num_hard, num_easy, n_view),
-// or a negative dcl_status.
-extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_samples, int max_views,
-                                  void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
-                                  int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
-                                  int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor) {
-    if (!counts || !info || B <= 0) return dcl::fail(DCL_ERR_ARG, "bad argument");
+// split rule, the randperm draws and the class-sorted device row layout.  Shared by the single-process entry point
+// and the sharded one: `world` ranks own `Bl` consecutive images each; every rank replays the SAME generator stream
+// over the global batch, but only draws the permutations of its own anchors (the others just advance the state).
+static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignore_label, int max_samples,
+                     int max_views, void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                     int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard, int64_t* ranks,
+                     int32_t* req, int32_t* y_all, int64_t* ref_row, int64_t* anchor) {
+    if (!counts || !info || Bl <= 0 || world <= 0 || rank < 0 || rank >= world) return dcl::fail(DCL_ERR_ARG, "bad argument");
+    const int B = Bl * world;
     int A = 0;
     for (int b = 0; b < B; ++b)
         for (int c = 0; c < 256; ++c) {
@@ -197,7 +192,8 @@ extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label
             image[A] = b; cls[A] = c; num_hard[A] = nh; num_easy[A] = ne;
             ++A;
         }
-    info[0] = A; info[1] = 0; info[2] = 0; info[3] = 0;
+    for (int i = 0; i < 6; ++i) info[i] = 0;
+    info[0] = A;
     if (A == 0) return 1;
     int n_view = max_samples / A;                                              // loss.py:290-291
     if (n_view > max_views) n_view = max_views;
@@ -213,6 +209,7 @@ extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label
             return 2;
         }
     }
+    const int lo = rank * Bl, hi = lo + Bl;
     if (n_view > 0) {
         Mt m;
         if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
@@ -223,41 +220,95 @@ extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label
                 num_easy[a] >= 214748364)
                 return dcl::fail(DCL_ERR_ARG, "anchor %d: keep (%lld,%lld) exceeds counts (%lld,%lld)", a,
                                  (long long)kh, (long long)ke, (long long)num_hard[a], (long long)num_easy[a]);
-            randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
-            randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
+            if (image[a] >= lo && image[a] < hi) {
+                randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
+                randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
+            } else {
+                // another rank's anchor: randperm(n) consumes n - 1 draws (none for n <= 1)
+                if (num_hard[a] > 1) skip(m, num_hard[a] - 1);
+                if (num_easy[a] > 1) skip(m, num_easy[a] - 1);
+            }
         }
         store_state(torch_rng_state, m);
     }
-    // rows: anchors stably sorted by class (counting sort), views contiguous per anchor
-    const int n = A * n_view;
-    int n_pad = (n + 127) / 128 * 128;
+    // rows per rank -> common padded block size
+    std::vector<int> per_rank(world, 0);
+    for (int a = 0; a < A; ++a) per_rank[image[a] / Bl] += n_view;
+    int n_max = 0, n_global = 0;
+    for (int r = 0; r < world; ++r) { n_max = per_rank[r] > n_max ? per_rank[r] : n_max; n_global += per_rank[r]; }
+    int n_pad = (n_max + 127) / 128 * 128;
     if (n_pad < 128) n_pad = 128;
-    info[2] = n; info[3] = n_pad;
-    std::vector<int> start(257, 0), order(A);
-    for (int a = 0; a < A; ++a) ++start[cls[a] + 1];
-    for (int c = 0; c < 256; ++c) start[c + 1] += start[c];
-    for (int a = 0; a < A; ++a) order[start[cls[a]]++] = a;
-    int row = 0;
-    for (int o = 0; o < A; ++o) {
-        const int a = order[o];
-        const int64_t* rk = ranks + static_cast<size_t>(a) * n_view;
-        for (int v = 0; v < n_view; ++v, ++row) {
-            req[row * 4 + 0] = static_cast<int32_t>(image[a]);
-            req[row * 4 + 1] = static_cast<int32_t>(cls[a]);
-            req[row * 4 + 2] = v >= keep_hard[a];
-            req[row * 4 + 3] = static_cast<int32_t>(rk[v]);
-            y[row] = static_cast<int32_t>(cls[a]);
-            ref_row[row] = static_cast<int64_t>(v) * A + a;
-            anchor[row] = a;
+    info[2] = per_rank[rank]; info[3] = n_pad; info[4] = n_global;
+    // rows of every rank block: anchors of that rank stably sorted by class (counting sort), views contiguous;
+    // labels for all blocks (y_all), requests / bookkeeping for the local block only
+    std::vector<int> start(257), order(A);
+    for (int r = 0; r < world; ++r) {
+        std::fill(start.begin(), start.end(), 0);
+        const int rlo = r * Bl, rhi = rlo + Bl;
+        int cnt = 0;
+        for (int a = 0; a < A; ++a)
+            if (image[a] >= rlo && image[a] < rhi) { ++start[cls[a] + 1]; ++cnt; }
+        for (int c = 0; c < 256; ++c) start[c + 1] += start[c];
+        for (int a = 0; a < A; ++a)
+            if (image[a] >= rlo && image[a] < rhi) order[start[cls[a]]++] = a;
+        int32_t* yb = y_all + static_cast<size_t>(r) * n_pad;
+        int row = 0;
+        for (int o = 0; o < cnt; ++o) {
+            const int a = order[o];
+            const int64_t* rk = ranks + static_cast<size_t>(a) * n_view;
+            for (int v = 0; v < n_view; ++v, ++row) {
+                yb[row] = static_cast<int32_t>(cls[a]);
+                if (r == rank) {
+                    req[row * 4 + 0] = static_cast<int32_t>(image[a] - lo);
+                    req[row * 4 + 1] = static_cast<int32_t>(cls[a]);
+                    req[row * 4 + 2] = v >= keep_hard[a];
+                    req[row * 4 + 3] = static_cast<int32_t>(rk[v]);
+                    ref_row[row] = static_cast<int64_t>(v) * A + a;
+                    anchor[row] = a;
+                }
+            }
+        }
+        for (; row < n_pad; ++row) {
+            yb[row] = -1;
+            if (r == rank) {
+                req[row * 4 + 0] = req[row * 4 + 1] = req[row * 4 + 2] = req[row * 4 + 3] = -1;
+                ref_row[row] = -1;
+                anchor[row] = -1;
+            }
         }
     }
-    for (; row < n_pad; ++row) {
-        req[row * 4 + 0] = req[row * 4 + 1] = req[row * 4 + 2] = req[row * 4 + 3] = -1;
-        y[row] = -1;
-        ref_row[row] = -1;
-        anchor[row] = -1;
-    }
     return 0;
+}
+
+//   counts [B][256][2] i32 : pixels per (image, label, hard|easy) from dcl_sample_classify
+//   info out [6] i32      : A, n_view, n (valid local rows), n_pad, n_global, -
+//   anchor arrays out     : image, cls, num_hard, num_easy, keep_hard [A <= B*256] i64; ranks [A*n_view] i64
+//   row arrays out        : req [n_pad*4] i32 (image, label, easy, rank; -1 padding), y [n_pad] i32,
+//                           ref_row [n_pad] i64 (v*A + a in the reference's order), anchor [n_pad] i64
+// Returns 0, 1 when no class qualifies (the reference's `return None, None`, loss.py:287-288), 2 when the
+// split rule hits the reference's "this shoud be never touched" branch (info[0..2] = num_hard, num_easy, n_view),
+// or a negative dcl_status.
+extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_samples, int max_views,
+                                  void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                                  int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
+                                  int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor) {
+    int32_t inf[6];
+    const int rc = plan_rows(counts, B, 1, 0, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, inf,
+                             image, cls, num_hard, num_easy, keep_hard, ranks, req, y, ref_row, anchor);
+    if (info) for (int i = 0; i < 4; ++i) info[i] = inf[i];
+    return rc;
+}
+
+// Sharded form: counts [world*Bl][256][2] all-gathered, rank-major image order.  y_all [world*n_pad] receives the
+// labels of EVERY rank's row block (so they need not be exchanged); req / ref_row / anchor describe the local block;
+// `ranks` is filled for the local anchors only.  info [6] as above.
+extern "C" int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int rank, int ignore_label,
+                                          int max_samples, int max_views, void* torch_rng_state, size_t state_bytes,
+                                          int32_t* info, int64_t* image, int64_t* cls, int64_t* num_hard,
+                                          int64_t* num_easy, int64_t* keep_hard, int64_t* ranks, int32_t* req,
+                                          int32_t* y_all, int64_t* ref_row, int64_t* anchor) {
+    return plan_rows(counts, Bl, world, rank, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, info,
+                     image, cls, num_hard, num_easy, keep_hard, ranks, req, y_all, ref_row, anchor);
 }
 
 extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int n_view,

@@ -282,7 +282,7 @@ def contrast_forward(tiles, y, sqnorm, nJ, rb0, nI, n_valid, mode, T, Tb, colA=N
         colA = torch.empty((nJ * _TILE, 4), dtype=torch.float32, device=dev)
         colB = torch.empty((nJ * _TILE, 4), dtype=torch.float32, device=dev)
     rowloss = torch.empty(nJ * _TILE, dtype=torch.float32, device=dev)
-    loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+    loss_sum = torch.empty(2, dtype=torch.float32, device=dev)
     nbytes = _lib.workspace_bytes(nI, nJ)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with _Timed("contrast_fwd"):
@@ -305,6 +305,49 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 
 
 # ----------------------------------------------------------------------------------------------
+# lean single-GPU step: one device allocation per direction, cached sizes, raw pointers into it
+# ----------------------------------------------------------------------------------------------
+_WS_BYTES = {}
+_WS_CACHE = {}
+_LAUNCHES_CACHE = {}
+
+
+def _ws_bytes(nI, nJ):
+    v = _WS_BYTES.get((nI, nJ))
+    if v is None:
+        v = _WS_BYTES[(nI, nJ)] = _lib.workspace_bytes(nI, nJ)
+    return v
+
+
+def _workspace(dev, nbytes):
+    """Scratch for one contrast call.  Calls on a device are stream-ordered, so one buffer per device is reused
+    (grown when needed) instead of a fresh allocation per call."""
+    key = (dev.index, torch._C._cuda_getCurrentRawStream(dev.index))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS_CACHE[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return ws
+
+
+def _launches(mode, backward):
+    v = _LAUNCHES_CACHE.get((mode, backward))
+    if v is None:
+        v = _LAUNCHES_CACHE[(mode, backward)] = _lib.contrast_launches(mode, backward)
+    return v
+
+
+def _carve(dev, sizes):
+    """One uint8 tensor holding consecutive 256-byte-aligned regions of the given byte sizes -> (tensor, pointers)."""
+    offs, o = [], 0
+    for sz in sizes:
+        offs.append(o)
+        o += (sz + 255) // 256 * 256
+    buf = torch.empty(o, dtype=torch.uint8, device=dev)
+    base = buf.data_ptr()
+    return buf, [ctypes.c_void_p(base + x) for x in offs]
+
+
+# ----------------------------------------------------------------------------------------------
 # autograd glue
 # ----------------------------------------------------------------------------------------------
 class _PixelContrastFn(torch.autograd.Function):
@@ -314,32 +357,45 @@ class _PixelContrastFn(torch.autograd.Function):
     def forward(ctx, feats, pix, y_dev, n_valid, T, Tb, dzero=None):
         B, C, h, w = feats.shape
         n_pad = pix.shape[0]
-        tiles, sqnorm = gather_tiles(feats, pix, n_pad)
         nJ = n_pad // _TILE
-        colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_dev, sqnorm, nJ, 0, nJ, n_valid,
-                                                         MODE_PIXEL, T, Tb)
-        ctx.save_for_backward(tiles, y_dev, colA, colB, pix)
-        ctx.meta = dict(nJ=nJ, rb0=0, nI=nJ, n_local_pad=n_pad, shape=(B, C, h, w))
+        dev = feats.device
+        st = _stream()
+        # state kept for the backward: tiles | sqnorm | colA | colB | rowloss, one allocation
+        keep, (p_tiles, p_sq, p_cA, p_cB, p_rl) = _carve(dev, (n_pad * _DIM * 2, n_pad * 4, n_pad * 16, n_pad * 16,
+                                                               n_pad * 4))
+        loss2 = torch.empty(2, dtype=torch.float32, device=dev)
+        nbytes = _ws_bytes(nJ, nJ)
+        ws = _workspace(dev, nbytes)
+        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, p_tiles, p_sq, st)
+        with _Timed("contrast_fwd"):
+            _lib.call("dcl_contrast_fwd", p_tiles, _p(y_dev), p_sq, nJ, 0, nJ, n_valid, MODE_PIXEL, float(T), float(Tb),
+                      _p(ws), nbytes, p_cA, p_cB, p_rl, _p(loss2), st)
+        _count(1 + _launches(MODE_PIXEL, 0))
+        ctx.save_for_backward(keep, y_dev, pix)
+        ctx.meta = (nJ, n_pad, (B, C, h, w), (p_tiles, p_cA, p_cB))
         ctx.dzero = dzero          # dense gradient buffer zero-filled while the host planned the sample
-        return (loss_sum / n_valid).reshape(())
+        return loss2[1]
 
     @staticmethod
     def backward(ctx, grad_out):
-        tiles, y, colA, colB, pix = ctx.saved_tensors
-        m = ctx.meta
-        dF = contrast_backward(tiles, y, colA, colB, m["nJ"], m["rb0"], m["nI"], MODE_PIXEL)
-        B, C, h, w = m["shape"]
-        g = grad_out.to(torch.float32).contiguous()
+        keep, y, pix = ctx.saved_tensors
+        nJ, n_pad, (B, C, h, w), (p_tiles, p_cA, p_cB) = ctx.meta
+        dev = keep.device
+        st = _stream()
+        dF = torch.empty((n_pad, _DIM), dtype=torch.float32, device=dev)
+        nbytes = _ws_bytes(nJ, nJ)
+        ws = _workspace(dev, nbytes)
+        with _Timed("contrast_bwd"):
+            _lib.call("dcl_contrast_bwd", p_tiles, _p(y), p_cA, p_cB, nJ, 0, nJ, MODE_PIXEL, _p(ws), nbytes, _p(dF), st)
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
+            grad_out.to(torch.float32).contiguous()
         dfeats, ctx.dzero = ctx.dzero, None
+        zero_fill = 0
         if dfeats is None:
-            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
-            _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
-                      _stream())
-            _count(2)
-        else:
-            _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 0,
-                      _stream())
-            _count(1)
+            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
+            zero_fill = 1
+        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfeats), B, h * w, zero_fill, st)
+        _count(_launches(MODE_PIXEL, 1) + 1 + zero_fill)
         return dfeats, None, None, None, None, None, None
 
 
@@ -358,7 +414,7 @@ class _ContrastRowsFn(torch.autograd.Function):
         colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_pad, sqnorm, nJ, 0, nJ, n, mode, T, Tb)
         ctx.save_for_backward(tiles, y_pad, colA, colB)
         ctx.meta = (n, nJ, mode)
-        return (loss_sum / n).reshape(())
+        return (loss_sum[0] / n).reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -649,9 +705,52 @@ def shard_plan(counts_all: np.ndarray, rank: int, world: int, images_per_rank: i
     return ShardPlan(plan, lay, n_pad, int(rows.sum()), rows)
 
 
+def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank: int, ignore_label: int,
+                 max_samples: int, max_views: int, stage_req: Optional[np.ndarray] = None,
+                 stage_y: Optional[np.ndarray] = None):
+    """C form of shard_plan (dcl_host_plan_rows_sharded): same plan, same local layout, plus the labels of every
+    rank's row block (so they need no exchange); non-local permutations only advance the generator.
+    Returns None (no class qualifies) or (ShardPlan, y_all [world*n_pad] i32).  `stage_req` / `stage_y` may be
+    caller-owned (pinned) output arrays of sufficient size."""
+    B = world * images_per_rank
+    cap = max(_TILE, (int(max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
+    counts = np.ascontiguousarray(counts_all, dtype=np.int32).reshape(-1)
+    info = np.zeros(6, dtype=np.int32)
+    an = np.empty((5, B * 256), dtype=np.int64)
+    ranks = np.empty(max(int(max_samples), 1), dtype=np.int64)
+    req = stage_req if stage_req is not None else np.empty(cap * 4, dtype=np.int32)
+    y_all = stage_y if stage_y is not None else np.empty(world * cap, dtype=np.int32)
+    rows = np.empty((2, cap), dtype=np.int64)
+    st = torch.get_rng_state()
+    sbuf = st.numpy()
+    lib = _lib.load()
+    rc = lib.dcl_host_plan_rows_sharded(counts.ctypes.data, images_per_rank, world, rank, int(ignore_label),
+                                        int(max_samples), int(max_views), sbuf.ctypes.data, sbuf.nbytes,
+                                        info.ctypes.data, an[0].ctypes.data, an[1].ctypes.data, an[2].ctypes.data,
+                                        an[3].ctypes.data, an[4].ctypes.data, ranks.ctypes.data, req.ctypes.data,
+                                        y_all.ctypes.data, rows[0].ctypes.data, rows[1].ctypes.data)
+    if rc == 1:
+        return None
+    if rc == 2:
+        print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
+        raise Exception
+    if rc != 0:
+        raise _lib.DclError("dcl_host_plan_rows_sharded failed with status %d: %s"
+                            % (rc, lib.dcl_last_error().decode("utf-8", "replace")))
+    torch.set_rng_state(st)
+    A, n_view, n, n_pad, n_global = (int(v) for v in info[:5])
+    plan = AnchorPlan(A, n_view, an[0, :A], an[1, :A], an[2, :A], an[3, :A], an[4, :A],
+                      ranks[: A * n_view].reshape(A, n_view))
+    lay = RowLayout(n, n_pad, req[: n_pad * 4].reshape(n_pad, 4), y_all[rank * n_pad:(rank + 1) * n_pad],
+                    rows[0, :n_pad], rows[1, :n_pad])
+    owner = plan.image // images_per_rank
+    rpr = np.bincount(owner, minlength=world).astype(np.int64) * n_view
+    return ShardPlan(plan, lay, n_pad, n_global, rpr), y_all[: world * n_pad]
+
+
 class _ShardedPixelContrastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, pix, y_local, n_global, T, Tb, group):
+    def forward(ctx, feats, pix, y_all, n_global, T, Tb, group):
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         B, C, h, w = feats.shape
@@ -659,23 +758,24 @@ class _ShardedPixelContrastFn(torch.autograd.Function):
         dev = feats.device
         tiles_l, sqnorm_l = gather_tiles(feats, pix, n_pad)
         tiles = torch.empty(world * n_pad * _DIM * 2, dtype=torch.uint8, device=dev)
-        y_all = torch.empty(world * n_pad, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(tiles, tiles_l, group=group)        # the one real exchange step
-        dist.all_gather_into_tensor(y_all, y_local.contiguous(), group=group)
-        sqnorm = torch.zeros(world * n_pad, dtype=torch.float32, device=dev)
-        sqnorm[rank * n_pad:(rank + 1) * n_pad] = sqnorm_l
+        sqnorm = torch.empty(world * n_pad, dtype=torch.float32, device=dev)
+        # the one real exchange step: the contrast set (and its 4 B/row norms), one coalesced NCCL launch
+        with dist._coalescing_manager(group=group, device=dev, async_ops=False):
+            dist.all_gather_into_tensor(tiles, tiles_l, group=group)
+            dist.all_gather_into_tensor(sqnorm, sqnorm_l, group=group)
         nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
         colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_all, sqnorm, nJ, rb0, nI, n_global,
                                                          MODE_PIXEL, T, Tb)
-        # backward needs every row's constants (the dS_ki terms): 32 B per row
+        # backward needs every row's constants (the dS_ki terms): 32 B per row; the loss is the sum over ranks
         la = colA[rank * n_pad:(rank + 1) * n_pad].clone()
         lb = colB[rank * n_pad:(rank + 1) * n_pad].clone()
-        dist.all_gather_into_tensor(colA, la, group=group)
-        dist.all_gather_into_tensor(colB, lb, group=group)
-        dist.all_reduce(loss_sum, group=group)
+        with dist._coalescing_manager(group=group, device=dev, async_ops=False):
+            dist.all_gather_into_tensor(colA, la, group=group)
+            dist.all_gather_into_tensor(colB, lb, group=group)
+            dist.all_reduce(loss_sum, group=group)        # [0] = sum over the local rows
         ctx.save_for_backward(tiles, y_all, colA, colB, pix)
         ctx.meta = dict(nJ=nJ, rb0=rb0, nI=nI, n_local_pad=n_pad, shape=(B, C, h, w))
-        return (loss_sum / n_global).reshape(())
+        return (loss_sum[0] / n_global).reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -724,8 +824,21 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         counts_all = torch.empty((world * B, _BINS), dtype=torch.int32, device=feats.device)
         dist.all_gather_into_tensor(counts_all, counts, group=group)
         counts_host = counts_all.cpu().numpy().reshape(world * B, 256, 2)
-        sp = shard_plan(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
-                        int(self.max_views))
+        if _verify_host_rng():
+            cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
+            key = (world, cap)
+            stg = getattr(self, "_shard_stage", None)
+            if stg is None or stg[0] != key:
+                t = torch.empty(cap * 4 + world * cap, dtype=torch.int32).pin_memory()
+                stg = self._shard_stage = (key, t, t.numpy())
+            _, stage_t, stage_np = stg
+            out = shard_plan_c(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
+                               int(self.max_views), stage_np[: cap * 4], stage_np[cap * 4:])
+            sp = None if out is None else out[0]
+        else:
+            sp = shard_plan(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
+                            int(self.max_views))
+            stage_t = None
         self.last_plan = None if sp is None else sp.plan
         if sp is None:
             return feats_c.sum() * 0.0
@@ -733,10 +846,17 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
             raise RuntimeError("max_samples // total_classes == 0: no views to sample")
         lay = sp.layout
         self.last_layout, self.last_n_global = lay, sp.n_global
-        host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
-        packed = host.to(feats.device, non_blocking=True)
-        req_dev, y_dev = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
+        if stage_t is not None:
+            packed = stage_t.to(feats.device, non_blocking=True)
+            req_dev = packed[: lay.n_pad * 4]
+            y_all = packed[cap * 4: cap * 4 + world * lay.n_pad]
+        else:
+            host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
+            packed = host.to(feats.device, non_blocking=True)
+            req_dev, y_dev = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
+            y_all = torch.empty(world * lay.n_pad, dtype=torch.int32, device=feats.device)
+            dist.all_gather_into_tensor(y_all, y_dev.contiguous(), group=group)
         pix = select_pixels(code, chunk, B, h * w, req_dev, lay.n_pad)
         self.last_pix = pix
-        return _ShardedPixelContrastFn.apply(feats_c, pix, y_dev, sp.n_global, self.temperature,
+        return _ShardedPixelContrastFn.apply(feats_c, pix, y_all, sp.n_global, self.temperature,
                                              self.base_temperature, group)

@@ -120,6 +120,18 @@ int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_s
                        int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
                        int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor);
 
+/* Sharded form of dcl_host_plan_rows for one process per GPU (the reference has no multi-GPU path, SURVEY
+ * D7): `counts` is the all-gathered table [world*Bl][256][2] in rank-major image order; every rank
+ * replays the same generator stream but only draws the permutations of its own anchors.
+ * info [6]: A, n_view, n (valid LOCAL rows), n_pad (common block size), n_global, -.  y_all
+ * [world*n_pad] receives the labels of every rank's row block; req / ref_row / anchor [n_pad] describe
+ * the local block (image index relative to the rank's first image). */
+int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int rank, int ignore_label,
+                               int max_samples, int max_views, void* torch_rng_state, size_t state_bytes,
+                               int32_t* info, int64_t* image, int64_t* cls, int64_t* num_hard,
+                               int64_t* num_easy, int64_t* keep_hard, int64_t* ranks, int32_t* req,
+                               int32_t* y_all, int64_t* ref_row, int64_t* anchor);
+
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.
@@ -130,7 +142,8 @@ int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_s
  *            constants consumed by dcl_contrast_bwd - (a, b, p, q) and (wn, Den, label bits, logit range L);
  *            all-gather them before a sharded backward
  *   rowloss [nJ*128] f32 out (local rows): per-row loss term, 0 for padding
- *   loss_sum [1] f32 out: sum of rowloss over the local rows (caller divides by n_valid)
+ *   loss_sum [2] f32 out: [0] sum of rowloss over the local rows, [1] that sum / n_valid (the loss when
+ *            the rows are not sharded)
  *   workspace: dcl_contrast_workspace_bytes(nI, nJ) bytes
  */
 size_t dcl_contrast_workspace_bytes(int nI, int nJ);

@@ -94,3 +94,35 @@ def test_shard_plan_union_equals_single_process_reference(B, h, w, K, mv, ms):
         assert np.all(np.diff(r["y"][: r["n"]]) >= 0)          # class-sorted inside the rank block
         assert np.all(r["y"][r["n"]:] == -1)
     assert np.array_equal(got, plan.pixels)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("B,h,w,K,mv,ms", [(4, 16, 32, 5, 6, 1024), (8, 12, 20, 3, 5, 40), (4, 64, 64, 7, 48, 2048)])
+def test_c_shard_plan_equals_numpy_shard_plan(world, B, h, w, K, mv, ms):
+    """dcl_host_plan_rows_sharded (the product's host path) == shard_plan (numpy) for every rank: same plan, same
+    local layout, same final generator state; y_all holds every rank's labels; non-local draws are skipped."""
+    from doubly_contrastive_semseg_b200.loss import shard_plan, shard_plan_c
+    lab, pred = _inputs(B, h, w, K, seed=9)
+    counts_all = _counts(lab, pred).reshape(B, 256, 2)
+    bl = B // world
+    ys = []
+    for rank in range(world):
+        torch.manual_seed(123)
+        ref = shard_plan(counts_all, rank, world, bl, 255, ms, mv)
+        end_ref = torch.get_rng_state().clone()
+        torch.manual_seed(123)
+        got, y_all = shard_plan_c(counts_all, rank, world, bl, 255, ms, mv)
+        assert torch.equal(torch.get_rng_state(), end_ref)
+        assert (got.plan.A, got.plan.n_view, got.n_pad, got.n_global) == (ref.plan.A, ref.plan.n_view, ref.n_pad, ref.n_global)
+        assert np.array_equal(got.rows_per_rank, ref.rows_per_rank)
+        for name in ("image", "cls", "num_hard", "num_easy", "keep_hard"):
+            assert np.array_equal(getattr(got.plan, name), getattr(ref.plan, name)), name
+        mine = (ref.plan.image // bl) == rank
+        assert np.array_equal(got.plan.ranks[mine], ref.plan.ranks[mine])
+        for name in ("req", "y", "ref_row", "anchor"):
+            assert np.array_equal(getattr(got.layout, name), getattr(ref.layout, name)), name
+        assert got.layout.n == ref.layout.n
+        assert np.array_equal(y_all[rank * ref.n_pad:(rank + 1) * ref.n_pad], ref.layout.y)
+        ys.append(y_all.copy())
+    for y in ys[1:]:
+        assert np.array_equal(y, ys[0])

@@ -62,7 +62,7 @@ def check_rows(n, K, mode, seed=0, T=0.07, offset=0.0, sort=True):
     p_o = -kappa_o * st["R"] * np.log(2.0)
     q_o = -kappa_o * st["Q"]
     e_p, e_q = rel(cA[:, 2], p_o), rel(cA[:, 3], q_o)
-    loss_d = float(loss_sum.item()) / n
+    loss_d = float(loss_sum[0].item()) / n
     # stage 3: backward
     dF = L.contrast_backward(tiles, ypad, colA, colB, nJ, 0, nJ, mode)
     torch.cuda.synchronize()

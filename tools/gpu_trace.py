@@ -22,6 +22,7 @@ torch.cuda.synchronize()
 lib.dcl_debug_trace(None)
 t = buf.cpu().view(5, 32, 8)
 t0 = int(t[t > 0].min())
+print("kernel entry", int(t[0, 0, 7]) - t0, "set-up done", int(t[0, 2, 7]) - t0, "all roles done", int(t[0, 1, 7]) - t0)
 print("tile | prod: wait_e got_e | issS: wait_full got_full got_sfree issued | issD: wait_pfull got_pfull issued | g0: start got_tfull done | g1: start got_tfull done")
 for it in range(28):
     r = lambda role, ev: (int(t[role, it, ev]) - t0) if int(t[role, it, ev]) else -1

@@ -8,7 +8,8 @@ from doubly_contrastive_semseg_b200 import loss as L, _lib
 lib = _lib.load()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 g = torch.Generator(device="cuda").manual_seed(n)
-y = torch.arange(n, device="cuda").int()
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+y = torch.arange(n, device="cuda").int() if K == 0 else torch.randint(0, K, (n,), generator=g, device="cuda").sort().values.int()
 Z = torch.randn(n, 128, generator=g, device="cuda")
 tiles, sq = L.pack_rows(Z, n)
 nJ = n // 128

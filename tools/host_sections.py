@@ -33,12 +33,19 @@ for it in range(25):
                                 an[4].ctypes.data, hb["ranks"].ctypes.data, stage.ctypes.data, stage[cap * 4:].ctypes.data,
                                 rows[0].ctypes.data, rows[1].ctypes.data); t4 = pc()
     torch.set_rng_state(st)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     A, n_view, n, n_pad = (int(v) for v in info)
     packed = hb["stage"].to(feats.device, non_blocking=True)
     pix = L.select_pixels(code, chunk, B, h * w, packed[: n_pad * 4], n_pad); t5 = pc()
     loss = L._PixelContrastFn.apply(feats, pix, packed[cap * 4: cap * 4 + n_pad], n, 0.07, 0.07, dz); t6 = pc()
+    e1.record()
     loss.backward(); t7 = pc()
+    e2.record()
     torch.cuda.synchronize(); t8 = pc()
+    if it >= 5:
+        add("gpu: plan-end -> fwd done", e0.elapsed_time(e1) * 1e-3)
+        add("gpu: fwd done -> bwd done", e1.elapsed_time(e2) * 1e-3)
     if it >= 5:
         for k, v in (("classify launch", t1 - t0), ("copy+zero launch", t2 - t1), ("sync wait", t3 - t2), ("C plan", t4 - t3),
                      ("h2d+select launch", t5 - t4), ("fn.forward launch", t6 - t5), ("backward launch", t7 - t6), ("drain", t8 - t7)):

@@ -20,4 +20,4 @@ for _ in range(reps):
     colA, colB, rl, ls = L.contrast_forward(tiles, y, sq, nJ, 0, nJ, n, 0, 0.07, 0.07)
     dF = L.contrast_backward(tiles, y, colA, colB, nJ, 0, nJ, 0)
 torch.cuda.synchronize()
-print("loss", float(ls.item()) / n, "dF", float(dF.abs().max()))
+print("loss", float(ls[0].item()) / n, "dF", float(dF.abs().max()))
