@@ -7,6 +7,7 @@ image-level term only) the two tiny projection GEMMs.  No CPU path exists here.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
@@ -759,23 +760,23 @@ class _ShardedPixelContrastFn(torch.autograd.Function):
         tiles_l, sqnorm_l = gather_tiles(feats, pix, n_pad)
         tiles = torch.empty(world * n_pad * _DIM * 2, dtype=torch.uint8, device=dev)
         sqnorm = torch.empty(world * n_pad, dtype=torch.float32, device=dev)
-        # the one real exchange step: the contrast set (and its 4 B/row norms), one coalesced NCCL launch
-        with dist._coalescing_manager(group=group, device=dev, async_ops=False):
-            dist.all_gather_into_tensor(tiles, tiles_l, group=group)
-            dist.all_gather_into_tensor(sqnorm, sqnorm_l, group=group)
+        # the one real exchange step: the contrast set (and its 4 B/row norms).  Plain back-to-back launches:
+        # torch's coalescing manager made the step time erratic (3-7 ms with 70 ms spikes on 2 B200s)
+        dist.all_gather_into_tensor(tiles, tiles_l, group=group)
+        dist.all_gather_into_tensor(sqnorm, sqnorm_l, group=group)
         nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
         colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_all, sqnorm, nJ, rb0, nI, n_global,
                                                          MODE_PIXEL, T, Tb)
         # backward needs every row's constants (the dS_ki terms): 32 B per row; the loss is the sum over ranks
         la = colA[rank * n_pad:(rank + 1) * n_pad].clone()
         lb = colB[rank * n_pad:(rank + 1) * n_pad].clone()
-        with dist._coalescing_manager(group=group, device=dev, async_ops=False):
-            dist.all_gather_into_tensor(colA, la, group=group)
-            dist.all_gather_into_tensor(colB, lb, group=group)
-            dist.all_reduce(loss_sum, group=group)        # [0] = sum over the local rows
+        parts = torch.empty(world, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(colA, la, group=group)
+        dist.all_gather_into_tensor(colB, lb, group=group)
+        dist.all_gather_into_tensor(parts, loss_sum[:1], group=group)     # per-rank sums over their rows
         ctx.save_for_backward(tiles, y_all, colA, colB, pix)
         ctx.meta = dict(nJ=nJ, rb0=rb0, nI=nI, n_local_pad=n_pad, shape=(B, C, h, w))
-        return (loss_sum[0] / n_global).reshape(())
+        return (parts.sum() / n_global).reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
