@@ -220,8 +220,12 @@ def run_ours(args):
 
     feats.requires_grad_(True)
 
+    # Identical CPU generator state on every rank, set ONCE: every rank consumes the same stream (each replays the
+    # global plan), so the states stay identical, and an untouched generator lets the library's look-ahead thread
+    # regenerate mt19937 state blocks off the step's critical path.
+    torch.manual_seed(1234)
+
     def step(seed, f=feats, lab=labels, pred=predict):
-        torch.manual_seed(seed)              # identical CPU RNG state on every rank
         f.grad = None
         loss = crit(f, labels=lab, predict=pred)
         loss.backward()

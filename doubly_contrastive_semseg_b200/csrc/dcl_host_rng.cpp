@@ -11,20 +11,21 @@
 // u64 state[624] | normal-distribution cache.
 // randperm(n) for n < 2^32/20: r = arange(n); for i < n-1: z = u32() % (n-i); swap(r[i], r[i+z]).
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
+#include <unistd.h>
 #include "dcl_common.cuh"
 
 namespace {
 
 constexpr int kN = 624, kM = 397;
-
-struct Mt {
-    uint32_t s[kN];
-    int left;
-    uint32_t next;
-};
 
 inline __attribute__((always_inline)) uint32_t mix(uint32_t u, uint32_t v) {
     uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -38,7 +39,6 @@ inline __attribute__((always_inline)) uint32_t mix(uint32_t u, uint32_t v) {
 inline __attribute__((always_inline)) void twist_body(uint32_t* __restrict__ s) {
 #pragma GCC ivdep
     for (int i = 0; i < kN - kM; ++i) s[i] = s[i + kM] ^ mix(s[i], s[i + 1]);
-    // split the second range so that the vectorised part never reads an element written inside the same vector
 #pragma GCC ivdep
     for (int i = kN - kM; i < kN - 1; ++i) s[i] = s[i + kM - kN] ^ mix(s[i], s[i + 1]);
     s[kN - 1] = s[kM - 1] ^ mix(s[kN - 1], s[0]);
@@ -46,12 +46,116 @@ inline __attribute__((always_inline)) void twist_body(uint32_t* __restrict__ s) 
 __attribute__((target("avx512f"))) void twist_avx512(uint32_t* s) { twist_body(s); }
 __attribute__((target("avx2"))) void twist_avx2(uint32_t* s) { twist_body(s); }
 void twist_generic(uint32_t* s) { twist_body(s); }
+inline void twist_words(uint32_t* s) {
+    static const int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+    if (isa == 2) twist_avx512(s);
+    else if (isa == 1) twist_avx2(s);
+    else twist_generic(s);
+}
+
+// Look-ahead of the generator's state sequence.  The sequence of regenerated state blocks depends only on the
+// generator state, not on the data, so a worker thread produces it ahead of time into a ring; the sampler then
+// consumes blocks instead of regenerating them on the step's critical path (0.2 ms per step at cfg2).  The stream is
+// valid while torch's generator is where the previous plan left it (`expected`); any other use of the generator
+// (manual_seed, torch.rand, ...) is detected by comparing the serialized state and the stream restarts from it.
+class Lookahead {
+public:
+    static constexpr uint64_t kRing = 4096;                    // blocks (10 MB): ~2.5 M draws ahead
+    const uint32_t* block(uint64_t idx) {                      // blocks [floor, produced) are readable
+        while (produced_.load(std::memory_order_acquire) <= idx) std::this_thread::yield();
+        return ring_.data() + (idx % kRing) * kN;
+    }
+    // does the serialized torch state equal where the last plan left the generator?  (same process only)
+    bool active() const { return active_ && pid_ == getpid(); }
+    bool matches(const uint8_t* raw) const {
+        return have_expected_ && epid_ == getpid() && std::memcmp(raw + 8, expected_ + 8, 16 + 8 * kN) == 0;
+    }
+    void expect(const uint8_t* raw) {                          // record where a plan left the generator
+        std::memcpy(expected_, raw, sizeof(expected_));
+        have_expected_ = true;
+        epid_ = getpid();
+    }
+    uint64_t position() const { return pos_block_; }
+    // restart from the state words `s` as block 0
+    void restart(const uint32_t* s) {
+        stop();
+        if (ring_.empty()) ring_.resize(kRing * kN);
+        std::memcpy(ring_.data(), s, sizeof(uint32_t) * kN);
+        std::memcpy(last_, s, sizeof(uint32_t) * kN);
+        produced_.store(1, std::memory_order_release);
+        floor_.store(0, std::memory_order_release);
+        quit_ = false;
+        pid_ = getpid();
+        pos_block_ = 0;
+        worker_ = std::thread([this] { run(); });
+        active_ = true;
+    }
+    // the plan ended in block `idx`; remember the serialized state torch now holds
+    void commit(uint64_t idx, const uint8_t* raw) {
+        pos_block_ = idx;
+        expect(raw);
+        floor_.store(idx, std::memory_order_release);
+        cv_.notify_one();
+    }
+    void stop() {
+        if (worker_.joinable() && pid_ == getpid()) {
+            { std::lock_guard<std::mutex> g(mu_); quit_ = true; }
+            cv_.notify_one();
+            worker_.join();
+        } else if (worker_.joinable()) {
+            worker_.detach();                                  // forked child: the thread does not exist here
+        }
+        active_ = false;
+    }
+    ~Lookahead() { stop(); }
+
+private:
+    void run() {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait_for(lk, std::chrono::milliseconds(50), [this] {
+                    return quit_ || produced_.load(std::memory_order_relaxed) - floor_.load(std::memory_order_acquire) < kRing - 1;
+                });
+                if (quit_) return;
+            }
+            while (produced_.load(std::memory_order_relaxed) - floor_.load(std::memory_order_acquire) < kRing - 1) {
+                twist_words(last_);
+                const uint64_t idx = produced_.load(std::memory_order_relaxed);
+                std::memcpy(ring_.data() + (idx % kRing) * kN, last_, sizeof(uint32_t) * kN);
+                produced_.store(idx + 1, std::memory_order_release);
+                if (quit_) return;
+            }
+        }
+    }
+    std::vector<uint32_t> ring_;
+    uint32_t last_[kN];
+    std::atomic<uint64_t> produced_{0}, floor_{0};
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread worker_;
+    bool quit_ = false, active_ = false, have_expected_ = false;
+    pid_t pid_ = 0, epid_ = 0;
+    uint64_t pos_block_ = 0;
+    uint8_t expected_[24 + 8 * kN] = {0};
+};
+
+struct Mt {
+    const uint32_t* s;       // current state block: `own` or a block of the look-ahead ring
+    uint32_t own[kN];
+    int left;
+    uint32_t next;
+    Lookahead* la = nullptr;
+    uint64_t blk = 0;
+};
 
 void twist(Mt& m) {
-    static const int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
-    if (isa == 2) twist_avx512(m.s);
-    else if (isa == 1) twist_avx2(m.s);
-    else twist_generic(m.s);
+    if (m.la) {
+        m.s = m.la->block(++m.blk);
+    } else {
+        twist_words(m.own);
+        m.s = m.own;
+    }
     m.left = kN;
     m.next = 0;
 }
@@ -155,7 +259,8 @@ int load_state(void* torch_rng_state, size_t state_bytes, Mt& m) {
     std::memcpy(&left, raw + 8, 4);
     std::memcpy(&next, raw + 16, 8);
     const uint64_t* st = reinterpret_cast<const uint64_t*>(raw + 24);
-    for (int i = 0; i < kN; ++i) m.s[i] = static_cast<uint32_t>(st[i]);
+    for (int i = 0; i < kN; ++i) m.own[i] = static_cast<uint32_t>(st[i]);
+    m.s = m.own;
     m.left = left;
     m.next = static_cast<uint32_t>(next);
     if (m.left < 0 || m.left > kN || m.next > static_cast<uint32_t>(kN))
@@ -178,6 +283,12 @@ void store_state(void* torch_rng_state, const Mt& m) {
 // split rule, the randperm draws and the class-sorted device row layout.  Shared by the single-process entry point
 // and the sharded one: `world` ranks own `Bl` consecutive images each; every rank replays the SAME generator stream
 // over the global batch, but only draws the permutations of its own anchors (the others just advance the state).
+static long long g_la_stats[4] = {0, 0, 0, 0};   // plans served by the look-ahead stream, inline plans, stream starts, drops
+// Diagnostics: counters of the generator look-ahead (see Lookahead): out[4] = stream plans, inline plans, starts, drops.
+extern "C" int dcl_host_lookahead_stats(long long* out) {
+    for (int i = 0; i < 4; ++i) out[i] = g_la_stats[i];
+    return 0;
+}
 static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignore_label, int max_samples,
                      int max_views, void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
                      int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard, int64_t* ranks,
@@ -213,6 +324,27 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
     if (n_view > 0) {
         Mt m;
         if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
+        // Look-ahead policy: the stream is used while the generator is exactly where the previous plan left it.
+        // A mismatch (manual_seed, other draws) drops to the inline replay; the stream is (re)started after a plan
+        // that found the generator untouched, so loops that reseed every step never pay for a useless worker.
+        static Lookahead la;
+        static std::mutex la_mu;
+        static const bool la_enabled = [] { const char* e = std::getenv("DCL_HOST_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+        std::lock_guard<std::mutex> la_lock(la_mu);
+        const uint8_t* raw = static_cast<const uint8_t*>(torch_rng_state);
+        const bool continuous = la_enabled && la.matches(raw);
+        if (la.active()) {
+            if (continuous) {
+                m.la = &la;
+                m.blk = la.position();
+                m.s = la.block(m.blk);
+                ++g_la_stats[0];
+            } else {
+                la.stop();
+                ++g_la_stats[3];
+            }
+        }
+        if (!m.la) ++g_la_stats[1];
         Sparse sp;
         for (int a = 0; a < A; ++a) {
             const int64_t kh = keep_hard[a], ke = n_view - kh;
@@ -230,6 +362,19 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             }
         }
         store_state(torch_rng_state, m);
+        if (m.la) {
+            la.commit(m.blk, raw);
+        } else {
+            if (continuous) {
+                uint32_t words[kN];
+                for (int i = 0; i < kN; ++i) words[i] = m.s[i];
+                la.restart(words);                 // generator untouched since the last plan: stream from here on
+                ++g_la_stats[2];
+                la.commit(0, raw);
+            } else {
+                la.expect(raw);
+            }
+        }
     }
     // rows per rank -> common padded block size
     std::vector<int> per_rank(world, 0);

@@ -132,6 +132,12 @@ int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int ran
                                int64_t* num_easy, int64_t* keep_hard, int64_t* ranks, int32_t* req,
                                int32_t* y_all, int64_t* ref_row, int64_t* anchor);
 
+/* Diagnostics: counters of the host generator look-ahead used by the two plan calls above (a worker
+ * thread regenerates mt19937 state blocks ahead of the step while torch's generator stays where the
+ * previous plan left it): out[4] = plans served by the stream, inline plans, stream starts, drops.
+ * DCL_HOST_LOOKAHEAD=0 in the environment disables the stream. */
+int dcl_host_lookahead_stats(long long* out);
+
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.

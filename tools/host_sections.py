@@ -16,6 +16,7 @@ lib = _lib.load()
 pc = time.perf_counter
 acc = {}
 def add(k, t): acc[k] = acc.get(k, 0.0) + t
+import ctypes
 for it in range(25):
     feats.grad = None
     torch.cuda.synchronize()
@@ -52,3 +53,4 @@ for it in range(25):
             add(k, v)
 for k, v in acc.items(): print(f"{k:22s} {v / 20 * 1e6:8.1f} us")
 print("total", sum(acc.values()) / 20 * 1e6)
+stats = (ctypes.c_longlong * 4)(); lib.dcl_host_lookahead_stats(stats); print("lookahead stats (stream, inline, starts, drops):", list(stats))
