@@ -72,6 +72,7 @@ struct Params {
     const int32_t* y;        // [nJ*128]
     const float* sqnorm;     // [nJ*128]
     int nJ, rb0, nI, nP, n_valid, mode, ctas;
+    int jstride;             // column-block visiting stride (coprime with nJ)
     int use_series;          // v3 forward: positive-pair sums come from the series unless iscal[4] says otherwise
     float T, Tb;
     Part partS;              // sweeps: units = pairs of row blocks
@@ -361,6 +362,7 @@ template <bool kRelevantOnly>
 struct TileIter {
     int left;                 // flat mode: tiles remaining
     int nJ, U, J, r, s, splitc;
+    int jp, jstride;          // flat mode: permuted column block (J * jstride) % nJ, kept incrementally
     int2 r0, r1;
     const int4* info;
     __device__ TileIter(const Params& p, const Part& part, const int4* sInfo) {
@@ -386,6 +388,11 @@ struct TileIter {
             U = static_cast<int>(t0 / nJ);            // the only divisions: once per CTA and role
             J = static_cast<int>(t0 - static_cast<long long>(U) * nJ);
         }
+        // Column blocks are visited in a stride-permuted order: the tiles that hold same-class pairs are
+        // consecutive in J (rows are class-sorted) and cost 2-3x a plain tile; the permutation spreads them over
+        // the CTAs that share a row unit instead of piling them onto one.
+        jstride = p.jstride;
+        jp = static_cast<int>((static_cast<long long>(J) * jstride) % nJ);
     }
     __device__ bool next(int& oU, int& oJ, bool& last_of_seg) {
         if (kRelevantOnly) {
@@ -406,9 +413,11 @@ struct TileIter {
         } else {
             if (left <= 0) return false;
             oU = U;
-            oJ = J;
+            oJ = jp;
             --left;
-            if (++J == nJ) { J = 0; ++U; }
+            jp += jstride;
+            if (jp >= nJ) jp -= nJ;
+            if (++J == nJ) { J = 0; jp = 0; ++U; }
             last_of_seg = (left == 0) || (J == 0);
             return true;
         }
@@ -609,12 +618,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     if (elect_one()) {
                         if (run && two) {
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, k > 0);
+                            for (int k = 0; k < 2; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, k > 0);
                         }
-                        mbar_arrive(b_turn + 8 * (s ^ 1));
+                        mbar_arrive(b_turn + 8 * (s ^ 1));            // six MMAs (~400 clk, the other issuer's wake-up) early
                         if (run && two) {
 #pragma unroll
-                            for (int k = 6; k < 8; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, true);
+                            for (int k = 2; k < 8; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, true);
                         }
                         tc_commit(b_tfull + 8 * b1);
                         tc_commit(b_empty + 8 * slot);
@@ -632,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         const int r = q * 32 + lane;                       // row inside the block == TMEM lane
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
+        if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + (warp >> 2), 31, 3);                  // iterator built
         int U, J, curU = -1, it = 0;
         bool last, valid = false;
         float acc0[4], acc1[4], acc2[4], acc3[4];
@@ -711,6 +721,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         xw[h * 8 + c] = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes + ((c ^ (r & 7)) << 4)));
                 yi = yload;
                 cshift = cload;
+                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 0);     // loads issued
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
                     uint32_t w[16];
@@ -721,7 +732,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     }
                     tmem_st16(tmem + lane_off + g * 64 + qq * 16, w);
                 }
+                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 1);     // loads arrived, stores issued
                 tmem_st_wait();
+                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 2);     // stores done
             }
             tc_fence_before();
             if (nunits > 0) mbar_wait(b_aseen, (nunits - 1) & 1);   // both issuers are past the previous unit's wait
@@ -768,7 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             } else if (kSweep == SWEEP_P) {
                 const bool fast = all_valid && !ranges_overlap(rI, rJ);
                 if (fast) {
-                    for_each_chunk_loop(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk(v, negc, q3, q4, mx4); });
+                    for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk(v, negc, q3, q4, mx4); });
                     mN0 += 128.f;
                 } else {
                     // masked tile: stage the column labels once per warp, then packed masked sums
@@ -1253,7 +1266,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     const uint32_t bar = base + SmemBwd::kBar;
     constexpr int kSlots = SmemBwd::kSlots, kStages = SmemBwd::kStages;
     const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104, b_sfree = bar + 128,
-                   b_dfull = bar + 152, b_dempty = bar + 160, b_ifull = bar + 168, b_iempty = bar + 176;
+                   b_dfull = bar + 152, b_dempty = bar + 160, b_ifull = bar + 168, b_iempty = bar + 176, b_turn = bar + 184;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemBwd::kTmem);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
@@ -1272,6 +1285,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         mbar_init(b_dempty, 8);
         mbar_init(b_ifull, 1);
         mbar_init(b_iempty, 1);
+        mbar_init(b_turn, 1);
+        mbar_init(b_turn + 8, 1);
         mbar_fence_init();
     }
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
@@ -1321,80 +1336,100 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
             __syncwarp();
             ++it;
         }
-    } else if (warp == kIssuerWarp0) {
+    } else if (warp >= kIssuerWarp0) {
         {
-            // ------------------------------------------------------------------ issuer 0: S = F_I F_J^T
+            // ------------------------------------------------------------------ MMA issuers (whole warp, see elect_one)
+            // Burst k = [dF(k-3) = G(k-3) F_J(k-3), then S(k) = F_I F_J(k)^T], issued by issuer k % 2 while the other
+            // one waits on the barriers of burst k+1.  S(k) reuses the TMEM stage of tile k-3: the tensor pipe
+            // executes in issue order, so G(k-3) has been consumed when S(k) overwrites it - no completion round
+            // trip (commit -> mbarrier -> wake-up, ~200 clk per tile) sits between them.  S runs three tiles ahead
+            // of dF, which leaves each epilogue two bursts (~2000 clk) for its tile.
+            const int s = warp - kIssuerWarp0;
             TileIter<false> iter(p, p.partD, nullptr);
             const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-            uint64_t dI[8], dJk[8];
+            const uint32_t idesc_d = umma_idesc_bf16(128, 128, 0, 1);   // B = F_J, MN-major
+            uint64_t dI[8], dJk[8], dJm[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 dI[k] = ftile_desc_kmajor(sI, k);
                 dJk[k] = ftile_desc_kmajor(sJ, k);
+                dJm[k] = ftile_desc_mnmajor(sJ, k);
             }
-            int I, J, curI = -1, it = 0, seg = 0;
-            bool last;
-            while (iter.next(I, J, last)) {
-                if (I != curI) {
-                    mbar_wait(b_ifull, seg & 1);
-                    curI = I;
-                    ++seg;
+            // flags of the last four tiles (bit 0 first of its segment, bit 1 last) and their segment index
+            int tflags[4] = {0, 0, 0, 0}, tseg[4] = {0, 0, 0, 0};
+            int I, J, curI = -1, ntiles = -1, units = 0, segidx = 0, turn = 0;
+            bool last = false;
+            for (int k = 0;; ++k) {
+                bool have = false, first = false;
+                if (ntiles < 0) {
+                    have = iter.next(I, J, last);
+                    if (!have) ntiles = k;
                 }
-                const int slot = it % kSlots, st = it % kStages;
-                if (lane == 0) trace_stamp(p, 1, it, 0);
-                mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
-                if (lane == 0) trace_stamp(p, 1, it, 1);
-                mbar_wait(b_sfree + 8 * st, ((it / kStages) & 1) ^ 1);     // G(it-3) consumed
-                if (lane == 0) trace_stamp(p, 1, it, 2);
-                tc_fence_after();
-                const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
-                if (elect_one()) {
-                    if (!(p.debug & 2)) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) umma_ss(tmem + st * 128, dI[k], dJk[k] + soff, idesc_s, k > 0);
+                if (have) {
+                    first = (I != curI);
+                    if (first) {
+                        // both issuers observe every row block landing (either may issue its S tiles)
+                        mbar_wait(b_ifull, units & 1);
+                        curI = I;
+                        ++units;
                     }
-                    tc_commit(b_tfull + 8 * st);
-                    if (last) tc_commit(b_iempty);
+                    tflags[k & 3] = (first ? 1 : 0) | (last ? 2 : 0);
+                    tseg[k & 3] = segidx;
+                    if (last) ++segidx;
+                }
+                const int kd = k - 3;
+                const bool have_d = kd >= 0 && (ntiles < 0 || kd < ntiles);
+                if (ntiles >= 0 && k >= ntiles + 3) break;     // bursts 0 .. ntiles+2 (empty ones still pass the turn on)
+                if ((k & 1) != s) continue;
+                const int slot = k % kSlots, st = k % kStages;
+                if (lane == 0) trace_stamp(p, 1 + s, k, 0);
+                if (have) mbar_wait(b_full + 8 * slot, (k / kSlots) & 1);
+                if (lane == 0) trace_stamp(p, 1 + s, k, 1);
+                int dflags = 0;
+                if (have_d) {
+                    dflags = tflags[kd & 3];
+                    mbar_wait(b_pfull + 8 * (kd % kStages), (kd / kStages) & 1);            // G(k-3) is in TMEM
+                    if ((dflags & 1) && tseg[kd & 3] > 0) mbar_wait(b_dempty, (tseg[kd & 3] - 1) & 1);   // accumulator drained
+                }
+                if (lane == 0) trace_stamp(p, 1 + s, k, 2);
+                mbar_wait(b_turn + 8 * s, (turn & 1) ^ (s == 0 ? 1 : 0));
+                ++turn;
+                if (lane == 0) trace_stamp(p, 1 + s, k, 4);
+                tc_fence_after();
+                if (elect_one()) {
+                    if (have_d) {
+                        const uint64_t poff = static_cast<uint64_t>((kd % kSlots) * (kTileBytes >> 4));
+                        if (!(p.debug & 4)) {
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                umma_ts(tD, tmem + (kd % kStages) * 128 + kk * 8, dJm[kk] + poff, idesc_d,
+                                        !(dflags & 1) || kk > 0);
+                        }
+                        tc_commit(b_empty + 8 * (kd % kSlots));
+                        if (dflags & 2) tc_commit(b_dfull);
+                    }
+                    if (have) {
+                        const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
+                        const bool run = !(p.debug & 2);
+                        if (run) {
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) umma_ss(tmem + st * 128, dI[kk], dJk[kk] + soff, idesc_s, kk > 0);
+                        }
+                        // hand the turn over six MMAs (~400 clk: the other issuer's wake-up) early; its dF MMAs
+                        // touch another stage and the accumulator, so interleaving with the rest of S(k) is safe
+                        mbar_arrive(b_turn + 8 * (s ^ 1));
+                        if (run) {
+#pragma unroll
+                            for (int kk = 2; kk < 8; ++kk) umma_ss(tmem + st * 128, dI[kk], dJk[kk] + soff, idesc_s, true);
+                        }
+                        tc_commit(b_tfull + 8 * st);
+                        if (last) tc_commit(b_iempty);
+                    } else {
+                        mbar_arrive(b_turn + 8 * (s ^ 1));
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) trace_stamp(p, 1, it, 3);
-                ++it;
-            }
-        }
-    } else if (warp == kIssuerWarp0 + 1) {
-        {
-            // ------------------------------------------------------------------ issuer 1: dF_I += G F_J
-            TileIter<false> iter(p, p.partD, nullptr);
-            const uint32_t idesc_d = umma_idesc_bf16(128, 128, 0, 1);   // B = F_J, MN-major
-            uint64_t dJm[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dJm[k] = ftile_desc_mnmajor(sJ, k);
-            int I, J, curI = -1, it = 0, seg = 0;
-            bool last;
-            while (iter.next(I, J, last)) {
-                const bool first = (I != curI);
-                curI = I;
-                const int slot = it % kSlots, st = it % kStages;
-                if (lane == 0) trace_stamp(p, 2, it, 0);
-                mbar_wait(b_pfull + 8 * st, (it / kStages) & 1);
-                if (lane == 0) trace_stamp(p, 2, it, 1);
-                if (first && seg > 0) mbar_wait(b_dempty, (seg - 1) & 1);
-                tc_fence_after();
-                const uint64_t poff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
-                if (elect_one()) {
-                    if (!(p.debug & 4)) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_ts(tD, tmem + st * 128 + k * 8, dJm[k] + poff, idesc_d, (!first) || k > 0);
-                    }
-                    tc_commit(b_empty + 8 * slot);
-                    tc_commit(b_sfree + 8 * st);
-                    if (last) tc_commit(b_dfull);
-                }
-                __syncwarp();
-                if (last) ++seg;
-                if (lane == 0) trace_stamp(p, 2, it, 2);
-                ++it;
+                if (lane == 0) trace_stamp(p, 1 + s, k, 3);
             }
         }
     } else {
@@ -1411,6 +1446,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         int2 rI = make_int2(INT_MAX, -1);
         float denI = 0.f;
         while (iter.next(I, J, last)) {
+            if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 3);      // loop top (every tile, own or not)
             if (I != curI) {
                 curI = I;
                 gi = (p.rb0 + I) * 128 + r;
@@ -1455,8 +1491,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
                     };
-                    if (deg == 1) body(std::integral_constant<int, 1>{});
-                    else if (deg == 2) body(std::integral_constant<int, 2>{});
+                    // the two common degrees walk the row with the next chunk's TMEM load in flight
+                    auto body_pf = [&](auto degc) {
+                        for_each_chunk<4>(tS, [&](int c0, const uint32_t (&v)[32]) {
+                            uint32_t pk[16];
+                            bwd_chunk<decltype(degc)::value>(v, rn, cp + (c0 >> 1) * 3, pk);
+                            tmem_st16(tS + (c0 >> 1), pk);
+                        });
+                    };
+                    if (deg == 1) body_pf(std::integral_constant<int, 1>{});
+                    else if (deg == 2) body_pf(std::integral_constant<int, 2>{});
                     else if (deg == 3) body(std::integral_constant<int, 3>{});
                     else body(std::integral_constant<int, 4>{});
                 } else if (series) {
@@ -1605,6 +1649,16 @@ static void make_part(Part& part, int& maxseg, int nU, int nJ, int ctas) {
     maxseg = static_cast<int>((nJ + q - 1) / q + 1);
 }
 
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+// stride ~ 0.38 nJ, coprime with nJ: consecutive visits land far apart, every block is visited once per period
+static int coprime_stride(int nJ) {
+    if (nJ <= 2) return 1;
+    int s = static_cast<int>(nJ * 0.381966f + 0.5f);
+    if (s < 1) s = 1;
+    while (gcd_int(s, nJ) != 1) ++s;
+    return s % nJ == 0 ? 1 : s % nJ;
+}
+
 static Layout make_layout(int nI, int nJ) {
     Layout L;
     const int ctas = sm_count();
@@ -1648,6 +1702,7 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.y = y;
     p.sqnorm = sqnorm;
     p.nJ = nJ; p.rb0 = rb0; p.nI = nI; p.nP = L.nP; p.n_valid = n_valid; p.mode = mode; p.ctas = L.ctas;
+    p.jstride = coprime_stride(nJ);
     p.T = T; p.Tb = Tb;
     p.partS = L.partS;
     p.partD = L.partD;

@@ -23,8 +23,9 @@ lib.dcl_debug_trace(None)
 t = buf.cpu().view(5, 32, 8)
 t0 = int(t[t > 0].min())
 print("kernel entry", int(t[0, 0, 7]) - t0, "set-up done", int(t[0, 2, 7]) - t0, "all roles done", int(t[0, 1, 7]) - t0)
-print("tile | prod: wait_e got_e | issS: wait_full got_full got_sfree issued | issD: wait_pfull got_pfull issued | g0: start got_tfull done | g1: start got_tfull done")
+print("burst| prod: wait_e got_e | issuer(k%2): wait_full got_full got_pfull got_turn issued | g0: top start got_tfull done | g1: top start got_tfull done")
 for it in range(28):
     r = lambda role, ev: (int(t[role, it, ev]) - t0) if int(t[role, it, ev]) else -1
-    print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(1,0):6d} {r(1,1):6d} {r(1,2):6d} {r(1,3):6d} | {r(2,0):6d} {r(2,1):6d} {r(2,2):6d} | "
-          f"{r(3,0):6d} {r(3,1):6d} {r(3,2):6d} | {r(4,0):6d} {r(4,1):6d} {r(4,2):6d}")
+    i = 1 + (it & 1)
+    print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(i,0):6d} {r(i,1):6d} {r(i,2):6d} {r(i,4):6d} {r(i,3):6d} | "
+          f"{r(3,3):6d} {r(3,0):6d} {r(3,1):6d} {r(3,2):6d} | {r(4,3):6d} {r(4,0):6d} {r(4,1):6d} {r(4,2):6d}")

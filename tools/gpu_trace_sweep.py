@@ -24,6 +24,7 @@ lib.dcl_debug_trace(None)
 t = buf.cpu().view(5, 32, 8)
 base = int(t[0, 0, 7])
 print("kernel entry 0, set-up done", int(t[0, 2, 7]) - base, ", all roles done", int(t[0, 1, 7]) - base)
+print("g0 first unit: iterator built", int(t[3,31,3])-base, "loads issued", int(t[3,31,0])-base, "loads arrived", int(t[3,31,1])-base, "A stored", int(t[3,31,2])-base)
 print(f"forward sweep, n={n}")
 print("tile | prod: wait_e got_e | issuer(it%2): wait_full got_full got_te0 got_turn got_te1 issued | g0: start got_tfull done | g1: start got_tfull done")
 for it in range(0, 30):
