@@ -1617,7 +1617,25 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
     __shared__ float sf[8];
     const int J = blockIdx.x, t = threadIdx.x;
     const int yv = p.y[J * 128 + t];
-    const float c = p.sqnorm ? p.sqnorm[J * 128 + t] : 0.f;
+    // |f|^2 of row t straight from the F-tile (the two 128-byte panel rows of the row, any chunk order): `sqnorm`
+    // only has to be valid for the caller's own rows, so a sharded caller need not exchange it
+    float c = 0.f;
+    if (yv >= 0) {
+        const uint8_t* trow = p.tiles + static_cast<size_t>(J) * kTileBytes + t * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes) + q);
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                    c = fmaf(lo, lo, c);
+                    c = fmaf(hi, hi, c);
+                }
+            }
+    }
     const BlockStat b = block_stat(yv, c, true, si, sf);
     if (t == 0) {
         p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);

@@ -757,23 +757,30 @@ class _ShardedPixelContrastFn(torch.autograd.Function):
         B, C, h, w = feats.shape
         n_pad = pix.shape[0]
         dev = feats.device
-        tiles_l, sqnorm_l = gather_tiles(feats, pix, n_pad)
+        nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
+        # the one real exchange step: the contrast set, gathered straight into place (the norms of the other ranks'
+        # rows are recomputed from their tiles by the library, so only the local slice of `sqnorm` is filled)
         tiles = torch.empty(world * n_pad * _DIM * 2, dtype=torch.uint8, device=dev)
         sqnorm = torch.empty(world * n_pad, dtype=torch.float32, device=dev)
-        # the one real exchange step: the contrast set (and its 4 B/row norms).  Plain back-to-back launches:
-        # torch's coalescing manager made the step time erratic (3-7 ms with 70 ms spikes on 2 B200s)
-        dist.all_gather_into_tensor(tiles, tiles_l, group=group)
-        dist.all_gather_into_tensor(sqnorm, sqnorm_l, group=group)
-        nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
+        tl = tiles[rank * n_pad * _DIM * 2:(rank + 1) * n_pad * _DIM * 2]
+        sl = sqnorm[rank * n_pad:(rank + 1) * n_pad]
+        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tl), _p(sl), _stream())
+        _count(1)
+        dist.all_gather_into_tensor(tiles, tl, group=group)
         colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_all, sqnorm, nJ, rb0, nI, n_global,
                                                          MODE_PIXEL, T, Tb)
-        # backward needs every row's constants (the dS_ki terms): 32 B per row; the loss is the sum over ranks
-        la = colA[rank * n_pad:(rank + 1) * n_pad].clone()
-        lb = colB[rank * n_pad:(rank + 1) * n_pad].clone()
-        parts = torch.empty(world, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(colA, la, group=group)
-        dist.all_gather_into_tensor(colB, lb, group=group)
-        dist.all_gather_into_tensor(parts, loss_sum[:1], group=group)     # per-rank sums over their rows
+        # backward needs every row's constants (the dS_ki terms, 32 B per row) and the loss is the sum over ranks:
+        # one all-gather of [colA | colB | local loss sum] per rank, unpacked with two strided copies
+        m4 = n_pad * 4
+        send = torch.empty(2 * m4 + 4, dtype=torch.float32, device=dev)
+        send[:m4].copy_(colA[rank * n_pad:(rank + 1) * n_pad].reshape(-1))
+        send[m4:2 * m4].copy_(colB[rank * n_pad:(rank + 1) * n_pad].reshape(-1))
+        send[2 * m4:2 * m4 + 1].copy_(loss_sum[:1])
+        recv = torch.empty((world, 2 * m4 + 4), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        colA.view(world, m4).copy_(recv[:, :m4])
+        colB.view(world, m4).copy_(recv[:, m4:2 * m4])
+        parts = recv[:, 2 * m4]
         ctx.save_for_backward(tiles, y_all, colA, colB, pix)
         ctx.meta = dict(nJ=nJ, rb0=rb0, nI=nI, n_local_pad=n_pad, shape=(B, C, h, w))
         return (parts.sum() / n_global).reshape(())
@@ -848,9 +855,12 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         lay = sp.layout
         self.last_layout, self.last_n_global = lay, sp.n_global
         if stage_t is not None:
-            packed = stage_t.to(feats.device, non_blocking=True)
-            req_dev = packed[: lay.n_pad * 4]
-            y_all = packed[cap * 4: cap * 4 + world * lay.n_pad]
+            # one compact H2D: the local requests followed by every rank's labels
+            n4 = lay.n_pad * 4
+            stage_np[n4:n4 + world * lay.n_pad] = stage_np[cap * 4: cap * 4 + world * lay.n_pad]
+            packed = stage_t[: n4 + world * lay.n_pad].to(feats.device, non_blocking=True)
+            req_dev = packed[:n4]
+            y_all = packed[n4:]
         else:
             host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
             packed = host.to(feats.device, non_blocking=True)

@@ -142,7 +142,7 @@ int dcl_host_lookahead_stats(long long* out);
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.
  *   tiles  [nJ] F-tiles (the whole contrast set; all-gathered by the caller when sharded)
- *   y      [nJ*128] i32 labels, -1 = padding        sqnorm [nJ*128]
+ *   y      [nJ*128] i32 labels, -1 = padding        sqnorm [nJ*128] (read for the local rows only)
  *   n_valid : number of valid rows over the WHOLE contrast set (the reference's N)
  *   colA, colB [nJ*128] float4 out (rows of the local blocks only are written): per-row
  *            constants consumed by dcl_contrast_bwd - (a, b, p, q) and (wn, Den, label bits, logit range L);
