@@ -751,52 +751,72 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
 
 class _ShardedPixelContrastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, pix, y_all, n_global, T, Tb, group):
+    def forward(ctx, feats, pix, y_all, n_global, T, Tb, group, dzero=None):
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         B, C, h, w = feats.shape
         n_pad = pix.shape[0]
         dev = feats.device
+        st = _stream()
         nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
+        N = world * n_pad
+        m4 = n_pad * 4
         # the one real exchange step: the contrast set, gathered straight into place (the norms of the other ranks'
         # rows are recomputed from their tiles by the library, so only the local slice of `sqnorm` is filled)
-        tiles = torch.empty(world * n_pad * _DIM * 2, dtype=torch.uint8, device=dev)
-        sqnorm = torch.empty(world * n_pad, dtype=torch.float32, device=dev)
+        tiles = torch.empty(N * _DIM * 2, dtype=torch.uint8, device=dev)
         tl = tiles[rank * n_pad * _DIM * 2:(rank + 1) * n_pad * _DIM * 2]
-        sl = sqnorm[rank * n_pad:(rank + 1) * n_pad]
-        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tl), _p(sl), _stream())
-        _count(1)
+        # sqnorm | colA | colB | rowloss | loss(2) | send (colA_l | colB_l | loss part), one allocation
+        keep, (p_sq, p_cA, p_cB, p_rl, p_loss, p_send) = _carve(dev, (N * 4, N * 16, N * 16, N * 4, 8, (2 * m4 + 4) * 4))
+        base = keep.data_ptr()
+        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tl), ctypes.c_void_p(p_sq.value + rank * n_pad * 4), st)
         dist.all_gather_into_tensor(tiles, tl, group=group)
-        colA, colB, rowloss, loss_sum = contrast_forward(tiles, y_all, sqnorm, nJ, rb0, nI, n_global,
-                                                         MODE_PIXEL, T, Tb)
+        nbytes = _ws_bytes(nI, nJ)
+        ws = _workspace(dev, nbytes)
+        with _Timed("contrast_fwd"):
+            _lib.call("dcl_contrast_fwd", _p(tiles), _p(y_all), p_sq, nJ, rb0, nI, n_global, MODE_PIXEL, float(T), float(Tb),
+                      _p(ws), nbytes, p_cA, p_cB, p_rl, p_loss, st)
+        _count(1 + _launches(MODE_PIXEL, 0))
         # backward needs every row's constants (the dS_ki terms, 32 B per row) and the loss is the sum over ranks:
         # one all-gather of [colA | colB | local loss sum] per rank, unpacked with two strided copies
-        m4 = n_pad * 4
-        send = torch.empty(2 * m4 + 4, dtype=torch.float32, device=dev)
-        send[:m4].copy_(colA[rank * n_pad:(rank + 1) * n_pad].reshape(-1))
-        send[m4:2 * m4].copy_(colB[rank * n_pad:(rank + 1) * n_pad].reshape(-1))
-        send[2 * m4:2 * m4 + 1].copy_(loss_sum[:1])
+        kf = keep.view(torch.float32)
+        o_cA, o_cB, o_loss, o_send = ((p.value - base) // 4 for p in (p_cA, p_cB, p_loss, p_send))
+        colA, colB = kf[o_cA:o_cA + N * 4], kf[o_cB:o_cB + N * 4]
+        send = kf[o_send:o_send + 2 * m4 + 4]
+        send[:m4].copy_(colA[rank * m4:(rank + 1) * m4])
+        send[m4:2 * m4].copy_(colB[rank * m4:(rank + 1) * m4])
+        send[2 * m4:2 * m4 + 1].copy_(kf[o_loss:o_loss + 1])
         recv = torch.empty((world, 2 * m4 + 4), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(recv, send, group=group)
         colA.view(world, m4).copy_(recv[:, :m4])
         colB.view(world, m4).copy_(recv[:, m4:2 * m4])
-        parts = recv[:, 2 * m4]
-        ctx.save_for_backward(tiles, y_all, colA, colB, pix)
-        ctx.meta = dict(nJ=nJ, rb0=rb0, nI=nI, n_local_pad=n_pad, shape=(B, C, h, w))
-        return (parts.sum() / n_global).reshape(())
+        loss = recv[:, 2 * m4].sum() / n_global
+        ctx.save_for_backward(tiles, y_all, keep, pix)
+        ctx.meta = (nJ, rb0, nI, n_pad, (B, C, h, w), (p_cA, p_cB))
+        ctx.dzero = dzero
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        tiles, y_all, colA, colB, pix = ctx.saved_tensors
-        m = ctx.meta
-        dF = contrast_backward(tiles, y_all, colA, colB, m["nJ"], m["rb0"], m["nI"], MODE_PIXEL)
-        B, C, h, w = m["shape"]
-        dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=tiles.device)
-        g = grad_out.to(torch.float32).contiguous()
-        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), m["n_local_pad"], _p(g), _p(dfeats), B, h * w, 1,
-                  _stream())
-        _count(2)
-        return dfeats, None, None, None, None, None, None
+        tiles, y_all, keep, pix = ctx.saved_tensors
+        nJ, rb0, nI, n_pad, (B, C, h, w), (p_cA, p_cB) = ctx.meta
+        dev = tiles.device
+        st = _stream()
+        dF = torch.empty((n_pad, _DIM), dtype=torch.float32, device=dev)
+        nbytes = _ws_bytes(nI, nJ)
+        ws = _workspace(dev, nbytes)
+        with _Timed("contrast_bwd"):
+            _lib.call("dcl_contrast_bwd", _p(tiles), _p(y_all), p_cA, p_cB, nJ, rb0, nI, MODE_PIXEL, _p(ws), nbytes,
+                      _p(dF), st)
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
+            grad_out.to(torch.float32).contiguous()
+        dfeats, ctx.dzero = ctx.dzero, None
+        zero_fill = 0
+        if dfeats is None:
+            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
+            zero_fill = 1
+        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfeats), B, h * w, zero_fill, st)
+        _count(_launches(MODE_PIXEL, 1) + 1 + zero_fill)
+        return dfeats, None, None, None, None, None, None, None
 
 
 class ShardedPixelContrastLoss(PixelContrastLoss):
@@ -831,7 +851,18 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         code, chunk, counts = classify(labels_c, predict_c, h, w)
         counts_all = torch.empty((world * B, _BINS), dtype=torch.int32, device=feats.device)
         dist.all_gather_into_tensor(counts_all, counts, group=group)
-        counts_host = counts_all.cpu().numpy().reshape(world * B, 256, 2)
+        hc = getattr(self, "_shard_counts", None)
+        if hc is None or hc[0].numel() != world * B * _BINS:
+            t = torch.empty(world * B * _BINS, dtype=torch.int32).pin_memory()
+            hc = self._shard_counts = (t, t.numpy(), torch.cuda.Event())
+        hc[0].copy_(counts_all.view(-1), non_blocking=True)
+        hc[2].record()
+        dzero = None
+        if feats_c.requires_grad and torch.is_grad_enabled():
+            dzero = torch.zeros_like(feats_c)              # runs on the GPU while the host plans below
+            _count(1)
+        hc[2].synchronize()
+        counts_host = hc[1].reshape(world * B, 256, 2)
         if _verify_host_rng():
             cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
             key = (world, cap)
@@ -855,12 +886,9 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         lay = sp.layout
         self.last_layout, self.last_n_global = lay, sp.n_global
         if stage_t is not None:
-            # one compact H2D: the local requests followed by every rank's labels
-            n4 = lay.n_pad * 4
-            stage_np[n4:n4 + world * lay.n_pad] = stage_np[cap * 4: cap * 4 + world * lay.n_pad]
-            packed = stage_t[: n4 + world * lay.n_pad].to(feats.device, non_blocking=True)
-            req_dev = packed[:n4]
-            y_all = packed[n4:]
+            # two small H2D copies: the local requests and every rank's labels
+            req_dev = stage_t[: lay.n_pad * 4].to(feats.device, non_blocking=True)
+            y_all = stage_t[cap * 4: cap * 4 + world * lay.n_pad].to(feats.device, non_blocking=True)
         else:
             host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
             packed = host.to(feats.device, non_blocking=True)
@@ -870,4 +898,4 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         pix = select_pixels(code, chunk, B, h * w, req_dev, lay.n_pad)
         self.last_pix = pix
         return _ShardedPixelContrastFn.apply(feats_c, pix, y_all, sp.n_global, self.temperature,
-                                             self.base_temperature, group)
+                                             self.base_temperature, group, dzero)
