@@ -13,7 +13,7 @@
 //     diagonal: the shift keeps every sum well conditioned).  ONE sweep (SWEEP_P) produces, per row, the exact
 //     maximum and P_0..P_2 of the different-class columns plus Q_0..Q_2 of the same-class columns (packed FFMA2, no
 //     MUFU, no per-row constants but c_i); kappa_i comes from P + Q, and with n = 1 (a few thousand anchors or
-//     more) everything else follows per row (k_combine1/2).  Rows whose range needs n > 1 trigger a second sweep
+//     more) everything else follows per row in k_rows.  Rows whose range needs n > 1 trigger a second sweep
 //     (SWEEP_H: x^3..x^{n+1}) that otherwise exits at once; the positive-pair terms use a first-order series in
 //     E/Den and fall back to the exact sweep C only when some row has fewer than ~170 negatives.
 //   * image term and the diagnostic legacy path: sweep A (max, sums), sweep B (Den), as in round 1.
@@ -36,6 +36,7 @@
 // are bit-reproducible.
 #include <cfloat>
 #include <type_traits>
+#include <utility>
 #include <cuda_bf16.h>
 #include "dcl_common.cuh"
 #include "dcl_ptx.cuh"
@@ -52,17 +53,34 @@ constexpr int kMaxBlocks = 1024;      // column blocks whose info is cached in s
 constexpr int kCoefPairFloats = 12;   // backward column coefficients of one column pair: 3 x float4
 
 // ---------------------------------------------------------------------------------------------
-// flattened-range partition of nU row units x nJ column blocks over G CTAs
+// Partition of nU row units x nJ column blocks (the flattened tile list, unit-major) over G CTAs.
+//   flat     : G equal contiguous ranges; a range may cross unit boundaries (the CTA then works on two or more
+//              units one after the other, each ending in a pipeline drain, an operand reload and a segment partial).
+//   exclusive: when there are at least as many CTAs as units, every unit owns `base` or `base + 1` whole CTAs
+//              (the first `extra` units get one more) that split its nJ column blocks evenly; no CTA crosses a
+//              unit.  Chosen by make_part when its longest range beats the flat range plus one unit switch.
 struct Part {
     long long total;
     int G, nJ;
-    __host__ __device__ long long begin(int c) const { return static_cast<long long>(c) * total / G; }
-    // CTA whose range contains flat tile index x
+    int excl, base, extra;
+    __host__ __device__ long long begin(int c) const {
+        if (!excl) return static_cast<long long>(c) * total / G;
+        const int wide = extra * (base + 1);             // CTAs of the units that own base + 1
+        int u, k, parts;
+        if (c < wide) { u = c / (base + 1); k = c - u * (base + 1); parts = base + 1; }
+        else { const int d = c - wide; u = extra + d / base; k = d - (u - extra) * base; parts = base; }
+        return static_cast<long long>(u) * nJ + static_cast<long long>(k) * nJ / parts;
+    }
+    // CTA whose range contains flat tile index x (flat mode)
     __host__ __device__ int cta_of(long long x) const {
         return static_cast<int>(((x + 1) * G + total - 1) / total - 1);
     }
-    __host__ __device__ int first_cta(int U) const { return cta_of(static_cast<long long>(U) * nJ); }
+    __host__ __device__ int first_cta(int U) const {
+        if (excl) return U < extra ? U * (base + 1) : extra * (base + 1) + (U - extra) * base;
+        return cta_of(static_cast<long long>(U) * nJ);
+    }
     __host__ __device__ int nseg(int U) const {
+        if (excl) return U < extra ? base + 1 : base;
         return cta_of(static_cast<long long>(U + 1) * nJ - 1) - first_cta(U) + 1;
     }
 };
@@ -80,23 +98,27 @@ struct Params {
     int maxsegS, maxsegD;
     int splitc;              // sweep C: CTAs per row-block pair
     // block info (all nJ column blocks)
-    int4* binfo;             // (ymin, ymax, nvalid, 0); (INT_MAX, -1, 0) when the block has no valid row
+    int4* binfo;             // (ymin, ymax, nvalid, backward: largest polynomial degree); (INT_MAX, -1, 0) when no row is valid
     float2* bnorm;           // (max, min) of |f|^2 over the block's valid rows
     // legacy sweeps A / B
     float4* pA;              // [nI][maxsegS][128] (max(s-c), S1, S2, -)
     float2* pB;              // [nI][maxsegS][128] (Den, Bt)
     // v3 power-sum forward
-    int* iscal;              // [0] largest polynomial degree of the local rows, [3] the same for the backward (all rows),
+    int* iscal;              // [0] largest polynomial degree of the local rows,
                              // [4] != 0: some row has too few negatives for the positive-pair series (sweep C runs)
+                             // [5] != 0: some row was not finished by k_rows (k_combine2 and k_finalize run)
     float4* pF;              // [nI][maxsegS][2][128] sweep P partials: (max x, P0, P1, P2) (Q0, Q1, Q2, -)
     float4* pH;              // [nI][maxsegS][2][128] sweep H partials: (P3, P4, P5, -) (Q3, Q4, Q5, -)
     float* rowM;             // [nI*128][8] (P0, P1, P2, Q0, Q1, Q2, d = max x, L)
     float4* rowPos;          // [nI*128] positive-pair sums from the series: (P, sum lp, sum inv, sum inv*l)
+    int* rowflag;            // [nI*128] != 0: k_rows left the row to k_combine2 / sweep C / k_finalize
     // per-row state shared by sweep C / finalize
     float4* rowS;            // [nI*128] (a, b, kappa, m)   t = a s + b = l log2(e)
     float4* rowD;            // [nI*128] (Den, Bt = sum_den E t, L, 0)
     float4* pC;              // [nI][splitc][128] (P, sum lp | sum l, sum inv, sum inv*l)
     float* pD;               // [nI][maxsegD][128][128] dF partials
+    float* dF;               // [nI*128][128] backward result
+    unsigned int* dticket;   // [nI] backward: segments of a row block that have landed
     float4* colA;            // [nJ*128] (a, b, p, q)
     float4* colB;            // [nJ*128] (wn, Den, y bits, L)
     float* coefR;            // [nJ*128][16] backward row polynomials (n0..n4 - - - p0..p4 - - -), see k_bwd_prep
@@ -106,8 +128,9 @@ struct Params {
     float* rowloss;          // [nJ*128]
     float* blockloss;        // [nI]
     float* loss_sum;
-    unsigned int* ticket;    // last-block counter of k_finalize
+    unsigned int* ticket;    // last-block counters: [0] k_rows, [1] k_finalize
     long long* trace;        // diagnostics only (dcl_debug_trace)
+    long long* cta_times;    // diagnostics only (dcl_debug_cta_times): [kernel slot][256 CTAs][4] globaltimer / clock64 at entry, exit
     int debug;               // diagnostics only (dcl_debug_flags)
 };
 
@@ -211,6 +234,14 @@ __device__ __forceinline__ bool elect_one() {
 // The same walk as a real loop (one chunk body in the instruction stream instead of four): the pipelined kernels
 // hold several alternative epilogue bodies, and unrolled they overflow the instruction cache.  The TMEM load
 // latency of a chunk is covered by the other epilogue warp of the scheduler.
+// Programmatic dependent launch: every kernel of a forward / backward chain lets its successor start at once
+// (launch_dependents at the top) and waits for its predecessor's results (wait) before the first access to global
+// memory that a predecessor writes or still reads; the successor's launch latency and set-up then overlap this
+// kernel.  EVERY thread passes pdl_wait() before it exits: a grid that completed without waiting would release its
+// own successor while the grid before it still runs.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class Fn>
 __device__ __forceinline__ void for_each_chunk_loop(uint32_t taddr, Fn&& fn) {
 #pragma unroll 1
@@ -227,6 +258,20 @@ __device__ __forceinline__ void trace_stamp(const Params& p, int role, int it, i
     if (p.trace && blockIdx.x == 0 && it < 32) p.trace[(role * 32 + it) * 8 + ev] = clock64();
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// kernel slot: 0 sweep P, 1 backward, 2 k_rows, 3 k_bwd_prep; which = 0 entry, 1 exit (one thread per CTA)
+__device__ __forceinline__ void cta_time(const Params& p, int slot, int which) {
+    if (p.cta_times && blockIdx.x < 256) {
+        long long* o = p.cta_times + (static_cast<size_t>(slot) * 256 + blockIdx.x) * 4 + which * 2;
+        o[0] = globaltimer_ns();
+        o[1] = clock64();
+    }
+}
+
 __device__ __forceinline__ bool ranges_overlap(int2 a, int2 b) { return a.x <= b.y && b.x <= a.y; }
 
 // =============================================================================================
@@ -241,18 +286,21 @@ __device__ __forceinline__ int poly_degree_for(double L) { return L <= 0.03 ? 1 
 __device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, double (&d)[5]) {
     double r = 0.5 * L;
     if (r < 1e-8) r = 1e-8;
-    // a_k = (2 - [k == 0]) I_k(r)
-    double a[5];
+    // a_k = (2 - [k == 0]) I_k(r),  I_k(r) = (r/2)^k / k! * sum_j (r^2/4)^j / (j! (k+1)..(k+j)): with r <= 1/2 the
+    // j-th term is below 0.0625^j / j!^2, five terms reach 1e-12.  Reciprocals are compile-time constants: this
+    // runs once per row on the critical path of k_rows / k_bwd_prep, where fp64 divisions dominate the latency.
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const double h = 0.5 * r, h2 = h * h;
-    double hk = 1.0, kfact = 1.0;
+    double hk = 1.0;
+#pragma unroll
     for (int k = 0; k <= 4; ++k) {
-        if (k > 0) { hk *= h; kfact *= k; }
-        double term = hk / kfact, sum = term;      // j = 0 term: h^k / k!
-        for (int j = 1; j <= 8; ++j) {
-            term *= h2 / (static_cast<double>(j) * (j + k));
-            sum += term;
+        if (k <= deg) {
+            if (k > 0) hk *= h * (1.0 / k);          // h^k / k!
+            double sum = 1.0;
+#pragma unroll
+            for (int j = 4; j >= 1; --j) sum = 1.0 + sum * h2 * (1.0 / (static_cast<double>(j) * (j + k)));   // Horner in h^2
+            a[k] = (k == 0 ? 1.0 : 2.0) * hk * sum;
         }
-        a[k] = (k == 0 ? 1.0 : 2.0) * sum;
     }
     // Chebyshev -> monomials in x = z / r
     double cx[5] = {0, 0, 0, 0, 0};
@@ -261,18 +309,22 @@ __device__ inline void exp_poly_in_s(double kappa, double m, double L, int deg, 
     if (deg >= 2) { cx[0] -= a[2]; cx[2] = 2.0 * a[2]; }
     if (deg >= 3) { cx[1] -= 3.0 * a[3]; cx[3] = 4.0 * a[3]; }
     if (deg >= 4) { cx[0] += a[4]; cx[2] -= 8.0 * a[4]; cx[4] = 8.0 * a[4]; }
-    const double er = exp(-r);
-    double cz[5], rn = 1.0;
-    for (int n = 0; n <= 4; ++n) { cz[n] = (n <= deg) ? er * cx[n] / rn : 0.0; rn *= r; }
+    const double er = exp(-r), ir = 1.0 / r;
+    double cz[5], irn = er;
+#pragma unroll
+    for (int n = 0; n <= 4; ++n) { cz[n] = (n <= deg) ? irn * cx[n] : 0.0; irn *= ir; }
     // z = al s + be
     const double al = kappa, be = r - kappa * m;
     const double binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
     double alp[5], bep[5];
     alp[0] = bep[0] = 1.0;
+#pragma unroll
     for (int n = 1; n <= 4; ++n) { alp[n] = alp[n - 1] * al; bep[n] = bep[n - 1] * be; }
+#pragma unroll
     for (int j = 0; j <= 4; ++j) {
         double s = 0.0;
-        for (int n = j; n <= deg; ++n) s += cz[n] * binom[n][j] * alp[j] * bep[n - j];
+#pragma unroll
+        for (int n = j; n <= 4; ++n) s += cz[n] * binom[n][j] * alp[j] * bep[n - j];      // cz[n] = 0 for n > deg
         d[j] = s;
     }
 }
@@ -493,10 +545,17 @@ __device__ __forceinline__ void hsweep_chunk(const uint32_t (&v)[32], f32x2 negc
 template <int kSweep, int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    // conditional sweeps leave before any set-up when their trigger (written by k_combine1) is clear
-    if (kSweep == SWEEP_H && p.iscal[0] <= 1) return;
-    if (kSweep == SWEEP_C && kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[4] == 0) return;
+    pdl_launch();
+    // conditional sweeps leave before any set-up when their trigger (written by k_rows) is clear; the others do
+    // their set-up first and wait for the predecessor just before the first global read
+    constexpr bool kConditional = kSweep == SWEEP_H || (kSweep == SWEEP_C && kMode == DCL_MODE_PIXEL);
+    if (kConditional) {
+        pdl_wait();
+        if (kSweep == SWEEP_H && p.iscal[0] <= 1) return;
+        if (kSweep == SWEEP_C && p.use_series && p.iscal[4] == 0) return;
+    }
     if (threadIdx.x == 0) trace_stamp(p, 0, 0, 7);          // kernel entry
+    if (kSweep == SWEEP_P && threadIdx.x == 0) cta_time(p, 0, 0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sJ = base + SmemSweep::kJ;
@@ -527,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         mbar_init(b_aseen, 2);                  // both issuers have observed the current row blocks
         mbar_fence_init();
     }
+    if (!kConditional) pdl_wait();
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) sInfo[j] = p.binfo[j];
     const Part& part = p.partS;
     const int deg = (kSweep == SWEEP_H) ? p.iscal[0] : 0;
@@ -918,6 +978,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) trace_stamp(p, 0, 1, 7);          // all roles done
+    if (kSweep == SWEEP_P && threadIdx.x == 0) cta_time(p, 0, 1);
     if (warp == kProducerWarp) tmem_dealloc<kTmemCols>(tmem);
 }
 
@@ -925,6 +986,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 // legacy combines: sweep A partials -> rowS, sweep B partials -> rowD
 // =============================================================================================
 __global__ void __launch_bounds__(128) k_combine_A(const Params p) {
+    pdl_launch();
+    pdl_wait();
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
     if (I == 0 && r == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
     const int ns = p.partS.nseg(I >> 1);
@@ -945,6 +1008,8 @@ __global__ void __launch_bounds__(128) k_combine_A(const Params p) {
     p.rowS[lrow] = make_float4(a, -smax * a, kappa, smax);
 }
 __global__ void __launch_bounds__(128) k_combine_B(const Params p) {
+    pdl_launch();
+    pdl_wait();
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
     const int ns = p.partS.nseg(I >> 1);
     float den = 0.f, bt = 0.f;
@@ -957,66 +1022,208 @@ __global__ void __launch_bounds__(128) k_combine_B(const Params p) {
 }
 
 // =============================================================================================
-// v3: per row, shifted power sums + exact maximum -> kappa, logit range, polynomial degree (k_combine1);
-//     polynomial, Den, Bt and the positive-pair sums (k_combine2)
+// v3: per row, shifted power sums + exact maximum -> kappa, logit range, polynomial degree, polynomial, Den, Bt and
+//     the positive-pair sums (k_rows; k_combine2 for the rows that need the higher power sums)
 // =============================================================================================
 constexpr float kMinNegSeries = 174.0f;     // E >= 1/e, so this many negatives guarantee Den >= kMinDenSeries
 
-__global__ void __launch_bounds__(128) k_combine1(const Params p) {
+// Per-row polynomial sums: Den, Bt and the positive-pair sums of the series from the power sums P_j (different
+// class) and Q_j (same class) of x = s - c, j = 0..deg+1
+__device__ __forceinline__ void row_poly_sums(const double (&P)[6], const double (&Q)[6], double kappa, double a, double d,
+                                              double L, float4& rowD, float4& rowPos) {
+    // E as a polynomial in x = s - c:  l = kappa (x - d)
+    double e[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
+    if (kappa > 0.0) exp_poly_in_s(kappa, d, L, poly_degree_for(L), e);
+    double den = 0.0, sex = 0.0, pe = 0.0, pex = 0.0;
+    for (int j = 0; j < 5; ++j) {
+        den += e[j] * P[j]; sex += e[j] * P[j + 1];
+        pe += e[j] * Q[j];  pex += e[j] * Q[j + 1];
+    }
+    // Bt = sum_neg E t,  t = log2(e) kappa (x - d)
+    rowD = make_float4(static_cast<float>(den), static_cast<float>(a * (sex - d * den)), static_cast<float>(L), 0.f);
+    // positive pairs, first-order series in E/Den (second-order term with sum E^2 ~ (sum E)^2 / P):
+    //   lp = l - log(E + Den) ~ l - log Den - E/Den + E^2/(2 Den^2),   1/(E + Den) ~ 1/Den - E/Den^2 + E^2/Den^3
+    const double Pn = Q[0], sl = kappa * (Q[1] - d * Q[0]), sel = kappa * (pex - d * pe);
+    const double pe2 = Pn > 0.0 ? pe * pe / Pn : 0.0;
+    const double id = 1.0 / den;
+    const double SL = sl - Pn * log(den) - pe * id + 0.5 * pe2 * id * id;
+    const double SI = Pn * id - pe * id * id + pe2 * id * id * id;
+    const double SIL = sl * id - sel * id * id;
+    rowPos = make_float4(static_cast<float>(Pn), static_cast<float>(SL), static_cast<float>(SI), static_cast<float>(SIL));
+}
+
+// Row loss and the packed backward constants from the row's scale (rs), denominator sums (db) and positive-pair
+// sums (P, SL, SI, SIL)
+template <int kMode>
+__device__ __forceinline__ float finalize_row(const Params& p, const float4 rs, const float4 db, float P, float SL, float SI,
+                                              float SIL, int yi, float4& cA, float4& cB) {
+    const float kappa = rs.z;
+    const float ratio = p.T / p.Tb;
+    const float c = ratio / static_cast<float>(p.n_valid);
+    const float w = -c / P;                       // P == 0 -> NaN, as in the reference (loss.py:383)
+    const float Bl = db.y * kLn2;                 // sum_den E*l
+    float rl, Q, R, wn;
+    if (kMode == DCL_MODE_PIXEL) {
+        rl = -ratio * SL / P;
+        Q = w * SI;
+        R = w * db.x * SIL - Q * Bl;
+        wn = kappa * w * db.x;
+    } else {
+        rl = -ratio * (SL - P * logf(db.x)) / P;
+        Q = -c / db.x;
+        R = w * SL - Q * Bl;
+        wn = kappa * w;
+    }
+    cA = make_float4(rs.x, rs.y, -kappa * R * kLn2, -kappa * Q);
+    cB = make_float4(wn, db.x, __int_as_float(yi), db.z);
+    return rl;
+}
+
+// Deterministic sum of the per-row losses: block sum in a fixed tree, then the last block to arrive adds the block
+// sums in index order
+__device__ __forceinline__ float block_sum128(float v, float* red4) {
+    // fixed tree: xor-shuffles inside each warp, then the four warp sums in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red4[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (red4[0] + red4[1]) + (red4[2] + red4[3]);
+}
+__device__ __forceinline__ void block_loss_sum(const Params& p, float rl, unsigned int* ticket) {
+    __shared__ float red[4], red2[4];
+    __shared__ bool is_last;
+    const int I = blockIdx.x, r = threadIdx.x;
+    const float bs = block_sum128(rl, red);
+    if (r == 0) {
+        p.blockloss[I] = bs;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        float s = 0.f;
+        for (int i = r; i < p.nI; i += 128) s += __ldcg(p.blockloss + i);     // fixed order per thread, fixed tree after
+        s = block_sum128(s, red2);
+        if (r == 0) {
+            p.loss_sum[0] = s;
+            p.loss_sum[1] = s / static_cast<float>(p.n_valid);      // the loss itself when the rows are not sharded
+        }
+    }
+}
+
+// k_rows (after sweep P, one thread per local row): segment partials -> power sums and the exact maximum ->
+// kappa, the logit range L and the polynomial degree.  A row of degree 1 with enough negatives for the series --
+// every row of a problem with a few thousand anchors or more -- is finished here: polynomial sums, loss and
+// backward constants.  Any other row raises the triggers of the conditional kernels (sweep H for degree > 1,
+// k_combine2, sweep C for the exact positive-pair sums, k_finalize), which otherwise leave at once.
+__global__ void __launch_bounds__(128) k_rows(const Params p) {
+    pdl_launch();
+    if (threadIdx.x == 0) cta_time(p, 2, 0);
+    pdl_wait();
+    if (threadIdx.x == 0) trace_stamp(p, 0, 0, 6);
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
+    // all loads of the row first (segment partials in batches of four), the block-wide reduction behind them
+    const int ns = p.partS.nseg(I >> 1);
+    const float4* pf = p.pF + static_cast<size_t>(I) * p.maxsegS * 2 * 128 + r;
+    float mx = -FLT_MAX;
+    double P[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    float4 a4[4], b4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (u < ns) { a4[u] = __ldcg(pf + u * 256); b4[u] = __ldcg(pf + u * 256 + 128); }
+    const int yi = p.y[gi];
+    const float cself = p.sqnorm[gi];
     // largest |f|^2 of the contrast set (per-block maxima from k_blockinfo)
-    __shared__ float scm[128];
+    __shared__ float scm[4];
     float cm = 0.f;
     for (int j = r; j < p.nJ; j += 128) cm = fmaxf(cm, p.bnorm[j].x);
-    scm[r] = cm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if ((r & 31) == 0) scm[r >> 5] = cm;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (r < o) scm[r] = fmaxf(scm[r], scm[r + o]);
-        __syncthreads();
+    const double cmax = fmaxf(fmaxf(scm[0], scm[1]), fmaxf(scm[2], scm[3]));
+    if (threadIdx.x == 0) trace_stamp(p, 0, 1, 6);
+    for (int s0 = 0; s0 < ns; s0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (s0 + u < ns) {
+                const float4 a = a4[u], b = b4[u];
+                mx = fmaxf(mx, a.x);
+                P[0] += a.y; P[1] += a.z; P[2] += a.w;
+                Q[0] += b.x; Q[1] += b.y; Q[2] += b.z;
+            }
+        if (s0 + 4 < ns) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s0 + 4 + u < ns) { a4[u] = __ldcg(pf + (s0 + 4 + u) * 256); b4[u] = __ldcg(pf + (s0 + 4 + u) * 256 + 128); }
+        }
     }
-    const double cmax = scm[0];
-    const int ns = p.partS.nseg(I >> 1);
-    float mx = -FLT_MAX;
-    double P[3] = {0.0, 0.0, 0.0}, Q[3] = {0.0, 0.0, 0.0};
-    for (int s = 0; s < ns; ++s) {
-        const float4* o = p.pF + ((static_cast<size_t>(I) * p.maxsegS + s) * 2) * 128 + r;
-        const float4 a = o[0], b = o[128];
-        mx = fmaxf(mx, a.x);
-        P[0] += a.y; P[1] += a.z; P[2] += a.w;
-        Q[0] += b.x; Q[1] += b.y; Q[2] += b.z;
-    }
+    if (threadIdx.x == 0) trace_stamp(p, 0, 2, 6);
     float4* rm = reinterpret_cast<float4*>(p.rowM + static_cast<size_t>(lrow) * 8);
-    if (p.y[gi] < 0) {
+    float rl = 0.f;
+    float4 cA = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 cB = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
+    int pending = 0;
+    if (yi < 0) {
         rm[0] = make_float4(0.f, 0.f, 0.f, 0.f);
         rm[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         p.rowS[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
-    // sum over every valid column of (s - m)^2 = sum (x - d)^2, d = max x (the row itself has x = 0)
-    const double d = mx, n = p.n_valid, c = p.sqnorm[gi], m = c + d;
-    const double nrm2 = (P[2] + Q[2]) - 2.0 * d * (P[1] + Q[1]) + n * d * d;
-    double kappa, L;
-    row_scale(nrm2, m, c, cmax, p.T, kappa, L);
-    const int deg = kappa > 0.0 ? poly_degree_for(L) : 1;
-    if (deg > 1) atomicMax(&p.iscal[0], deg);
-    if (P[0] < kMinNegSeries) p.iscal[4] = 1;       // same value from every such row
-    rm[0] = make_float4(static_cast<float>(P[0]), static_cast<float>(P[1]), static_cast<float>(P[2]), static_cast<float>(Q[0]));
-    rm[1] = make_float4(static_cast<float>(Q[1]), static_cast<float>(Q[2]), mx, static_cast<float>(L));
-    const double a = kappa * static_cast<double>(kLog2e);
-    p.rowS[lrow] = make_float4(static_cast<float>(a), static_cast<float>(-m * a), static_cast<float>(kappa), static_cast<float>(m));
-}
-
-__global__ void __launch_bounds__(128) k_combine2(const Params p) {
-    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r, gi = (p.rb0 + I) * 128 + r;
-    if (p.y[gi] < 0) {
         p.rowD[lrow] = make_float4(1.f, 0.f, 0.f, 0.f);
         p.rowPos[lrow] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
+    } else {
+        // sum over every valid column of (s - m)^2 = sum (x - d)^2, d = max x (the row itself has x = 0)
+        const double d = mx, n = p.n_valid, c = cself, m = c + d;
+        const double nrm2 = (P[2] + Q[2]) - 2.0 * d * (P[1] + Q[1]) + n * d * d;
+        double kappa, L;
+        row_scale(nrm2, m, c, cmax, p.T, kappa, L);
+        if (threadIdx.x == 0) trace_stamp(p, 0, 3, 6);
+        const int deg = kappa > 0.0 ? poly_degree_for(L) : 1;
+        const double a = kappa * static_cast<double>(kLog2e);
+        const float4 rs = make_float4(static_cast<float>(a), static_cast<float>(-m * a), static_cast<float>(kappa), static_cast<float>(m));
+        const float4 m0 = make_float4(static_cast<float>(P[0]), static_cast<float>(P[1]), static_cast<float>(P[2]), static_cast<float>(Q[0]));
+        const float4 m1 = make_float4(static_cast<float>(Q[1]), static_cast<float>(Q[2]), mx, static_cast<float>(L));
+        rm[0] = m0;
+        rm[1] = m1;
+        p.rowS[lrow] = rs;
+        const bool few = P[0] < kMinNegSeries;
+        pending = (!p.use_series || deg > 1 || few) ? 1 : 0;
+        if (pending) {
+            p.iscal[5] = 1;                          // same value from every such row
+            if (deg > 1) atomicMax(&p.iscal[0], deg);
+            if (few) p.iscal[4] = 1;
+        } else {
+            // the float-rounded values k_combine2 would read back, so both routes give identical bits
+            const double Pf[6] = {m0.x, m0.y, m0.z, 0.0, 0.0, 0.0}, Qf[6] = {m0.w, m1.x, m1.y, 0.0, 0.0, 0.0};
+            float4 db, pos;
+            row_poly_sums(Pf, Qf, rs.z, rs.x, m1.z, m1.w, db, pos);
+            if (threadIdx.x == 0) trace_stamp(p, 0, 4, 6);
+            p.rowD[lrow] = db;
+            rl = finalize_row<DCL_MODE_PIXEL>(p, rs, db, pos.x, pos.y, pos.z, pos.w, yi, cA, cB);
+        }
     }
+    p.rowflag[lrow] = pending;
+    if (!pending) {
+        p.colA[gi] = cA;
+        p.colB[gi] = cB;
+        p.rowloss[gi] = rl;
+    }
+    if (threadIdx.x == 0) trace_stamp(p, 0, 5, 6);
+    block_loss_sum(p, rl, p.ticket);               // provisional when rows are pending: k_finalize then redoes it
+    if (threadIdx.x == 0) trace_stamp(p, 0, 6, 6);
+    if (threadIdx.x == 0) cta_time(p, 2, 1);
+}
+
+// k_combine2 (conditional): the rows k_rows left pending, with the higher power sums of sweep H when it ran
+__global__ void __launch_bounds__(128) k_combine2(const Params p) {
+    pdl_launch();
+    pdl_wait();
+    if (p.iscal[5] == 0) return;
+    const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
+    if (p.rowflag[lrow] == 0) return;
     const float4* rm = reinterpret_cast<const float4*>(p.rowM + static_cast<size_t>(lrow) * 8);
     const float4 m0 = rm[0], m1 = rm[1];
     double P[6] = {m0.x, m0.y, m0.z, 0.0, 0.0, 0.0}, Q[6] = {m0.w, m1.x, m1.y, 0.0, 0.0, 0.0};
-    const double d = m1.z, L = m1.w;
     if (p.iscal[0] > 1) {
         const int ns = p.partS.nseg(I >> 1);
         for (int s = 0; s < ns; ++s) {
@@ -1027,99 +1234,49 @@ __global__ void __launch_bounds__(128) k_combine2(const Params p) {
         }
     }
     const float4 rs = p.rowS[lrow];                 // (a, b, kappa, m)
-    const double kappa = rs.z, a = rs.x;
-    // E as a polynomial in x = s - c:  l = kappa (x - d)
-    double e[5] = {1.0, 0.0, 0.0, 0.0, 0.0};
-    if (kappa > 0.0) exp_poly_in_s(kappa, d, L, poly_degree_for(L), e);
-    double den = 0.0, sex = 0.0, pe = 0.0, pex = 0.0;
-    for (int j = 0; j < 5; ++j) {
-        den += e[j] * P[j]; sex += e[j] * P[j + 1];
-        pe += e[j] * Q[j];  pex += e[j] * Q[j + 1];
-    }
-    // Bt = sum_neg E t,  t = log2(e) kappa (x - d)
-    p.rowD[lrow] = make_float4(static_cast<float>(den), static_cast<float>(a * (sex - d * den)), static_cast<float>(L), 0.f);
-    // positive pairs, first-order series in E/Den (second-order term with sum E^2 ~ (sum E)^2 / P):
-    //   lp = l - log(E + Den) ~ l - log Den - E/Den + E^2/(2 Den^2),   1/(E + Den) ~ 1/Den - E/Den^2 + E^2/Den^3
-    const double Pn = Q[0], sl = kappa * (Q[1] - d * Q[0]), sel = kappa * (pex - d * pe);
-    const double pe2 = Pn > 0.0 ? pe * pe / Pn : 0.0;
-    const double id = 1.0 / den;
-    const double SL = sl - Pn * log(den) - pe * id + 0.5 * pe2 * id * id;
-    const double SI = Pn * id - pe * id * id + pe2 * id * id * id;
-    const double SIL = sl * id - sel * id * id;
-    p.rowPos[lrow] = make_float4(static_cast<float>(Pn), static_cast<float>(SL), static_cast<float>(SI), static_cast<float>(SIL));
+    float4 db, pos;
+    row_poly_sums(P, Q, rs.z, rs.x, m1.z, m1.w, db, pos);
+    p.rowD[lrow] = db;
+    p.rowPos[lrow] = pos;
 }
 
 // =============================================================================================
 // finalize: per-row loss and backward constants (one thread per local row); the last block to finish adds the
-// per-block losses in fixed order
+// per-block losses in fixed order.  In the v3 pipeline (p.use_series) it only runs when k_rows left rows pending
+// and only redoes those; the legacy pipelines finish every row here.
 // =============================================================================================
 template <int kMode>
 __global__ void __launch_bounds__(128) k_finalize(const Params p) {
+    pdl_launch();
+    pdl_wait();
+    if (kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[5] == 0) return;
     const int I = blockIdx.x, r = threadIdx.x, lrow = I * 128 + r;
     const int gi = (p.rb0 + I) * 128 + r;
     const int yi = p.y[gi];
     float rl = 0.f;
-    float4 cA = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 cB = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
-    if (yi >= 0) {
-        const float4 rs = p.rowS[lrow];
-        const float4 db = p.rowD[lrow];
-        const float kappa = rs.z;
-        float P = 0.f, SL = 0.f, SI = 0.f, SIL = 0.f;
-        if (kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[4] == 0) {
-            const float4 v = p.rowPos[lrow];          // series sums from k_combine2 (sweep C did not run)
-            P = v.x; SL = v.y; SI = v.z; SIL = v.w;
-        } else {
-            for (int s = 0; s < p.splitc; ++s) {
-                float4 v = p.pC[(static_cast<size_t>(I) * p.splitc + s) * 128 + r];
-                P += v.x; SL += v.y; SI += v.z; SIL += v.w;
+    if (kMode == DCL_MODE_PIXEL && p.use_series && p.rowflag[lrow] == 0) {
+        rl = p.rowloss[gi];                           // finished by k_rows
+    } else {
+        float4 cA = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cB = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
+        if (yi >= 0) {
+            float P = 0.f, SL = 0.f, SI = 0.f, SIL = 0.f;
+            if (kMode == DCL_MODE_PIXEL && p.use_series && p.iscal[4] == 0) {
+                const float4 v = p.rowPos[lrow];          // series sums from k_combine2 (sweep C did not run)
+                P = v.x; SL = v.y; SI = v.z; SIL = v.w;
+            } else {
+                for (int s = 0; s < p.splitc; ++s) {
+                    float4 v = p.pC[(static_cast<size_t>(I) * p.splitc + s) * 128 + r];
+                    P += v.x; SL += v.y; SI += v.z; SIL += v.w;
+                }
             }
+            rl = finalize_row<kMode>(p, p.rowS[lrow], p.rowD[lrow], P, SL, SI, SIL, yi, cA, cB);
         }
-        const float ratio = p.T / p.Tb;
-        const float c = ratio / static_cast<float>(p.n_valid);
-        const float w = -c / P;                       // P == 0 -> NaN, as in the reference (loss.py:383)
-        const float Bl = db.y * kLn2;                 // sum_den E*l
-        float Q, R, wn;
-        if (kMode == DCL_MODE_PIXEL) {
-            rl = -ratio * SL / P;
-            Q = w * SI;
-            R = w * db.x * SIL - Q * Bl;
-            wn = kappa * w * db.x;
-        } else {
-            rl = -ratio * (SL - P * logf(db.x)) / P;
-            Q = -c / db.x;
-            R = w * SL - Q * Bl;
-            wn = kappa * w;
-        }
-        cA = make_float4(rs.x, rs.y, -kappa * R * kLn2, -kappa * Q);
-        cB = make_float4(wn, db.x, __int_as_float(yi), db.z);
+        p.colA[gi] = cA;
+        p.colB[gi] = cB;
+        p.rowloss[gi] = rl;
     }
-    p.colA[gi] = cA;
-    p.colB[gi] = cB;
-    p.rowloss[gi] = rl;
-    // deterministic block sum of the row losses
-    __shared__ float red[128];
-    __shared__ bool is_last;
-    red[r] = rl;
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if (r < s) red[r] += red[r + s];
-        __syncthreads();
-    }
-    if (r == 0) {
-        p.blockloss[I] = red[0];
-        __threadfence();
-        is_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (is_last && r == 0) {
-        __threadfence();
-        float s = 0.f;
-        const volatile float* bl = p.blockloss;
-        for (int i = 0; i < p.nI; ++i) s += bl[i];
-        p.loss_sum[0] = s;
-        p.loss_sum[1] = s / static_cast<float>(p.n_valid);      // the loss itself when the rows are not sharded
-    }
+    block_loss_sum(p, rl, p.ticket + 1);
 }
 
 // =============================================================================================
@@ -1133,6 +1290,8 @@ __global__ void __launch_bounds__(128) k_finalize(const Params p) {
 // spare floats of a coefP pair block hold the labels of its two columns.
 constexpr float kMinDenSeries = 64.0f;      // series error (E/Den)^2 <= 2.5e-4 of the positive-pair term
 __global__ void __launch_bounds__(128) k_bwd_prep(const Params p) {
+    pdl_launch();
+    pdl_wait();
     const int row = blockIdx.x * 128 + threadIdx.x;
     const float4 cA = p.colA[row];
     const float4 cB = p.colB[row];
@@ -1168,7 +1327,15 @@ __global__ void __launch_bounds__(128) k_bwd_prep(const Params p) {
     for (int j = 0; j < 5; ++j) { cn[2 * j] = static_cast<float>(dn[j]); cq[2 * j] = static_cast<float>(dp[j]); }
     cn[10] = __int_as_float(yv);
     cq[10] = 0.f;
-    if (deg > 1) atomicMax(&p.iscal[3], deg);
+    // block info of the backward (this kernel is the first of its chain): label range, valid rows, largest degree
+    __shared__ int si[12];
+    __shared__ float sf[8];
+    const BlockStat bs = block_stat(p.y[row], 0.f, true, si, sf);
+    const int d4 = __syncthreads_or(deg == 4), d3 = __syncthreads_or(deg == 3), d2 = __syncthreads_or(deg == 2);
+    if (threadIdx.x == 0) {
+        p.binfo[blockIdx.x] = make_int4(bs.lo, bs.hi, bs.n, d4 ? 4 : (d3 ? 3 : (d2 ? 2 : 1)));
+        if (blockIdx.x < p.nI) p.dticket[blockIdx.x] = 0u;
+    }
     // smallest Den of the block's valid rows
     for (int o2 = 16; o2 > 0; o2 >>= 1) den = fminf(den, __shfl_xor_sync(0xffffffffu, den, o2));
     __shared__ float sden[4];
@@ -1255,7 +1422,9 @@ __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const 
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch();
     if (threadIdx.x == 0) trace_stamp(p, 0, 0, 7);          // kernel entry
+    if (threadIdx.x == 0) cta_time(p, 1, 0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sI = base + SmemBwd::kI;
@@ -1268,6 +1437,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104, b_sfree = bar + 128,
                    b_dfull = bar + 152, b_dempty = bar + 160, b_ifull = bar + 168, b_iempty = bar + 176, b_turn = bar + 184;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + SmemBwd::kTmem);
+    volatile unsigned int* sTicket = reinterpret_cast<volatile unsigned int*>(gen + SmemBwd::kTmem + 8);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (warp == kProducerWarp) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
@@ -1289,14 +1459,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         mbar_init(b_turn + 8, 1);
         mbar_fence_init();
     }
+    pdl_wait();
+    int bdeg = 1;                                // largest polynomial degree of any row (per block from k_bwd_prep)
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
         const int4 q = p.binfo[j];
         sRange[j] = make_int2(q.x, q.y);
+        bdeg = max(bdeg, q.w);
     }
-    const int deg = (kMode == DCL_MODE_PIXEL) ? p.iscal[3] : 0;
     tc_fence_before();
-    __syncthreads();
+    const int d4 = __syncthreads_or(bdeg == 4), d3 = __syncthreads_or(bdeg == 3), d2 = __syncthreads_or(bdeg == 2);
     tc_fence_after();
+    const int deg = (kMode == DCL_MODE_PIXEL) ? (d4 ? 4 : (d3 ? 3 : (d2 ? 2 : 1))) : 0;
     if (threadIdx.x == 0) trace_stamp(p, 0, 2, 7);          // set-up done
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tD = tmem + 384;          // dF accumulator; S/G stage st lives at tmem + st*128
@@ -1573,8 +1746,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 // both groups drain half of the finished dF_I partial (64 columns each)
                 mbar_wait(b_dfull, seg & 1);
                 tc_fence_after();
-                const int sidx = blockIdx.x - p.partD.first_cta(I);
-                float* out = p.pD + ((static_cast<size_t>(I) * p.maxsegD + sidx) * 128 + r) * 128 + g * 64;
+                // a row block swept by this CTA alone goes straight to dF; otherwise a segment partial, and the last
+                // of the block's CTAs to arrive adds the partials in segment order (bit-reproducible, no atomics on data)
+                const int sidx = blockIdx.x - p.partD.first_cta(I), ns = p.partD.nseg(I);
+                float* out = (ns == 1 ? p.dF + (static_cast<size_t>(I) * 128 + r) * 128
+                                      : p.pD + ((static_cast<size_t>(I) * p.maxsegD + sidx) * 128 + r) * 128) + g * 64;
                 for_each_chunk<2>(tD + lane_off + g * 64, [&](int c0, const uint32_t (&v)[32]) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -1586,33 +1762,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_dempty);
                 ++seg;
+                if (ns > 1) {
+                    __threadfence();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");        // the eight epilogue warps
+                    if (threadIdx.x == 0) *sTicket = atomicAdd(p.dticket + I, 1u);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (*sTicket == static_cast<unsigned int>(ns - 1)) {
+                        __threadfence();
+                        const float* part = p.pD + static_cast<size_t>(I) * p.maxsegD * 128 * 128;
+                        // warp w: rows w, w+8, ..; a warp reads 512 contiguous bytes per (row, segment); eight rows
+                        // in flight per batch so the L2 round trips overlap
+#pragma unroll 1
+                        for (int r0 = warp; r0 < 128; r0 += 64) {
+                            float4 acc[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                            for (int sg = 0; sg < ns; ++sg) {
+                                float4 v[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    v[u] = __ldcg(reinterpret_cast<const float4*>(
+                                        part + (static_cast<size_t>(sg) * 128 + r0 + 8 * u) * 128 + lane * 4));
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                *reinterpret_cast<float4*>(p.dF + (static_cast<size_t>(I) * 128 + r0 + 8 * u) * 128 + lane * 4) = acc[u];
+                        }
+                    }
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) cta_time(p, 1, 1);
     if (threadIdx.x == 0) trace_stamp(p, 0, 1, 7);          // all roles done
     if (warp == kProducerWarp) tmem_dealloc<kTmemCols>(tmem);
 }
 
-// dF[row] = sum over segments of the partials
-__global__ void __launch_bounds__(256) k_reduce_dF(const Params p, float* __restrict__ dF) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);     // one warp per row
-    const int lane = threadIdx.x & 31;
-    if (row >= p.nI * 128) return;
-    const int I = row >> 7, r = row & 127;
-    const int ns = p.partD.nseg(I);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < ns; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(
-            p.pD + ((static_cast<size_t>(I) * p.maxsegD + s) * 128 + r) * 128 + lane * 4);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    *reinterpret_cast<float4*>(dF + static_cast<size_t>(row) * 128 + lane * 4) = acc;
-}
-
 // block info (first kernel of every forward / backward call; also resets the device-side scalars)
 __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
+    pdl_launch();
+    pdl_wait();     // first kernel of a chain: launched without the attribute, returns at once
     __shared__ int si[12];
     __shared__ float sf[8];
     const int J = blockIdx.x, t = threadIdx.x;
@@ -1640,7 +1836,8 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
     if (t == 0) {
         p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
         p.bnorm[J] = make_float2(b.cx, b.cn);
-        if (J == 0) { p.iscal[0] = 1; p.iscal[3] = 1; p.iscal[4] = 0; p.ticket[0] = 0u; }
+        if (J < p.nI) p.dticket[J] = 0u;
+        if (J == 0) { p.iscal[0] = 1; p.iscal[3] = 1; p.iscal[4] = 0; p.iscal[5] = 0; p.ticket[0] = 0u; p.ticket[1] = 0u; }
     }
 }
 
@@ -1650,21 +1847,38 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
 struct Layout {
     Part partS, partD;
     int nP, maxsegS, maxsegD, splitc, ctas;
-    size_t off_binfo, off_bnorm, off_pA, off_pB, off_iscal, off_pF, off_pH, off_rowM, off_rowPos, off_rowS, off_rowD,
-        off_pC, off_bl, off_ticket, off_coefR, off_coefP, off_coefPP, off_bden, off_pD, bytes;
+    size_t off_binfo, off_bnorm, off_pA, off_pB, off_iscal, off_pF, off_pH, off_rowM, off_rowPos, off_rowflag, off_rowS, off_rowD,
+        off_pC, off_bl, off_ticket, off_dticket, off_coefR, off_coefP, off_coefPP, off_bden, off_pD, bytes;
 };
 
 static int g_debug_flags = 0;
 static long long* g_trace = nullptr;
+static long long* g_cta_times = nullptr;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void make_part(Part& part, int& maxseg, int nU, int nJ, int ctas) {
+// `switch_tiles`: what one unit switch inside a CTA costs, in tiles (measured: ~4 in the sweeps, ~12 in the backward,
+// profiles/r01j_cta_times.log)
+static void make_part(Part& part, int& maxseg, int nU, int nJ, int ctas, int switch_tiles) {
     part.total = static_cast<long long>(nU) * nJ;
     part.nJ = nJ;
     part.G = static_cast<int>(part.total < ctas ? part.total : ctas);
+    part.excl = 0;
+    part.base = 1;
+    part.extra = 0;
     const long long q = part.total / part.G;                  // >= 1 tiles per CTA
     maxseg = static_cast<int>((nJ + q - 1) / q + 1);
+    if (nU <= part.G) {
+        const int base = part.G / nU, extra = part.G % nU;
+        const long long excl_longest = (nJ + base - 1) / base;                      // a unit that owns `base` CTAs
+        const long long flat_longest = (part.total + part.G - 1) / part.G + (part.G % nU == 0 ? 0 : switch_tiles);
+        if (excl_longest <= flat_longest) {
+            part.excl = 1;
+            part.base = base;
+            part.extra = extra;
+            maxseg = base + (extra ? 1 : 0);
+        }
+    }
 }
 
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
@@ -1682,8 +1896,8 @@ static Layout make_layout(int nI, int nJ) {
     const int ctas = sm_count();
     L.ctas = ctas;
     L.nP = (nI + 1) / 2;
-    make_part(L.partS, L.maxsegS, L.nP, nJ, ctas);
-    make_part(L.partD, L.maxsegD, nI, nJ, ctas);
+    make_part(L.partS, L.maxsegS, L.nP, nJ, ctas, 4);
+    make_part(L.partD, L.maxsegD, nI, nJ, ctas, 12);
     int sc = (ctas + L.nP - 1) / L.nP;
     L.splitc = sc < 1 ? 1 : (sc > 8 ? 8 : sc);
     const size_t rows = static_cast<size_t>(nI) * 128, allrows = static_cast<size_t>(nJ) * 128;
@@ -1698,11 +1912,13 @@ static Layout make_layout(int nI, int nJ) {
     L.off_pH = L.off_pB;
     take(L.off_rowM, sizeof(float) * 8 * rows);
     take(L.off_rowPos, sizeof(float4) * rows);
+    take(L.off_rowflag, sizeof(int) * rows);
     take(L.off_rowS, sizeof(float4) * rows);
     take(L.off_rowD, sizeof(float4) * rows);
     take(L.off_pC, sizeof(float4) * rows * L.splitc);
     take(L.off_bl, sizeof(float) * nI);
     take(L.off_ticket, sizeof(unsigned int) * 4);
+    take(L.off_dticket, sizeof(unsigned int) * nI);
     take(L.off_coefR, sizeof(float) * 16 * allrows);
     take(L.off_coefP, sizeof(float) * kCoefPairFloats * (allrows / 2));
     take(L.off_coefPP, sizeof(float) * kCoefPairFloats * (allrows / 2));
@@ -1736,6 +1952,7 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.pH = reinterpret_cast<float4*>(w + L.off_pH);
     p.rowM = reinterpret_cast<float*>(w + L.off_rowM);
     p.rowPos = reinterpret_cast<float4*>(w + L.off_rowPos);
+    p.rowflag = reinterpret_cast<int*>(w + L.off_rowflag);
     p.rowS = reinterpret_cast<float4*>(w + L.off_rowS);
     p.rowD = reinterpret_cast<float4*>(w + L.off_rowD);
     p.pC = reinterpret_cast<float4*>(w + L.off_pC);
@@ -1746,10 +1963,37 @@ static Params make_params(const Layout& L, const void* tiles, const int32_t* y, 
     p.bden = reinterpret_cast<float*>(w + L.off_bden);
     p.blockloss = reinterpret_cast<float*>(w + L.off_bl);
     p.ticket = reinterpret_cast<unsigned int*>(w + L.off_ticket);
+    p.dticket = reinterpret_cast<unsigned int*>(w + L.off_dticket);
     p.debug = g_debug_flags;
     p.trace = g_trace;
+    p.cta_times = g_cta_times;
     return p;
 }
+
+// Launch on `st`; `dependent` marks the kernel as a programmatic dependent of the launch before it on the stream
+// (see pdl_wait): the first kernel of a call is launched plainly and so is ordered after all earlier work.
+static bool g_use_pdl = true;
+template <class... KArgs, class... Args>
+static cudaError_t launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                          bool dependent, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && g_use_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define DCL_LAUNCH(name, ...)                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = launch(__VA_ARGS__);                                                              \
+        if (e_ != cudaSuccess)                                                                             \
+            return ::dcl::fail(static_cast<int>(e_), "launch %s: %s", name, cudaGetErrorString(e_));       \
+    } while (0)
 
 template <class K>
 static int set_smem(K kernel, int bytes) {
@@ -1758,7 +2002,7 @@ static int set_smem(K kernel, int bytes) {
 }
 
 // v3 pixel forward: block info, one power-sum sweep, per-row combination; the higher-moment sweep and the exact
-// positive-pair sweep C are launched too but leave at once unless k_combine1 raised their triggers
+// positive-pair sweep C are launched too but leave at once unless k_rows raised their triggers
 static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -1768,20 +2012,13 @@ static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
         configured = true;
     }
     p.use_series = 1;
-    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_blockinfo");
-    k_sweep<SWEEP_P, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<P>");
-    k_combine1<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine1");
-    k_sweep<SWEEP_H, DCL_MODE_PIXEL><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<H>");
-    k_combine2<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine2");
-    k_sweep<SWEEP_C, DCL_MODE_PIXEL><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<C>");
-    k_finalize<DCL_MODE_PIXEL><<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_finalize");
+    DCL_LAUNCH("k_blockinfo", k_blockinfo, p.nJ, 128, 0, st, false, p);
+    DCL_LAUNCH("k_sweep<P>", k_sweep<SWEEP_P, DCL_MODE_PIXEL>, L.partS.G, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_rows", k_rows, p.nI, 128, 0, st, true, p);
+    DCL_LAUNCH("k_sweep<H>", k_sweep<SWEEP_H, DCL_MODE_PIXEL>, L.partS.G, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_combine2", k_combine2, p.nI, 128, 0, st, true, p);
+    DCL_LAUNCH("k_sweep<C>", k_sweep<SWEEP_C, DCL_MODE_PIXEL>, L.nP * L.splitc, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_finalize", k_finalize<DCL_MODE_PIXEL>, p.nI, 128, 0, st, true, p);
     return 0;
 }
 
@@ -1794,20 +2031,13 @@ static int run_fwd_legacy(Params p, const Layout& L, cudaStream_t st) {
         if (int e = set_smem(k_sweep<SWEEP_C, kMode>, SmemSweep::kBytes)) return e;
         configured = true;
     }
-    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_blockinfo");
-    k_sweep<SWEEP_A, kMode><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<A>");
-    k_combine_A<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine_A");
-    k_sweep<SWEEP_B, kMode><<<L.partS.G, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<B>");
-    k_combine_B<<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_combine_B");
-    k_sweep<SWEEP_C, kMode><<<L.nP * L.splitc, kThreads, SmemSweep::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_sweep<C>");
-    k_finalize<kMode><<<p.nI, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_finalize");
+    DCL_LAUNCH("k_blockinfo", k_blockinfo, p.nJ, 128, 0, st, false, p);
+    DCL_LAUNCH("k_sweep<A>", k_sweep<SWEEP_A, kMode>, L.partS.G, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_combine_A", k_combine_A, p.nI, 128, 0, st, true, p);
+    DCL_LAUNCH("k_sweep<B>", k_sweep<SWEEP_B, kMode>, L.partS.G, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_combine_B", k_combine_B, p.nI, 128, 0, st, true, p);
+    DCL_LAUNCH("k_sweep<C>", k_sweep<SWEEP_C, kMode>, L.nP * L.splitc, kThreads, SmemSweep::kBytes, st, true, p);
+    DCL_LAUNCH("k_finalize", k_finalize<kMode>, p.nI, 128, 0, st, true, p);
     return 0;
 }
 
@@ -1818,16 +2048,11 @@ static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
         if (int e = set_smem(k_backward<kMode>, SmemBwd::kBytes)) return e;
         configured = true;
     }
-    k_blockinfo<<<p.nJ, 128, 0, st>>>(p);
-    DCL_LAUNCH_CHECK("k_blockinfo");
-    if (kMode == DCL_MODE_PIXEL) {
-        k_bwd_prep<<<p.nJ, 128, 0, st>>>(p);
-        DCL_LAUNCH_CHECK("k_bwd_prep");
-    }
-    k_backward<kMode><<<L.partD.G, kThreads, SmemBwd::kBytes, st>>>(p);
-    DCL_LAUNCH_CHECK("k_backward");
-    k_reduce_dF<<<(p.nI * 128 + 7) / 8, 256, 0, st>>>(p, dF);
-    DCL_LAUNCH_CHECK("k_reduce_dF");
+    // first kernel of the chain (launched plainly): block info, and for the pixel term the row polynomials with it
+    if (kMode == DCL_MODE_PIXEL) DCL_LAUNCH("k_bwd_prep", k_bwd_prep, p.nJ, 128, 0, st, false, p);
+    else DCL_LAUNCH("k_blockinfo", k_blockinfo, p.nJ, 128, 0, st, false, p);
+    p.dF = dF;
+    DCL_LAUNCH("k_backward", k_backward<kMode>, L.partD.G, kThreads, SmemBwd::kBytes, st, true, p);
     return 0;
 }
 
@@ -1836,14 +2061,23 @@ static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
 using namespace dcl;
 
 // Diagnostics only: component-isolation switches for profiling (results are invalid when bits 0..2 are set).
-// Bit 3 (8) selects the legacy three-sweep forward for the pixel term.
+// Bit 3 (8) selects the legacy three-sweep forward for the pixel term; bit 4 (16) launches every kernel plainly
+// (no programmatic dependent launch).
 extern "C" int dcl_debug_flags(int flags) {
     const int old = g_debug_flags;
     g_debug_flags = flags;
+    g_use_pdl = !(flags & 16);
     return old;
 }
 
 // Diagnostics only: device buffer of 5*32*8 int64 that CTA 0 of the pipelined kernels fills with clock64 stamps.
+// Diagnostics only: device buffer of 4*256*4 int64; every CTA of the sweep-P, backward and k_rows kernels records
+// (globaltimer, clock64) at entry and exit.
+extern "C" int dcl_debug_cta_times(void* device_buffer) {
+    g_cta_times = static_cast<long long*>(device_buffer);
+    return 0;
+}
+
 extern "C" int dcl_debug_trace(void* device_buffer) {
     g_trace = static_cast<long long*>(device_buffer);
     return 0;
@@ -1851,7 +2085,7 @@ extern "C" int dcl_debug_trace(void* device_buffer) {
 
 // kernels launched by one forward (backward != 0: one backward) call for `mode` with the current debug flags
 extern "C" int dcl_contrast_launches(int mode, int backward) {
-    if (backward) return mode == DCL_MODE_PIXEL ? 4 : 3;
+    if (backward) return 2;
     return 7;
 }
 

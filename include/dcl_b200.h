@@ -48,12 +48,16 @@ const char* dcl_last_error(void);
 int dcl_check_device(void);
 /* Diagnostics only: profiling switches for the contrast kernels (1 = skip epilogue math, 2 = skip
  * the S = F_I F_J^T MMAs, 4 = skip the dF MMAs: results are invalid while any of these is set;
- * 8 = run the pixel term's forward through the legacy three-sweep path, results stay valid).
+ * 8 = run the pixel term's forward through the legacy three-sweep path, 16 = launch every kernel
+ * plainly instead of as a programmatic dependent of the one before it; results stay valid for both).
  * Returns the previous value. */
 int dcl_debug_flags(int flags);
 /* Diagnostics only: device buffer (5*32*8 int64, or NULL to disable) that CTA 0 of the pipelined
  * kernels fills with per-role clock64 stamps of its first 32 tiles. */
 int dcl_debug_trace(void* device_buffer);
+/* Diagnostics only: device buffer of 4*256*4 int64; every CTA of the sweep-P, backward and k_rows kernels
+ * records (globaltimer ns, clock64) at entry and exit.  NULL switches it off. */
+int dcl_debug_cta_times(void* device_buffer);
 /* Number of kernels one dcl_contrast_fwd (backward == 0) or dcl_contrast_bwd call launches for `mode`. */
 int dcl_contrast_launches(int mode, int backward);
 

@@ -32,3 +32,7 @@ for it in range(0, 30):
     i = 1 + (it & 1)
     print(f"{it:3d} | {r(0,0):6d} {r(0,1):6d} | {r(i,0):6d} {r(i,1):6d} {r(i,2):6d} {r(i,4):6d} {r(i,5):6d} {r(i,3):6d} | "
           f"{r(3,0):6d} {r(3,1):6d} {r(3,2):6d} | {r(4,0):6d} {r(4,1):6d} {r(4,2):6d}")
+rows = [int(t[0, k, 6]) for k in range(7)]
+if rows[0]:
+    print("k_rows block 0 (clk from its start): after cmax", rows[1] - rows[0], "partials", rows[2] - rows[0], "row_scale", rows[3] - rows[0],
+          "poly sums", rows[4] - rows[0], "finalize+stores", rows[5] - rows[0], "loss sum", rows[6] - rows[0])
