@@ -66,6 +66,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so is stale: loud by design
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("DCL_DEBUG_FLAGS"):      # tools/ experiments only (see dcl_debug_flags in the header)
+        lib.dcl_debug_flags(int(os.environ["DCL_DEBUG_FLAGS"]))
     _lib = lib
     return lib
 

@@ -231,9 +231,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// The same walk as a real loop (one chunk body in the instruction stream instead of four): the pipelined kernels
-// hold several alternative epilogue bodies, and unrolled they overflow the instruction cache.  The TMEM load
-// latency of a chunk is covered by the other epilogue warp of the scheduler.
 // Programmatic dependent launch: every kernel of a forward / backward chain lets its successor start at once
 // (launch_dependents at the top) and waits for its predecessor's results (wait) before the first access to global
 // memory that a predecessor writes or still reads; the successor's launch latency and set-up then overlap this
@@ -242,6 +239,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// The same walk as a real loop (one chunk body in the instruction stream instead of four): the pipelined kernels
+// hold several alternative epilogue bodies, and unrolled they overflow the instruction cache.  The TMEM load
+// latency of a chunk is covered by the other epilogue warp of the scheduler.
 template <class Fn>
 __device__ __forceinline__ void for_each_chunk_loop(uint32_t taddr, Fn&& fn) {
 #pragma unroll 1
@@ -250,6 +250,24 @@ __device__ __forceinline__ void for_each_chunk_loop(uint32_t taddr, Fn&& fn) {
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait_on(v);
         fn(c0, v);
+    }
+}
+// Middle ground: a real loop of two trips, each with two chunk bodies, the next chunk's TMEM load in flight behind
+// the current body (half the code of for_each_chunk<4>, none of the exposed load latency of for_each_chunk_loop,
+// which costs a mixed tile about twice a plain one).
+template <class Fn>
+__device__ __forceinline__ void for_each_chunk_loop2(uint32_t taddr, Fn&& fn) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr, va);
+    tmem_ld_wait_on(va);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 64) {
+        tmem_ld32(taddr + c0 + 32, vb);
+        fn(c0, va);
+        tmem_ld_wait_on(vb);
+        if (c0 == 0) tmem_ld32(taddr + 64, va);
+        fn(c0 + 32, vb);
+        if (c0 == 0) tmem_ld_wait_on(va);
     }
 }
 
@@ -398,8 +416,10 @@ struct SmemBwd {
     static constexpr int kI = 0;
     static constexpr int kJ = kTileBytes;
     static constexpr int kCP = (1 + kSlots) * kTileBytes;
-    static constexpr int kRange = kCP + kSlots * kCoefBytes;      // int2[kMaxBlocks]
-    static constexpr int kBar = kRange + 8 * kMaxBlocks;  // full[5] empty[5] tfull[3] pfull[3] sfree[3] dfull dempty ifull iempty
+    static constexpr int kCQ = kCP + kSlots * kCoefBytes;         // same-class column polynomials (tiles that can hold such pairs)
+    static constexpr int kRange = kCQ + kSlots * kCoefBytes;      // uint16[kMaxBlocks]: label range of a block, lo | hi << 8
+    static constexpr int kDenOk = kRange + 2 * kMaxBlocks;        // uint8[kMaxBlocks]: every Den of the block >= kMinDenSeries
+    static constexpr int kBar = kDenOk + kMaxBlocks;      // full[5] empty[5] tfull[3] pfull[3] sfree[3] dfull dempty ifull iempty
     static constexpr int kTmem = kBar + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;
 };
@@ -713,6 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         int* wy = sLab + warp * 128;
         float cshift = 0.f, ra = 0.f, rb = 0.f, rden = 1.f;
         int yi = -1, gi = -1, Iloc = 0, lrow = 0, nunits = 0;
+        int wlo = INT_MAX, whi = -1;                        // label range of this warp's 32 valid rows
         int2 rI = make_int2(INT_MAX, -1);
 
         auto reset = [&]() {
@@ -805,6 +826,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             lrow = Iloc * 128 + r;
             const int4 bi = sInfo[p.rb0 + Iloc];
             rI = make_int2(bi.x, bi.y);
+            wlo = __reduce_min_sync(0xffffffffu, yi >= 0 ? yi : INT_MAX);
+            whi = __reduce_max_sync(0xffffffffu, yi);
             if (kSweep == SWEEP_A) {
                 // cshift loaded above
             } else if (kSweep == SWEEP_P || kSweep == SWEEP_H) {
@@ -849,10 +872,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     reinterpret_cast<int4*>(wy)[lane] = __ldg(reinterpret_cast<const int4*>(yJ) + lane);
                     __syncwarp();
                     if (all_valid) {
+                        // rows are class-sorted, so most 32-row x 32-column pieces of a mixed tile are uniform: no
+                        // shared class (plain sums, counted as different-class) or one class on both sides (plain
+                        // sums into the all-columns accumulators); only pieces on a class boundary go element-wise
                         for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
-                            psweep_chunk_masked<true>(v, wy + c0, yi, negc, mA0, mA1, mA2, mP0, mP1, mP2, mx4);
+                            const int yl = wy[c0 + lane];
+                            const int cmin = __reduce_min_sync(0xffffffffu, yl), cmax = __reduce_max_sync(0xffffffffu, yl);
+                            if (cmax < wlo || cmin > whi) {
+                                psweep_chunk(v, negc, q3, q4, mx4);
+                                mN0 += 32.f;
+                            } else if (cmin == cmax && wlo == whi && cmin == wlo) {
+                                f32x2 t1[4] = {0ull, 0ull, 0ull, 0ull}, t2[4] = {0ull, 0ull, 0ull, 0ull};
+                                psweep_chunk(v, negc, t1, t2, mx4);
+                                mA1 = fadd2(mA1, fadd2(fadd2(t1[0], t1[1]), fadd2(t1[2], t1[3])));
+                                mA2 = fadd2(mA2, fadd2(fadd2(t2[0], t2[1]), fadd2(t2[2], t2[3])));
+                                mQ0 += 32.f;
+                            } else {
+                                psweep_chunk_masked<true>(v, wy + c0, yi, negc, mA0, mA1, mA2, mP0, mP1, mP2, mx4);
+                                mQ0 += 32.f;
+                            }
                         });
-                        mQ0 += 128.f;
                     } else {
                         for_each_chunk_loop(taddr, [&](int c0, const uint32_t (&v)[32]) {
                             psweep_chunk_masked<false>(v, wy + c0, yi, negc, mA0, mA1, mA2, mP0, mP1, mP2, mx4);
@@ -1387,8 +1426,8 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], const f32x2 (
         pk[j] = pack_bf16x2(g);
     }
 }
-// The same for a tile that mixes classes: both polynomials, selected per element by label equality.  `cq` points
-// at the same-class column polynomials in global memory (L1-resident: every row of the tile reads the same words).
+// The same for a tile that mixes classes: both polynomials, selected per element by label equality (`cq`: the
+// same-class column polynomials, staged in shared memory like `cp`).
 // `self` is the tile-local column of the row's own pair (0..31 inside this chunk, anything else = none): that
 // element is neither a denominator nor a positive pair, only the linear term survives: 2 p (a s + b) = fma(s, l1, l0).
 template <int kDeg>
@@ -1401,12 +1440,9 @@ __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const 
         const float4 n0 = cp[3 * j], n2 = cp[3 * j + 2];
         f32x2 gn = ffma2(col_horner<kDeg>(cp + 3 * j, n0, s), s, row_horner<kDeg>(rn, s));
         gn = fadd2(gn, pack2(n0.x, n0.y));
-        float4 u[3];
-        u[0] = __ldg(cq + 3 * j);
-        if (kDeg >= 2) u[1] = __ldg(cq + 3 * j + 1);
-        if (kDeg >= 4) u[2] = __ldg(cq + 3 * j + 2);
-        f32x2 gp = ffma2(col_horner<kDeg>(u, u[0], s), s, row_horner<kDeg>(rq, s));
-        gp = fadd2(gp, pack2(u[0].x, u[0].y));
+        const float4 u0 = cq[3 * j];
+        f32x2 gp = ffma2(col_horner<kDeg>(cq + 3 * j, u0, s), s, row_horner<kDeg>(rq, s));
+        gp = fadd2(gp, pack2(u0.x, u0.y));
         float nl, nh, pl, ph;
         unpack2(gn, nl, nh);
         unpack2(gp, pl, ph);
@@ -1431,7 +1467,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     const uint32_t sJ = base + SmemBwd::kJ;
     const uint32_t sCP = base + SmemBwd::kCP;
     const float4* gCP = reinterpret_cast<const float4*>(gen + SmemBwd::kCP);
-    int2* sRange = reinterpret_cast<int2*>(gen + SmemBwd::kRange);
+    const uint32_t sCQ = base + SmemBwd::kCQ;
+    const float4* gCQ = reinterpret_cast<const float4*>(gen + SmemBwd::kCQ);
+    // label range of every block, packed (labels are 0..255; an empty block is (255, 0))
+    uint16_t* sRangeRaw = reinterpret_cast<uint16_t*>(gen + SmemBwd::kRange);
+    auto block_range = [&](int j) { const int v = sRangeRaw[j]; return make_int2(v & 255, v >> 8); };
+    uint8_t* sDenOk = gen + SmemBwd::kDenOk;
     const uint32_t bar = base + SmemBwd::kBar;
     constexpr int kSlots = SmemBwd::kSlots, kStages = SmemBwd::kStages;
     const uint32_t b_full = bar, b_empty = bar + 40, b_tfull = bar + 80, b_pfull = bar + 104, b_sfree = bar + 128,
@@ -1463,7 +1504,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     int bdeg = 1;                                // largest polynomial degree of any row (per block from k_bwd_prep)
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) {
         const int4 q = p.binfo[j];
-        sRange[j] = make_int2(q.x, q.y);
+        // labels outside 0..255 cannot be packed: such a block overlaps everything (the element-wise path is always right)
+        if (kMode == DCL_MODE_PIXEL) sDenOk[j] = p.bden[j] >= kMinDenSeries;
+        sRangeRaw[j] = static_cast<uint16_t>(q.z > 0 ? ((q.x >= 0 && q.y <= 255) ? (q.x | (q.y << 8)) : 0xff00) : 255);
         bdeg = max(bdeg, q.w);
     }
     tc_fence_before();
@@ -1494,12 +1537,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
             if (lane == 0) trace_stamp(p, 0, it, 0);
             mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
             if (lane == 0) trace_stamp(p, 0, it, 1);
+            const bool mixed = kMode == DCL_MODE_PIXEL && ranges_overlap(block_range(p.rb0 + I), block_range(J));
             if (elect_one()) {
                 if (kMode == DCL_MODE_PIXEL) {
-                    mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes + SmemBwd::kCoefBytes);
+                    mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes + (mixed ? 2 : 1) * SmemBwd::kCoefBytes);
                     tma_bulk_g2s(sCP + slot * SmemBwd::kCoefBytes,
                                  p.coefP + static_cast<size_t>(J) * 64 * kCoefPairFloats, SmemBwd::kCoefBytes,
                                  b_full + 8 * slot);
+                    if (mixed)
+                        tma_bulk_g2s(sCQ + slot * SmemBwd::kCoefBytes,
+                                     p.coefPP + static_cast<size_t>(J) * 64 * kCoefPairFloats, SmemBwd::kCoefBytes,
+                                     b_full + 8 * slot);
                 } else {
                     mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes);
                 }
@@ -1616,8 +1664,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
         float4 rA = make_float4(0.f, 0.f, 0.f, 0.f), rB = make_float4(0.f, 1.f, 0.f, 0.f);
         f32x2 rn[5] = {0ull, 0ull, 0ull, 0ull, 0ull}, rq[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
         int yi = -1, gi = -1;
+        int wlo = INT_MAX, whi = -1;                 // label range of this warp's 32 valid rows
         int2 rI = make_int2(INT_MAX, -1);
-        float denI = 0.f;
+        bool denI = false;                           // every Den of the row block is large enough for the series
         while (iter.next(I, J, last)) {
             if ((threadIdx.x & 127) == 0) trace_stamp(p, 3 + g, it, 3);      // loop top (every tile, own or not)
             if (I != curI) {
@@ -1626,7 +1675,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 rA = p.colA[gi];
                 rB = p.colB[gi];
                 yi = __float_as_int(rB.z);
-                rI = sRange[p.rb0 + I];
+                wlo = __reduce_min_sync(0xffffffffu, yi >= 0 ? yi : INT_MAX);
+                whi = __reduce_max_sync(0xffffffffu, yi);
+                rI = block_range(p.rb0 + I);
                 if (kMode == DCL_MODE_PIXEL) {
                     const float4* cr = reinterpret_cast<const float4*>(p.coefR + static_cast<size_t>(gi) * 16);
                     const float4 n0 = cr[0], n1 = cr[1], q0 = cr[2], q1 = cr[3];
@@ -1634,7 +1685,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                     rn[3] = pack2(n0.w, n0.w); rn[4] = pack2(n1.x, n1.x);
                     rq[0] = pack2(q0.x, q0.x); rq[1] = pack2(q0.y, q0.y); rq[2] = pack2(q0.z, q0.z);
                     rq[3] = pack2(q0.w, q0.w); rq[4] = pack2(q1.x, q1.x);
-                    denI = p.bden[p.rb0 + I];
+                    denI = sDenOk[p.rb0 + I] != 0;
                 }
             }
             if ((it & 1) == g) {
@@ -1651,9 +1702,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                 // Den large -> two polynomials selected per element (+ the self pair on the diagonal tile);
                 // otherwise (tiny denominators, image term) the exact masked form.  Padding needs no mask: padded F
                 // rows are zero and padded columns carry zero coefficients.
-                const bool overlap = ranges_overlap(rI, sRange[J]);
+                const bool overlap = ranges_overlap(rI, block_range(J));
                 const bool fast = kMode == DCL_MODE_PIXEL && !overlap;
-                const bool series = kMode == DCL_MODE_PIXEL && overlap && fminf(denI, p.bden[J]) >= kMinDenSeries;
+                const bool series = kMode == DCL_MODE_PIXEL && overlap && denI && sDenOk[J];
                 if (p.debug & 1) {
                     // diagnostics: no G is produced
                 } else if (fast) {
@@ -1672,26 +1723,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
                     };
+                    // degree 3 runs the degree-4 code (its x^4 coefficients are zero): one instantiation less
                     if (deg == 1) body_pf(std::integral_constant<int, 1>{});
                     else if (deg == 2) body_pf(std::integral_constant<int, 2>{});
-                    else if (deg == 3) body(std::integral_constant<int, 3>{});
                     else body(std::integral_constant<int, 4>{});
                 } else if (series) {
-                    const float4* cq = reinterpret_cast<const float4*>(p.coefPP) + static_cast<size_t>(J) * 64 * 3;
+                    const float4* cq = gCQ + slot * (SmemBwd::kCoefBytes / 16);
                     const int selfcol = ((p.rb0 + I) == J) ? r : -1000;
                     const float l1 = 2.f * rA.z * rA.x, l0 = 2.f * rA.z * rA.y;
-                    auto body = [&](auto degc) {
-                        for_each_chunk_loop(tS, [&](int c0, const uint32_t (&v)[32]) {
+                    // rows are class-sorted, so most 32-row x 32-column pieces of a mixed tile are uniform: no shared
+                    // class -> the different-class polynomials alone; one class on both sides (and not the piece
+                    // with the rows' own columns) -> the same-class polynomials alone; element-wise only on a boundary
+                    const bool diag = (p.rb0 + I) == J;
+                    auto body = [&](auto degc, auto walk) {
+                        constexpr int kD = decltype(degc)::value;
+                        walk(tS, [&](int c0, const uint32_t (&v)[32]) {
                             uint32_t pk[16];
-                            bwd_chunk_masked<decltype(degc)::value>(v, rn, rq, cp + (c0 >> 1) * 3, cq + (c0 >> 1) * 3, yi,
-                                                                    selfcol - c0, l1, l0, pk);
+                            const float4* cpc = cp + (c0 >> 1) * 3;
+                            const int yl = __float_as_int(reinterpret_cast<const float*>(cpc + 3 * (lane >> 1) + 2)[2 + (lane & 1)]);
+                            const int cmin = __reduce_min_sync(0xffffffffu, yl), cmax = __reduce_max_sync(0xffffffffu, yl);
+                            if (cmax < wlo || cmin > whi) {
+                                bwd_chunk<kD>(v, rn, cpc, pk);
+                            } else if (cmin == cmax && wlo == whi && cmin == wlo && !(diag && c0 == q * 32)) {
+                                bwd_chunk<kD>(v, rq, cq + (c0 >> 1) * 3, pk);
+                            } else {
+                                bwd_chunk_masked<kD>(v, rn, rq, cpc, cq + (c0 >> 1) * 3, yi, selfcol - c0, l1, l0, pk);
+                            }
                             tmem_st16(tS + (c0 >> 1), pk);
                         });
                     };
-                    if (deg == 1) body(std::integral_constant<int, 1>{});
-                    else if (deg == 2) body(std::integral_constant<int, 2>{});
-                    else if (deg == 3) body(std::integral_constant<int, 3>{});
-                    else body(std::integral_constant<int, 4>{});
+                    auto walk1 = [](uint32_t t, auto&& fn) { for_each_chunk_loop(t, fn); };
+                    if (deg == 1) body(std::integral_constant<int, 1>{}, walk1);
+                    else if (deg == 2) body(std::integral_constant<int, 2>{}, walk1);
+                    else body(std::integral_constant<int, 4>{}, walk1);
                 } else {
                     const float4* cA = p.colA + static_cast<size_t>(J) * 128;
                     const float4* cB = p.colB + static_cast<size_t>(J) * 128;
