@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -250,6 +251,106 @@ void randperm_prefix(Mt& m, int64_t n, int64_t k, int64_t* out, Sparse& sp) {
     skip(m, (n - 1) - drawn);
 }
 
+// Small persistent pool for the stream mode of plan_rows: with the state blocks coming from the look-ahead ring the
+// permutations of different anchors are independent (each starts at a known offset of the stream), so they are
+// replayed on several cores.  Helpers sleep on a condition variable between plans.
+class Pool {
+public:
+    // run fn(i) for i in [0, n) on up to `threads` threads (the caller is one of them)
+    template <class Fn>
+    void run(int n, int threads, Fn&& fn) {
+        if (threads > n) threads = n;
+        if (threads <= 1) {
+            for (int i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        ensure(threads - 1);
+        std::function<void(int)> f = fn;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &f;
+            n_ = n;
+            next_.store(0, std::memory_order_relaxed);
+            pending_ = threads - 1;
+            wanted_ = threads - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (int i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < n;) f(i);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~Pool() { shutdown(); }
+
+private:
+    void ensure(int helpers) {
+        if (pid_ != getpid()) {                     // forked child: the helper threads do not exist here
+            for (auto& t : workers_) t.detach();
+            workers_.clear();
+            pid_ = getpid();
+        }
+        while (static_cast<int>(workers_.size()) < helpers) {
+            const int id = static_cast<int>(workers_.size());
+            workers_.emplace_back([this, id] { loop(id); });
+        }
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)>* f;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return quit_ || (epoch_ != seen && id < wanted_); });
+                if (quit_) return;
+                seen = epoch_;
+                f = fn_;
+                n = n_;
+            }
+            for (int i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < n;) (*f)(i);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    void shutdown() {
+        if (pid_ == getpid()) {
+            { std::lock_guard<std::mutex> g(mu_); quit_ = true; }
+            cv_.notify_all();
+            for (auto& t : workers_) t.join();
+        } else {
+            for (auto& t : workers_) t.detach();
+        }
+        workers_.clear();
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, pending_ = 0, wanted_ = 0;
+    uint64_t epoch_ = 0;
+    bool quit_ = false;
+    pid_t pid_ = getpid();
+};
+
+// threads for `draws` sampled positions: waking the helpers only pays from a few ten thousand draws on (measured on
+// the 16-core B200 host: 8192 draws 126 us alone, 148 us on two threads; 65536 draws 660 us alone, 215 us on eight)
+int host_threads(int64_t draws) {
+    static const int cap = [] {
+        if (const char* e = std::getenv("DCL_HOST_THREADS")) return std::max(1, std::atoi(e));
+        const unsigned hc = std::thread::hardware_concurrency();
+        return static_cast<int>(std::min(8u, std::max(1u, hc / 2)));
+    }();
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, draws / 8192)));
+}
+Pool& pool() {
+    static Pool p;
+    return p;
+}
+
 int load_state(void* torch_rng_state, size_t state_bytes, Mt& m) {
     if (!torch_rng_state || state_bytes < 24 + 8 * static_cast<size_t>(kN))
         return dcl::fail(DCL_ERR_ARG, "rng state buffer too small (%zu bytes)", state_bytes);
@@ -333,8 +434,12 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
         std::lock_guard<std::mutex> la_lock(la_mu);
         const uint8_t* raw = static_cast<const uint8_t*>(torch_rng_state);
         const bool continuous = la_enabled && la.matches(raw);
+        // the ring is only refilled when a plan commits: a plan longer than the ring has to run inline
+        int64_t total_draws = 0;
+        for (int a = 0; a < A; ++a) total_draws += (num_hard[a] > 1 ? num_hard[a] - 1 : 0) + (num_easy[a] > 1 ? num_easy[a] - 1 : 0);
+        const bool fits = total_draws / kN + 4 < static_cast<int64_t>(Lookahead::kRing) - 4;
         if (la.active()) {
-            if (continuous) {
+            if (continuous && fits) {
                 m.la = &la;
                 m.blk = la.position();
                 m.s = la.block(m.blk);
@@ -345,27 +450,55 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             }
         }
         if (!m.la) ++g_la_stats[1];
-        Sparse sp;
+        int n_local = 0;
         for (int a = 0; a < A; ++a) {
             const int64_t kh = keep_hard[a], ke = n_view - kh;
             if (kh < 0 || ke < 0 || kh > num_hard[a] || ke > num_easy[a] || num_hard[a] >= 214748364 ||
                 num_easy[a] >= 214748364)
                 return dcl::fail(DCL_ERR_ARG, "anchor %d: keep (%lld,%lld) exceeds counts (%lld,%lld)", a,
                                  (long long)kh, (long long)ke, (long long)num_hard[a], (long long)num_easy[a]);
-            if (image[a] >= lo && image[a] < hi) {
-                randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
-                randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
-            } else {
-                // another rank's anchor: randperm(n) consumes n - 1 draws (none for n <= 1)
+            n_local += image[a] >= lo && image[a] < hi;
+        }
+        const int threads = m.la ? std::min(n_local, host_threads(static_cast<int64_t>(n_local) * n_view)) : 1;
+        if (threads > 1) {
+            // Stream mode: randperm(n) consumes n - 1 draws whatever its outcome, so every anchor's position in the
+            // stream is known up front.  One cheap pass records the generator at the start of each local anchor
+            // (and leaves `m` where the whole plan ends); the permutations themselves then run in parallel.
+            std::vector<Mt> at(static_cast<size_t>(n_local));
+            std::vector<int> which(static_cast<size_t>(n_local));
+            int li = 0;
+            for (int a = 0; a < A; ++a) {
+                if (image[a] >= lo && image[a] < hi) { at[li] = m; which[li] = a; ++li; }
                 if (num_hard[a] > 1) skip(m, num_hard[a] - 1);
                 if (num_easy[a] > 1) skip(m, num_easy[a] - 1);
+            }
+            pool().run(n_local, threads, [&](int i) {
+                thread_local Sparse sp;
+                Mt mm = at[i];
+                const int a = which[i];
+                const int64_t kh = keep_hard[a];
+                randperm_prefix(mm, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
+                randperm_prefix(mm, num_easy[a], n_view - kh, ranks + static_cast<size_t>(a) * n_view + kh, sp);
+            });
+        } else {
+            Sparse sp;
+            for (int a = 0; a < A; ++a) {
+                const int64_t kh = keep_hard[a], ke = n_view - kh;
+                if (image[a] >= lo && image[a] < hi) {
+                    randperm_prefix(m, num_hard[a], kh, ranks + static_cast<size_t>(a) * n_view, sp);
+                    randperm_prefix(m, num_easy[a], ke, ranks + static_cast<size_t>(a) * n_view + kh, sp);
+                } else {
+                    // another rank's anchor: randperm(n) consumes n - 1 draws (none for n <= 1)
+                    if (num_hard[a] > 1) skip(m, num_hard[a] - 1);
+                    if (num_easy[a] > 1) skip(m, num_easy[a] - 1);
+                }
             }
         }
         store_state(torch_rng_state, m);
         if (m.la) {
             la.commit(m.blk, raw);
         } else {
-            if (continuous) {
+            if (continuous && fits) {
                 uint32_t words[kN];
                 for (int i = 0; i < kN; ++i) words[i] = m.s[i];
                 la.restart(words);                 // generator untouched since the last plan: stream from here on
@@ -397,10 +530,10 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
         for (int a = 0; a < A; ++a)
             if (image[a] >= rlo && image[a] < rhi) order[start[cls[a]]++] = a;
         int32_t* yb = y_all + static_cast<size_t>(r) * n_pad;
-        int row = 0;
-        for (int o = 0; o < cnt; ++o) {
+        auto fill_anchor = [&](int o) {
             const int a = order[o];
             const int64_t* rk = ranks + static_cast<size_t>(a) * n_view;
+            int row = o * n_view;
             for (int v = 0; v < n_view; ++v, ++row) {
                 yb[row] = static_cast<int32_t>(cls[a]);
                 if (r == rank) {
@@ -412,8 +545,11 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
                     anchor[row] = a;
                 }
             }
-        }
-        for (; row < n_pad; ++row) {
+        };
+        const int fill_threads = (r == rank) ? std::min(cnt, host_threads(static_cast<int64_t>(cnt) * n_view)) : 1;
+        if (fill_threads > 1) pool().run(cnt, fill_threads, fill_anchor);
+        else for (int o = 0; o < cnt; ++o) fill_anchor(o);
+        for (int row = cnt * n_view; row < n_pad; ++row) {
             yb[row] = -1;
             if (r == rank) {
                 req[row * 4 + 0] = req[row * 4 + 1] = req[row * 4 + 2] = req[row * 4 + 3] = -1;

@@ -1,6 +1,7 @@
 """world_size-2 gloo test (CPU) of the sharded sampler's host logic: every rank replays the same
 RNG stream over the all-gathered histograms and keeps its own anchors; the union must be exactly
 the single-process reference sample of the concatenated batch."""
+import ctypes
 import os
 import socket
 
@@ -126,3 +127,36 @@ def test_c_shard_plan_equals_numpy_shard_plan(world, B, h, w, K, mv, ms):
         ys.append(y_all.copy())
     for y in ys[1:]:
         assert np.array_equal(y, ys[0])
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world):
+    """Plans that follow each other without any other use of the generator run from the look-ahead stream, their
+    permutations replayed in parallel (anchor positions in the stream are known up front); every one of them must
+    still equal the numpy / torch.randperm plan, including the generator state it leaves behind."""
+    from doubly_contrastive_semseg_b200 import _lib
+    from doubly_contrastive_semseg_b200.loss import shard_plan, shard_plan_c
+    B, h, w, K, mv, ms = 8, 96, 128, 9, 40, 4096
+    lab, pred = _inputs(B, h, w, K, seed=21)
+    counts_all = _counts(lab, pred).reshape(B, 256, 2)
+    bl = B // world
+    rank = world - 1
+    steps = 6
+    torch.manual_seed(77)
+    refs = []
+    for _ in range(steps):
+        refs.append(shard_plan(counts_all, rank, world, bl, 255, ms, mv))
+    end_ref = torch.get_rng_state().clone()
+    stats0 = (ctypes.c_longlong * 4)()
+    _lib.load().dcl_host_lookahead_stats(stats0)
+    torch.manual_seed(77)
+    for ref in refs:
+        got, _ = shard_plan_c(counts_all, rank, world, bl, 255, ms, mv)
+        mine = (ref.plan.image // bl) == rank
+        assert np.array_equal(got.plan.ranks[mine], ref.plan.ranks[mine])
+        assert np.array_equal(got.layout.req, ref.layout.req)
+    assert torch.equal(torch.get_rng_state(), end_ref)
+    stats1 = (ctypes.c_longlong * 4)()
+    _lib.load().dcl_host_lookahead_stats(stats1)
+    if os.environ.get("DCL_HOST_LOOKAHEAD", "1") != "0":
+        assert stats1[0] - stats0[0] >= steps - 2          # all but the first plans after the seed came from the stream
