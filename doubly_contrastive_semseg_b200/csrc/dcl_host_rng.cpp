@@ -339,11 +339,10 @@ private:
 // threads for `draws` sampled positions: waking the helpers only pays from a few ten thousand draws on (measured on
 // the 16-core B200 host: 8192 draws 126 us alone, 148 us on two threads; 65536 draws 660 us alone, 215 us on eight)
 int host_threads(int64_t draws) {
-    static const int cap = [] {
-        if (const char* e = std::getenv("DCL_HOST_THREADS")) return std::max(1, std::atoi(e));
-        const unsigned hc = std::thread::hardware_concurrency();
-        return static_cast<int>(std::min(8u, std::max(1u, hc / 2)));
-    }();
+    // DCL_HOST_THREADS=n: exactly n threads whatever the size (tests, experiments)
+    static const int forced = [] { const char* e = std::getenv("DCL_HOST_THREADS"); return e ? std::max(1, std::atoi(e)) : 0; }();
+    if (forced) return forced;
+    static const int cap = static_cast<int>(std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, draws / 8192)));
 }
 Pool& pool() {

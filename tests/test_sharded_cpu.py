@@ -129,11 +129,7 @@ def test_c_shard_plan_equals_numpy_shard_plan(world, B, h, w, K, mv, ms):
         assert np.array_equal(y, ys[0])
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world):
-    """Plans that follow each other without any other use of the generator run from the look-ahead stream, their
-    permutations replayed in parallel (anchor positions in the stream are known up front); every one of them must
-    still equal the numpy / torch.randperm plan, including the generator state it leaves behind."""
+def _consecutive_plans_check(world):
     from doubly_contrastive_semseg_b200 import _lib
     from doubly_contrastive_semseg_b200.loss import shard_plan, shard_plan_c
     B, h, w, K, mv, ms = 8, 96, 128, 9, 40, 4096
@@ -143,9 +139,7 @@ def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world):
     rank = world - 1
     steps = 6
     torch.manual_seed(77)
-    refs = []
-    for _ in range(steps):
-        refs.append(shard_plan(counts_all, rank, world, bl, 255, ms, mv))
+    refs = [shard_plan(counts_all, rank, world, bl, 255, ms, mv) for _ in range(steps)]
     end_ref = torch.get_rng_state().clone()
     stats0 = (ctypes.c_longlong * 4)()
     _lib.load().dcl_host_lookahead_stats(stats0)
@@ -155,8 +149,29 @@ def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world):
         mine = (ref.plan.image // bl) == rank
         assert np.array_equal(got.plan.ranks[mine], ref.plan.ranks[mine])
         assert np.array_equal(got.layout.req, ref.layout.req)
+        assert np.array_equal(got.layout.ref_row, ref.layout.ref_row)
     assert torch.equal(torch.get_rng_state(), end_ref)
     stats1 = (ctypes.c_longlong * 4)()
     _lib.load().dcl_host_lookahead_stats(stats1)
     if os.environ.get("DCL_HOST_LOOKAHEAD", "1") != "0":
         assert stats1[0] - stats0[0] >= steps - 2          # all but the first plans after the seed came from the stream
+
+
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("threads", ["", "3"])
+def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world, threads):
+    """Plans that follow each other without any other use of the generator run from the look-ahead stream, their
+    permutations replayed in parallel on large problems (anchor positions in the stream are known up front; here
+    forced with DCL_HOST_THREADS, which the library reads once per process, hence the child process); every plan must
+    still equal the numpy / torch.randperm plan, including the generator state it leaves behind."""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop("DCL_HOST_THREADS", None)
+    if threads:
+        env["DCL_HOST_THREADS"] = threads
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path[:0] = [%r, %r]; from test_sharded_cpu import _consecutive_plans_check as c; c(%d)"
+            % (root, os.path.join(root, "tests"), world))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
