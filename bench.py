@@ -102,6 +102,19 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(workload, world):
+    """DRAM bytes per step of the similarity kernels (sweep P + backward) from the committed `ncu --set full`
+    capture of this workload on one GPU (profiles/r01o_ncu_dram_traffic.json); None where none was taken."""
+    path = os.path.join(ROOT, "profiles", "r01o_ncu_dram_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload, {}).get("similarity_step")
+    except (OSError, ValueError):
+        return None
+
+
 def pick_workload(args, world):
     from doubly_contrastive_semseg_b200.synthetic import WORKLOADS
     name = args.workload
@@ -312,7 +325,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_traffic(wl.name, world),
                          "kernel": "similarity sweeps + fused backward (dcl_contrast_fwd + dcl_contrast_bwd)",
                          "algorithmic": "6*N_local*N*D flops per step", "ms_per_step": sim_ms / args.steps,
                          "timed_calls": sim_launches, "peak_source": peaks["source"]},

@@ -36,7 +36,31 @@ SIGNATURES = {
     "dcl_unpack_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
     "dcl_gap_fwd": (_i, [_vp, _i, _i, _vp, _vp]),
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "dcl_pixel_fwd": (_i, [_vp, _vp]),
+    "dcl_pixel_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dcl_pixel_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
 }
+
+
+class PixelStep(ctypes.Structure):
+    """dcl_pixel_step_t of include/dcl_b200.h, field for field."""
+    _fields_ = [
+        ("labels", _vp), ("predict", _vp), ("feats", _vp),
+        ("B", _i), ("H", _i), ("W", _i), ("h", _i), ("w", _i), ("C_cls", _i), ("ignore_label", _i),
+        ("max_samples", _i), ("max_views", _i),
+        ("temperature", _f), ("base_temperature", _f),
+        ("torch_rng_state", _vp), ("state_bytes", _sz),
+        ("code", _vp), ("chunk_hist", _vp), ("counts_dev", _vp),
+        ("counts_host", _vp), ("stage_host", _vp), ("cap", _i),
+        ("info", _vp), ("image", _vp), ("cls", _vp), ("num_hard", _vp), ("num_easy", _vp), ("keep_hard", _vp),
+        ("ranks", _vp), ("ref_row", _vp), ("anchor", _vp),
+        ("stage_dev", _vp), ("pix", _vp), ("tiles", _vp), ("sqnorm", _vp), ("colA", _vp), ("colB", _vp),
+        ("rowloss", _vp), ("loss_sum", _vp),
+        ("workspace", _vp), ("workspace_bytes", _sz),
+        ("zero_fill", _vp), ("zero_fill_bytes", _sz),
+        ("ev_begin", _vp), ("ev_end", _vp),
+        ("begun", _i),
+    ]
 
 
 def contrast_launches(mode, backward):

@@ -308,6 +308,7 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 # ----------------------------------------------------------------------------------------------
 # lean single-GPU step: one device allocation per direction, cached sizes, raw pointers into it
 # ----------------------------------------------------------------------------------------------
+_FUSED_STEP = os.environ.get("DCL_FUSED_STEP", "1") != "0"     # 0: the stage-by-stage Python path (same results)
 _WS_BYTES = {}
 _WS_CACHE = {}
 _LAUNCHES_CACHE = {}
@@ -400,6 +401,143 @@ class _PixelContrastFn(torch.autograd.Function):
         return dfeats, None, None, None, None, None, None
 
 
+_WS_CAP_BYTES = {}
+
+
+def _ws_cap_bytes(cap):
+    """Workspace that serves every row count up to `cap` (the fused step learns its row count only after the plan)."""
+    v = _WS_CAP_BYTES.get(cap)
+    if v is None:
+        v = _WS_CAP_BYTES[cap] = max(_ws_bytes(n, n) for n in range(1, cap // _TILE + 1))
+    return v
+
+
+class _PixelStepFn(torch.autograd.Function):
+    """The pixel term through dcl_pixel_fwd / dcl_pixel_bwd: sampling, gather and the N x N forward are issued by
+    one C call (same stages, same results as _sample_fast + _PixelContrastFn; the interpreter no longer walks from
+    one entry point to the next, which was most of a cfg2 step's host time)."""
+
+    @staticmethod
+    def forward(ctx, feats, labels, predict, crit):
+        B, C, h, w = feats.shape
+        dev = feats.device
+        hw = h * w
+        n_chunks = (hw + _CHUNK - 1) // _CHUNK
+        hb = crit._host_buffers(B, dev)
+        cap, an, rows, info = hb["cap"], hb["anchors"], hb["rows"], hb["info"]
+        # per-step device state, one allocation: code | chunk prefixes | counts | requests+labels | pix | tiles |
+        # sqnorm | colA | colB | rowloss
+        keep, (p_code, p_chunk, p_cnt, p_stage, p_pix, p_tiles, p_sq, p_cA, p_cB, p_rl) = _carve(
+            dev, (B * hw * 2, B * n_chunks * _BINS * 4, B * _BINS * 4, cap * 20, cap * 4, cap * _DIM * 2, cap * 4,
+                  cap * 16, cap * 16, cap * 4))
+        want_grad = ctx.needs_input_grad[0]
+        dzero = torch.empty_like(feats) if want_grad else None     # cleared on the stream while the host plans
+        lib = _lib.load()
+        strm = _stream()
+        H, W, C_cls = labels.shape[1], labels.shape[2], predict.shape[1]
+        zp = dzero.data_ptr() if dzero is not None else None
+        zb = dzero.numel() * 4 if dzero is not None else 0
+        # first half at once (classify, count table D2H, zero-fill): everything below overlaps it
+        rc = lib.dcl_pixel_begin(labels.data_ptr(), predict.data_ptr(), B, H, W, h, w, C_cls, p_code, p_chunk, p_cnt,
+                                 hb["counts"].data_ptr(), zp, zb, strm)
+        if rc != 0:
+            raise _lib.DclError("dcl_pixel_begin failed with status %d: %s"
+                                % (rc, lib.dcl_last_error().decode("utf-8", "replace")))
+        loss2 = torch.empty(2, dtype=torch.float32, device=dev)
+        nbytes = _ws_cap_bytes(cap)
+        ws = _workspace(dev, nbytes)
+        st = torch.get_rng_state()
+        sbuf = st.numpy()
+        step = hb.get("step")
+        if step is None:
+            step = hb["step"] = _lib.PixelStep()
+            step.counts_host = hb["counts"].data_ptr()
+            step.stage_host = hb["stage"].data_ptr()
+            step.cap = cap
+            step.info = info.ctypes.data
+            step.image, step.cls, step.num_hard, step.num_easy, step.keep_hard = (an[i].ctypes.data for i in range(5))
+            step.ranks = hb["ranks"].ctypes.data
+            step.ref_row, step.anchor = rows[0].ctypes.data, rows[1].ctypes.data
+            step.begun = 1
+        step.labels, step.predict, step.feats = labels.data_ptr(), predict.data_ptr(), feats.data_ptr()
+        step.B, step.H, step.W, step.h, step.w, step.C_cls = B, H, W, h, w, C_cls
+        step.ignore_label, step.max_samples, step.max_views = int(crit.ignore_label), int(crit.max_samples), int(crit.max_views)
+        step.temperature, step.base_temperature = float(crit.temperature), float(crit.base_temperature)
+        step.torch_rng_state, step.state_bytes = sbuf.ctypes.data, sbuf.nbytes
+        step.code, step.chunk_hist, step.counts_dev = p_code, p_chunk, p_cnt
+        step.stage_dev, step.pix, step.tiles, step.sqnorm = p_stage, p_pix, p_tiles, p_sq
+        step.colA, step.colB, step.rowloss, step.loss_sum = p_cA, p_cB, p_rl, loss2.data_ptr()
+        step.workspace, step.workspace_bytes = ws.data_ptr(), nbytes
+        step.zero_fill, step.zero_fill_bytes = zp, zb
+        ev = None
+        if _PROFILE_HOOK is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            ev[1].record()                                # materialise the handles; the library re-records them
+            step.ev_begin, step.ev_end = ev[0].cuda_event, ev[1].cuda_event
+        else:
+            step.ev_begin = step.ev_end = None
+        rc = lib.dcl_pixel_fwd(ctypes.byref(step), strm)
+        if rc == 2:
+            print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
+            raise Exception
+        if rc == 3:
+            raise RuntimeError("max_samples // total_classes == 0: no views to sample "
+                               "(the reference fails in torch.cat at loss.py:345)")
+        if rc < 0 or rc > 3:
+            raise _lib.DclError("dcl_pixel_fwd failed with status %d: %s"
+                                % (rc, _lib.load().dcl_last_error().decode("utf-8", "replace")))
+        ctx.empty = rc == 1
+        ctx.shape = (B, C, h, w)
+        if rc == 1:                                        # no class qualifies: zero loss, zero gradient
+            _count(2)
+            crit.last_plan = None
+            return torch.zeros((), dtype=torch.float32, device=dev)
+        torch.set_rng_state(st)
+        if ev is not None:
+            _PROFILE_HOOK("contrast_fwd", ev[0], ev[1])
+        n_pad = int(info[3])
+        # last_plan / last_layout / last_pix are built on first access (views into the persistent host buffers and
+        # this step's device state: valid until the next forward of this module)
+        crit.__dict__["_last_step"] = (tuple(int(v) for v in info), hb, keep, p_pix.value - keep.data_ptr())
+        _count(2 + 1 + 1 + _launches(MODE_PIXEL, 0))
+        ctx.save_for_backward(keep)
+        ctx.meta = (n_pad, cap, (p_stage, p_pix, p_tiles, p_cA, p_cB), nbytes)
+        ctx.dzero = dzero
+        return loss2[1]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, C, h, w = ctx.shape
+        if ctx.empty:
+            return torch.zeros((B, C, h, w), dtype=torch.float32, device=grad_out.device), None, None, None
+        (keep,) = ctx.saved_tensors
+        n_pad, cap, (p_stage, p_pix, p_tiles, p_cA, p_cB), nbytes = ctx.meta
+        dev = keep.device
+        dF = torch.empty((n_pad, _DIM), dtype=torch.float32, device=dev)
+        ws = _workspace(dev, nbytes)
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
+            grad_out.to(torch.float32).contiguous()
+        dfeats, ctx.dzero = ctx.dzero, None
+        zero_fill = 0
+        if dfeats is None:
+            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
+            zero_fill = 1
+        ev = None
+        eb = ee = None
+        if _PROFILE_HOOK is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            ev[1].record()
+            eb, ee = ev[0].cuda_event, ev[1].cuda_event
+        _lib.call("dcl_pixel_bwd", p_tiles, ctypes.c_void_p(p_stage.value + cap * 16), p_cA, p_cB, n_pad, _p(ws), nbytes,
+                  _p(dF), p_pix, _p(g), _p(dfeats), B, h * w, zero_fill, eb, ee, _stream())
+        if ev is not None:
+            _PROFILE_HOOK("contrast_bwd", ev[0], ev[1])
+        _count(_launches(MODE_PIXEL, 1) + 1)
+        return dfeats, None, None, None
+
+
 class _ContrastRowsFn(torch.autograd.Function):
     """Row-normalised contrast of a dense [n,128] matrix (image-level term)."""
 
@@ -487,6 +625,28 @@ class PixelContrastLoss(nn.Module):
         self.last_plan: Optional[AnchorPlan] = None       # exposed for tests / diagnostics
         self.last_layout: Optional[RowLayout] = None
         self.last_pix: Optional[torch.Tensor] = None
+
+    # ---- what the last forward sampled (tests / diagnostics), built lazily after a fused step -------------
+    def _last(self, key):
+        d = self.__dict__
+        if d.get("_last_step") is not None:
+            (A, n_view, n, n_pad), hb, keep, o_pix = d["_last_step"]
+            an, rows, stage, cap = hb["anchors"], hb["rows"], hb["stage_np"], hb["cap"]
+            d["_last_plan"] = AnchorPlan(A, n_view, an[0, :A], an[1, :A], an[2, :A], an[3, :A], an[4, :A],
+                                         hb["ranks"][: A * n_view].reshape(A, n_view))
+            d["_last_layout"] = RowLayout(n, n_pad, stage[: n_pad * 4].reshape(n_pad, 4),
+                                          stage[cap * 4: cap * 4 + n_pad], rows[0, :n_pad], rows[1, :n_pad])
+            d["_last_pix"] = keep[o_pix:o_pix + n_pad * 4].view(torch.int32)
+            d["_last_step"] = None
+        return d.get("_last_" + key)
+
+    def _set_last(self, key, value):
+        self.__dict__["_last_step"] = None
+        self.__dict__["_last_" + key] = value
+
+    last_plan = property(lambda self: self._last("plan"), lambda self, v: self._set_last("plan", v))
+    last_layout = property(lambda self: self._last("layout"), lambda self, v: self._set_last("layout", v))
+    last_pix = property(lambda self: self._last("pix"), lambda self, v: self._set_last("pix", v))
 
     # ---- sampling front end ------------------------------------------------------------------
     def _host_buffers(self, B, dev):
@@ -602,6 +762,8 @@ class PixelContrastLoss(nn.Module):
         feats_c = feats.contiguous().to(torch.float32)
         labels_c = labels.contiguous().to(torch.int64)
         predict_c = predict.detach().contiguous().to(torch.float32)
+        if _verify_host_rng() and _FUSED_STEP:
+            return _PixelStepFn.apply(feats_c, labels_c, predict_c, self)
         if _verify_host_rng():
             sampled = self._sample_fast(feats_c, labels_c, predict_c,
                                         feats_c.requires_grad and torch.is_grad_enabled())

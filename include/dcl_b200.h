@@ -185,6 +185,52 @@ int dcl_unpack_rows(const float* dF, int n, const float* grad_out, float* dZ, vo
 int dcl_gap_fwd(const float* x, int R, int hw, float* pooled, void* stream);
 int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumulate, void* stream);
 
+/* ---------------------------------------------------------------- the pixel term in one call
+ * PixelContrastLoss.forward (loss.py:391-415 -> 250-389) issued from C: dcl_sample_classify -> count table to
+ * the host -> (optional zero-fill on the stream || dcl_host_plan_rows on the host) -> row requests to the device ->
+ * dcl_sample_select -> dcl_gather_tiles -> dcl_contrast_fwd.  Same results as calling the stages one by one; the
+ * only wait is for the count table.  All buffers are the caller's:
+ *   device scratch  code [B*h*w] u16, chunk_hist [B*n_chunks*512] i32, counts_dev [B*512] i32
+ *   pinned host     counts_host [B*512] i32, stage_host [5*cap] i32 (row requests [4*cap] | labels [cap])
+ *   host plan       info [4], image/cls/num_hard/num_easy/keep_hard [>= B*256], ranks [>= max_samples],
+ *                   ref_row/anchor [cap]   (as dcl_host_plan_rows)
+ *   device outputs  stage_dev [5*cap] i32 (requests | labels y at +4*cap), pix [cap], tiles [cap*256 B],
+ *                   sqnorm [cap], colA/colB [cap*4] f32, rowloss [cap], loss_sum [2]
+ *   workspace       >= dcl_contrast_workspace_bytes(n, n) for every n <= cap/128 (the row count is only known
+ *                   after the plan)
+ *   cap             multiple of 128, >= max_samples rounded up to 128
+ *   zero_fill       optional device buffer cleared on the stream while the host plans (the dense gradient)
+ *   ev_begin/ev_end optional cudaEvent_t recorded around the N x N forward (measurement)
+ * Returns 0; 1 when no class qualifies; 2 for the reference's "never touched" branch; 3 when
+ * max_samples / total_classes == 0; negative dcl_status on errors.  info = (A, n_view, n, n_pad). */
+typedef struct dcl_pixel_step {
+    const int64_t* labels; const float* predict; const float* feats;
+    int B, H, W, h, w, C_cls, ignore_label, max_samples, max_views;
+    float temperature, base_temperature;
+    void* torch_rng_state; size_t state_bytes;
+    uint16_t* code; int32_t* chunk_hist; int32_t* counts_dev;
+    int32_t* counts_host; int32_t* stage_host; int cap;
+    int32_t* info; int64_t* image; int64_t* cls; int64_t* num_hard; int64_t* num_easy; int64_t* keep_hard;
+    int64_t* ranks; int64_t* ref_row; int64_t* anchor;
+    int32_t* stage_dev; int32_t* pix; void* tiles; float* sqnorm; float* colA; float* colB; float* rowloss;
+    float* loss_sum;
+    void* workspace; size_t workspace_bytes;
+    void* zero_fill; size_t zero_fill_bytes;
+    void* ev_begin; void* ev_end;
+    int begun;          /* != 0: dcl_pixel_begin was already issued for this step on the same stream and thread */
+} dcl_pixel_step_t;
+int dcl_pixel_fwd(const dcl_pixel_step_t* step, void* stream);
+/* Optional first half of dcl_pixel_fwd (classify, count table D2H, zero-fill): issue it as soon as the inputs are
+ * known, prepare the rest of the descriptor while the GPU classifies, then call dcl_pixel_fwd with begun = 1. */
+int dcl_pixel_begin(const int64_t* labels, const float* predict, int B, int H, int W, int h, int w, int C_cls,
+                    uint16_t* code, int32_t* chunk_hist, int32_t* counts_dev, int32_t* counts_host,
+                    void* zero_fill, size_t zero_fill_bytes, void* stream);
+/* Backward of the same: dcl_contrast_bwd (all rows local) -> dcl_scatter_grad. */
+int dcl_pixel_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB, int n_pad,
+                  void* workspace, size_t workspace_bytes, float* dF, const int32_t* pix,
+                  const float* grad_out, float* dfeats, int B, int hw, int zero_fill, void* ev_begin,
+                  void* ev_end, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
