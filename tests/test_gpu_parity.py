@@ -160,6 +160,47 @@ def test_sampler_bit_exact_vs_oracle(dcl, B, H, W, h, w, K, mv, ms):
     assert np.array_equal(crit.last_plan.num_easy, np.array(plan.num_easy))
 
 
+@pytest.mark.parametrize("B,H,W,h,w,K,mv,ms", [
+    (3, 100, 180, 25, 45, 4, 7, 1024),
+    (2, 512, 1024, 128, 256, 19, 32, 1024),
+    (5, 37, 53, 19, 31, 6, 4, 50),
+    (4, 256, 512, 64, 128, 16, 32, 2048),
+])
+def test_fused_step_equals_stage_by_stage(dcl, B, H, W, h, w, K, mv, ms):
+    """PixelContrastLoss through dcl_pixel_begin/fwd/bwd (one C call per direction) == the same module walking the
+    stages from Python: identical sample, bit-identical loss and gradient, identical generator state afterwards."""
+    from doubly_contrastive_semseg_b200 import loss as L
+    g = torch.Generator().manual_seed(H * 7 + W)
+    bh = max(1, H // 6)
+    coarse = torch.randint(0, K, (B, (H + bh - 1) // bh, (W + bh - 1) // bh), generator=g)
+    labels = coarse.repeat_interleave(bh, 1).repeat_interleave(bh, 2)[:, :H, :W].contiguous().long().cuda()
+    predict = torch.randn(B, 19, h, w, generator=g).cuda()
+    feats = torch.randn(B, 128, h, w, generator=g).cuda()
+    out = {}
+    saved = L._FUSED_STEP
+    try:
+        for fused in (True, False):
+            L._FUSED_STEP = fused
+            crit = dcl.PixelContrastLoss(device="cuda")
+            crit.max_samples, crit.max_views = ms, mv
+            x = feats.clone().requires_grad_(True)
+            torch.manual_seed(5)
+            res = []
+            for _ in range(3):                       # consecutive steps: the second and third use the look-ahead stream
+                x.grad = None
+                loss = crit(x, labels=labels, predict=predict)
+                (loss * 1.5).backward()
+                res.append((loss.detach().clone(), x.grad.clone(), crit.last_pix.clone(), crit.last_plan.ranks.copy(),
+                            crit.last_layout.n))
+            out[fused] = (res, torch.get_rng_state().clone())
+    finally:
+        L._FUSED_STEP = saved
+    assert torch.equal(out[True][1], out[False][1])
+    for a, b in zip(out[True][0], out[False][0]):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        assert np.array_equal(a[3], b[3]) and a[4] == b[4]
+
+
 # ------------------------------------------------------------------ whole modules vs golden
 @pytest.mark.parametrize("case", _cases("pixel"))
 def test_pixel_module_vs_reference_golden(dcl, case):
