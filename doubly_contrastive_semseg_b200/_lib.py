@@ -36,6 +36,8 @@ SIGNATURES = {
     "dcl_unpack_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
     "dcl_gap_fwd": (_i, [_vp, _i, _i, _vp, _vp]),
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "dcl_shard_pack": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "dcl_shard_unpack": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "dcl_pixel_fwd": (_i, [_vp, _vp]),
     "dcl_pixel_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dcl_pixel_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

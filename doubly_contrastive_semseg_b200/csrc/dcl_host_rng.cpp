@@ -516,6 +516,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
     int n_pad = (n_max + 127) / 128 * 128;
     if (n_pad < 128) n_pad = 128;
     info[2] = per_rank[rank]; info[3] = n_pad; info[4] = n_global;
+    if (!y_all) y_all = req + static_cast<size_t>(4) * n_pad;      // compact form: labels right behind the requests
     // rows of every rank block: anchors of that rank stably sorted by class (counting sort), views contiguous;
     // labels for all blocks (y_all), requests / bookkeeping for the local block only
     std::vector<int> start(257), order(A);

@@ -369,6 +369,58 @@ extern "C" int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows,
     return 0;
 }
 
+// ------------------------------------------------------------------------------- sharded exchange
+// send = [colA of the local rows | colB of the local rows | (local loss sum, 0, 0, 0)] as float4
+__global__ void __launch_bounds__(256)
+k_shard_pack(const float4* __restrict__ colA, const float4* __restrict__ colB, const float* __restrict__ loss_sum,
+             int row0, int n_pad, float4* __restrict__ send) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) {
+        send[i] = colA[row0 + i];
+        send[n_pad + i] = colB[row0 + i];
+    }
+    if (i == 0) send[2 * n_pad] = make_float4(loss_sum[0], 0.f, 0.f, 0.f);
+}
+// recv = `world` such messages; colA / colB of every rank's rows land in place, loss = sum of the partials / n_global
+__global__ void __launch_bounds__(256)
+k_shard_unpack(const float4* __restrict__ recv, int world, int n_pad, float4* __restrict__ colA,
+               float4* __restrict__ colB, int n_global, float* __restrict__ loss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int msg = 2 * n_pad + 1;
+    if (i < world * n_pad) {
+        const int r = i / n_pad, k = i - r * n_pad;
+        colA[i] = recv[static_cast<size_t>(r) * msg + k];
+        colB[i] = recv[static_cast<size_t>(r) * msg + n_pad + k];
+    }
+    if (i == 0) {
+        float sum = 0.f;
+        for (int r = 0; r < world; ++r) sum += recv[static_cast<size_t>(r) * msg + 2 * n_pad].x;      // rank order
+        loss[0] = sum / static_cast<float>(n_global);
+    }
+}
+
+extern "C" int dcl_shard_pack(const float* colA, const float* colB, const float* loss_sum, int rank, int n_pad,
+                              float* send, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!colA || !colB || !loss_sum || !send || n_pad <= 0 || rank < 0) return fail(DCL_ERR_ARG, "bad argument");
+    k_shard_pack<<<(n_pad + 255) / 256, 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(colA), reinterpret_cast<const float4*>(colB), loss_sum, rank * n_pad, n_pad,
+        reinterpret_cast<float4*>(send));
+    DCL_LAUNCH_CHECK("k_shard_pack");
+    return 0;
+}
+
+extern "C" int dcl_shard_unpack(const float* recv, int world, int n_pad, float* colA, float* colB, int n_global,
+                                float* loss, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!recv || !colA || !colB || !loss || n_pad <= 0 || world <= 0 || n_global <= 0) return fail(DCL_ERR_ARG, "bad argument");
+    k_shard_unpack<<<(world * n_pad + 255) / 256, 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(recv), world, n_pad, reinterpret_cast<float4*>(colA),
+        reinterpret_cast<float4*>(colB), n_global, loss);
+    DCL_LAUNCH_CHECK("k_shard_unpack");
+    return 0;
+}
+
 extern "C" int dcl_unpack_rows(const float* dF, int n, const float* grad_out, float* dZ, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!dF || !grad_out || !dZ || n <= 0) return fail(DCL_ERR_ARG, "bad argument");

@@ -881,8 +881,9 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
     info = np.zeros(6, dtype=np.int32)
     an = np.empty((5, B * 256), dtype=np.int64)
     ranks = np.empty(max(int(max_samples), 1), dtype=np.int64)
+    compact = stage_req is not None and stage_y is None     # labels right behind the requests (one H2D copy)
     req = stage_req if stage_req is not None else np.empty(cap * 4, dtype=np.int32)
-    y_all = stage_y if stage_y is not None else np.empty(world * cap, dtype=np.int32)
+    y_all = None if compact else (stage_y if stage_y is not None else np.empty(world * cap, dtype=np.int32))
     rows = np.empty((2, cap), dtype=np.int64)
     st = torch.get_rng_state()
     sbuf = st.numpy()
@@ -891,7 +892,7 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
                                         int(max_samples), int(max_views), sbuf.ctypes.data, sbuf.nbytes,
                                         info.ctypes.data, an[0].ctypes.data, an[1].ctypes.data, an[2].ctypes.data,
                                         an[3].ctypes.data, an[4].ctypes.data, ranks.ctypes.data, req.ctypes.data,
-                                        y_all.ctypes.data, rows[0].ctypes.data, rows[1].ctypes.data)
+                                        None if compact else y_all.ctypes.data, rows[0].ctypes.data, rows[1].ctypes.data)
     if rc == 1:
         return None
     if rc == 2:
@@ -902,6 +903,8 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
                             % (rc, lib.dcl_last_error().decode("utf-8", "replace")))
     torch.set_rng_state(st)
     A, n_view, n, n_pad, n_global = (int(v) for v in info[:5])
+    if compact:
+        y_all = req[4 * n_pad: (4 + world) * n_pad]
     plan = AnchorPlan(A, n_view, an[0, :A], an[1, :A], an[2, :A], an[3, :A], an[4, :A],
                       ranks[: A * n_view].reshape(A, n_view))
     lay = RowLayout(n, n_pad, req[: n_pad * 4].reshape(n_pad, 4), y_all[rank * n_pad:(rank + 1) * n_pad],
@@ -941,17 +944,14 @@ class _ShardedPixelContrastFn(torch.autograd.Function):
         # backward needs every row's constants (the dS_ki terms, 32 B per row) and the loss is the sum over ranks:
         # one all-gather of [colA | colB | local loss sum] per rank, unpacked with two strided copies
         kf = keep.view(torch.float32)
-        o_cA, o_cB, o_loss, o_send = ((p.value - base) // 4 for p in (p_cA, p_cB, p_loss, p_send))
-        colA, colB = kf[o_cA:o_cA + N * 4], kf[o_cB:o_cB + N * 4]
+        o_send = (p_send.value - base) // 4
         send = kf[o_send:o_send + 2 * m4 + 4]
-        send[:m4].copy_(colA[rank * m4:(rank + 1) * m4])
-        send[m4:2 * m4].copy_(colB[rank * m4:(rank + 1) * m4])
-        send[2 * m4:2 * m4 + 1].copy_(kf[o_loss:o_loss + 1])
+        _lib.call("dcl_shard_pack", p_cA, p_cB, p_loss, rank, n_pad, p_send, st)
         recv = torch.empty((world, 2 * m4 + 4), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(recv, send, group=group)
-        colA.view(world, m4).copy_(recv[:, :m4])
-        colB.view(world, m4).copy_(recv[:, m4:2 * m4])
-        loss = recv[:, 2 * m4].sum() / n_global
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("dcl_shard_unpack", _p(recv), world, n_pad, p_cA, p_cB, int(n_global), _p(loss), st)
+        _count(2)
         ctx.save_for_backward(tiles, y_all, keep, pix)
         ctx.meta = (nJ, rb0, nI, n_pad, (B, C, h, w), (p_cA, p_cB))
         ctx.dzero = dzero
@@ -1034,7 +1034,7 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
                 stg = self._shard_stage = (key, t, t.numpy())
             _, stage_t, stage_np = stg
             out = shard_plan_c(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
-                               int(self.max_views), stage_np[: cap * 4], stage_np[cap * 4:])
+                               int(self.max_views), stage_np, None)
             sp = None if out is None else out[0]
         else:
             sp = shard_plan(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
@@ -1048,9 +1048,9 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
         lay = sp.layout
         self.last_layout, self.last_n_global = lay, sp.n_global
         if stage_t is not None:
-            # two small H2D copies: the local requests and every rank's labels
-            req_dev = stage_t[: lay.n_pad * 4].to(feats.device, non_blocking=True)
-            y_all = stage_t[cap * 4: cap * 4 + world * lay.n_pad].to(feats.device, non_blocking=True)
+            # one small H2D copy: the local requests with every rank's labels right behind them
+            packed = stage_t[: (4 + world) * lay.n_pad].to(feats.device, non_blocking=True)
+            req_dev, y_all = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
         else:
             host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
             packed = host.to(feats.device, non_blocking=True)

@@ -129,7 +129,9 @@ int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label, int max_s
  * replays the same generator stream but only draws the permutations of its own anchors.
  * info [6]: A, n_view, n (valid LOCAL rows), n_pad (common block size), n_global, -.  y_all
  * [world*n_pad] receives the labels of every rank's row block; req / ref_row / anchor [n_pad] describe
- * the local block (image index relative to the rank's first image). */
+ * the local block (image index relative to the rank's first image).  y_all == NULL selects the compact
+ * form: the labels are written right behind the requests, at req + 4*n_pad (req must then hold
+ * (4 + world) * n_cap ints), so one host-to-device copy moves both. */
 int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int rank, int ignore_label,
                                int max_samples, int max_views, void* torch_rng_state, size_t state_bytes,
                                int32_t* info, int64_t* image, int64_t* cls, int64_t* num_hard,
@@ -177,6 +179,16 @@ int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const floa
                      float* dfeats, int B, int hw, int zero_fill, void* stream);
 /* dZ [n,128] = dF[:n] * (*grad_out)  (image-level term). */
 int dcl_unpack_rows(const float* dF, int n, const float* grad_out, float* dZ, void* stream);
+
+/* ---------------------------------------------------------------- sharded exchange (one process per GPU)
+ * The one message a rank contributes before the backward: send [(2*n_pad + 1) float4] = colA of its rows | colB of
+ * its rows | (its loss sum, 0, 0, 0).  After an all-gather of these messages, dcl_shard_unpack puts every rank's
+ * constants in place (colA / colB [world*n_pad] float4) and writes loss[0] = sum of the partials (rank order) /
+ * n_global.  New design: the reference has no multi-GPU path. */
+int dcl_shard_pack(const float* colA, const float* colB, const float* loss_sum, int rank, int n_pad,
+                   float* send, void* stream);
+int dcl_shard_unpack(const float* recv, int world, int n_pad, float* colA, float* colB, int n_global,
+                     float* loss, void* stream);
 
 /* ---------------------------------------------------------------- global average pool
  * nn.AdaptiveAvgPool2d((1,1)) forward/backward (loss.py:104, :115): x [R,hw] rows = (image,

@@ -125,6 +125,14 @@ def test_c_shard_plan_equals_numpy_shard_plan(world, B, h, w, K, mv, ms):
         assert got.layout.n == ref.layout.n
         assert np.array_equal(y_all[rank * ref.n_pad:(rank + 1) * ref.n_pad], ref.layout.y)
         ys.append(y_all.copy())
+        # compact form (the product's path): labels right behind the requests in one caller-owned buffer
+        cap = max(128, (ms + 127) // 128 * 128) + 128
+        stage = np.full((4 + world) * cap, -7, dtype=np.int32)
+        torch.manual_seed(123)
+        got2, y2 = shard_plan_c(counts_all, rank, world, bl, 255, ms, mv, stage, None)
+        assert torch.equal(torch.get_rng_state(), end_ref)
+        assert np.array_equal(got2.layout.req, ref.layout.req) and np.array_equal(y2, y_all)
+        assert np.shares_memory(y2, stage) and np.array_equal(stage[4 * ref.n_pad:(4 + world) * ref.n_pad], y_all)
     for y in ys[1:]:
         assert np.array_equal(y, ys[0])
 

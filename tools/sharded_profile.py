@@ -14,8 +14,9 @@ d = make_inputs(wl, seed=1, device=dev)
 bl = wl.B // world; sl = slice(rank * bl, (rank + 1) * bl)
 feats = d["feats"][sl].contiguous().requires_grad_(True); labels = d["labels"][sl].contiguous(); predict = d["predict"][sl].contiguous()
 crit = pkg.ShardedPixelContrastLoss(device=dev); crit.max_samples, crit.max_views = wl.max_samples, wl.max_views
+torch.manual_seed(1234)          # once: every rank consumes the same stream, the look-ahead stays valid
 def step(s):
-    torch.manual_seed(s); feats.grad = None
+    feats.grad = None
     loss = crit(feats, labels=labels, predict=predict); loss.backward()
 for s in range(5): step(s)
 torch.cuda.synchronize(); dist.barrier()
