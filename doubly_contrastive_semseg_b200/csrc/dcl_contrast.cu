@@ -406,7 +406,9 @@ struct SmemSweep {
     static constexpr int kInfo = kSlots * kTileBytes;     // int4[kMaxBlocks]
     static constexpr int kLab = kInfo + 16 * kMaxBlocks;  // 8 epilogue warps x 128 labels of the current masked column block
     static constexpr int kBar = kLab + 8 * 512;           // full[6] empty[6] tfull[3] tempty[3] afull[2] turn[2] aseen
-    static constexpr int kTmem = kBar + 256;
+    static constexpr int kShiftA = kBar + 256;            // sweep P: -c_i of the two row blocks as a K = 16 operand (2 x 4 KB)
+    static constexpr int kShiftB = kShiftA + 2 * 4096;    // sweep P: the matching ones rows (256 B, every row group aliases it)
+    static constexpr int kTmem = kShiftB + 256;
     static constexpr int kBytes = kTmem + 16 + 1024;      // + alignment slack
 };
 struct SmemBwd {
@@ -503,10 +505,11 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
     return d;
 }
 // SWEEP_P fast-tile body for 32 columns (16 packed pairs), x = s - c_i: row max, sum x, sum x^2
+template <bool kShiftedByMma = false>
 __device__ __forceinline__ void psweep_chunk(const uint32_t (&v)[32], f32x2 negc, f32x2 (&x1)[4], f32x2 (&x2)[4], float (&mx)[4]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const f32x2 x = fadd2(pack2u(v[2 * j], v[2 * j + 1]), negc);
+        const f32x2 x = kShiftedByMma ? pack2u(v[2 * j], v[2 * j + 1]) : fadd2(pack2u(v[2 * j], v[2 * j + 1]), negc);
         float lo, hi;
         unpack2(x, lo, hi);
         mx[j & 3] = fmaxf(mx[j & 3], fmaxf(lo, hi));
@@ -606,6 +609,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
         mbar_init(b_aseen, 2);                  // both issuers have observed the current row blocks
         mbar_fence_init();
     }
+    // Sweep P folds the row shift x = s - c_i into the product: a ninth K = 16 step with A' = (-c_hi, -c_mid, -c_lo, 0..)
+    // per row (c_i split into three bf16, exact to 2^-24) and B' = (1, 1, 1, 0..) per column, both K-major without
+    // swizzle in shared memory.  That takes the subtraction (one of four FMA-pipe instructions per element pair) out
+    // of the epilogue, which is what bounds the sweep, for 1/8 more tensor work.
+    const uint32_t sShiftA = base + SmemSweep::kShiftA, sShiftB = base + SmemSweep::kShiftB;
+    if (kSweep == SWEEP_P && threadIdx.x < 16) {
+        // two core matrices (k 0..7, k 8..15) of 8 rows x 16 bytes; every 8-row group aliases them (stride 0)
+        const uint32_t one = 0x3f80u;                 // bf16 1.0
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < 8) v = make_uint4(one | (one << 16), one, 0u, 0u);
+        reinterpret_cast<uint4*>(gen + SmemSweep::kShiftB)[threadIdx.x] = v;
+        fence_proxy_async_smem();
+    }
     if (!kConditional) pdl_wait();
     for (int j = threadIdx.x; j < p.nJ; j += kThreads) sInfo[j] = p.binfo[j];
     const Part& part = p.partS;
@@ -653,6 +669,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             uint64_t dJ0[8];                         // built once; a slot only shifts the start address
 #pragma unroll
             for (int k = 0; k < 8; ++k) dJ0[k] = ftile_desc_kmajor(sJ, k);
+            // shift operands (sweep P): core matrices 128 B apart along K; 8-row groups 256 B apart (A') / aliased (B')
+            const uint64_t dShiftA0 = umma_smem_desc_noswizzle(sShiftA, 128, 256);
+            const uint64_t dShiftA1 = umma_smem_desc_noswizzle(sShiftA + 4096, 128, 256);
+            const uint64_t dShiftB = umma_smem_desc_noswizzle(sShiftB, 128, 0);
             int U, J, curU = -1, it = 0, seg = 0, turn = 0;
             bool last, two = false;
             while (iter.next(U, J, last)) {
@@ -686,6 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         if (run) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) umma_ts(tAcc + b0 * 128, tmem + k * 8, dJ0[k] + soff, idesc, k > 0);
+                            if (kSweep == SWEEP_P) umma_ss(tAcc + b0 * 128, dShiftA0, dShiftB, idesc, 1u);
                         }
                         tc_commit(b_tfull + 8 * b0);
                     }
@@ -704,6 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         if (run && two) {
 #pragma unroll
                             for (int k = 2; k < 8; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, true);
+                            if (kSweep == SWEEP_P) umma_ss(tAcc + b1 * 128, dShiftA1, dShiftB, idesc, 1u);
                         }
                         tc_commit(b_tfull + 8 * b1);
                         tc_commit(b_empty + 8 * slot);
@@ -814,6 +836,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     tmem_st16(tmem + lane_off + g * 64 + qq * 16, w);
                 }
                 if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 1);     // loads arrived, stores issued
+                if (kSweep == SWEEP_P) {
+                    // -c_i as three bf16 (hi + mid + lo reproduces the fp32 value to 2^-24): row r of group g's A'
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(cload);
+                    const float r1 = cload - __bfloat162float(hi);
+                    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+                    const uint32_t nh = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) ^ 0x8000u;
+                    const uint32_t nm = static_cast<uint32_t>(__bfloat16_as_ushort(mid)) ^ 0x8000u;
+                    const uint32_t nl = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) ^ 0x8000u;
+                    uint8_t* arow = gen + SmemSweep::kShiftA + g * 4096 + (r >> 3) * 256 + (r & 7) * 16;
+                    *reinterpret_cast<uint4*>(arow) = make_uint4(nh | (nm << 16), nl, 0u, 0u);
+                    *reinterpret_cast<uint4*>(arow + 128) = make_uint4(0u, 0u, 0u, 0u);
+                    fence_proxy_async_smem();
+                }
                 tmem_st_wait();
                 if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 2);     // stores done
             }
@@ -830,7 +866,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             whi = __reduce_max_sync(0xffffffffu, yi);
             if (kSweep == SWEEP_A) {
                 // cshift loaded above
-            } else if (kSweep == SWEEP_P || kSweep == SWEEP_H) {
+            } else if (kSweep == SWEEP_P) {
+                negc = 0ull;                            // the shift x = s - c_i is part of the product (ninth K step)
+            } else if (kSweep == SWEEP_H) {
                 negc = pack2(-cshift, -cshift);         // the only per-row constant: the shift x = s - c_i
             } else {
                 const float4 rs = p.rowS[lrow];
@@ -864,7 +902,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             } else if (kSweep == SWEEP_P) {
                 const bool fast = all_valid && !ranges_overlap(rI, rJ);
                 if (fast) {
-                    for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk(v, negc, q3, q4, mx4); });
+                    for_each_chunk<4>(taddr, [&](int, const uint32_t (&v)[32]) { psweep_chunk<true>(v, negc, q3, q4, mx4); });
                     mN0 += 128.f;
                 } else {
                     // masked tile: stage the column labels once per warp, then packed masked sums
@@ -879,11 +917,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                             const int yl = wy[c0 + lane];
                             const int cmin = __reduce_min_sync(0xffffffffu, yl), cmax = __reduce_max_sync(0xffffffffu, yl);
                             if (cmax < wlo || cmin > whi) {
-                                psweep_chunk(v, negc, q3, q4, mx4);
+                                psweep_chunk<true>(v, negc, q3, q4, mx4);
                                 mN0 += 32.f;
                             } else if (cmin == cmax && wlo == whi && cmin == wlo) {
                                 f32x2 t1[4] = {0ull, 0ull, 0ull, 0ull}, t2[4] = {0ull, 0ull, 0ull, 0ull};
-                                psweep_chunk(v, negc, t1, t2, mx4);
+                                psweep_chunk<true>(v, negc, t1, t2, mx4);
                                 mA1 = fadd2(mA1, fadd2(fadd2(t1[0], t1[1]), fadd2(t1[2], t1[3])));
                                 mA2 = fadd2(mA2, fadd2(fadd2(t2[0], t2[1]), fadd2(t2[2], t2[3])));
                                 mQ0 += 32.f;

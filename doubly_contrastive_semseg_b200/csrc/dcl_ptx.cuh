@@ -166,6 +166,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= 2ull << 61;
     return d;
 }
+// The same without swizzle (layout type 0, "interleave"): core matrices of 8 rows x 16 bytes, `lbo` bytes apart along
+// K and `sbo` bytes apart along M/N.
+__device__ __forceinline__ uint64_t umma_smem_desc_noswizzle(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
 // K-major view of an F-tile panel (reduce over channels): 8-row groups are 1024 B apart.
 // `k16` selects the 16-channel slice (0..7); slices 0..3 live in panel 0, 4..7 in panel 1.
 __device__ __forceinline__ uint64_t ftile_desc_kmajor(uint32_t tile_saddr, int k16) {
