@@ -10,9 +10,10 @@
 //   * pixel term ("v3", the hot path).  e^{l} on a row's logit range [-L_i, 0] (L_i <= 1 because |l_i|_2 = 1) is a
 //     per-row economised Chebyshev polynomial of degree n = 1..4, so  Den_i = sum_neg E = sum_j e_j P_j  and
 //     sum_neg E x = sum_j e_j P_{j+1}  with the shifted power sums P_j = sum_neg x^j, x = s - c_i (c_i = |f_i|^2, the
-//     diagonal: the shift keeps every sum well conditioned).  ONE sweep (SWEEP_P) produces, per row, the exact
+//     diagonal: the shift keeps every sum well conditioned; the tensor pipe applies it, as a ninth K step of the
+//     product with -c_i split into three bf16 against a ones operand).  ONE sweep (SWEEP_P) produces, per row, the exact
 //     maximum and P_0..P_2 of the different-class columns plus Q_0..Q_2 of the same-class columns (packed FFMA2, no
-//     MUFU, no per-row constants but c_i); kappa_i comes from P + Q, and with n = 1 (a few thousand anchors or
+//     MUFU, no per-row constants at all in the epilogue); kappa_i comes from P + Q, and with n = 1 (a few thousand anchors or
 //     more) everything else follows per row in k_rows.  Rows whose range needs n > 1 trigger a second sweep
 //     (SWEEP_H: x^3..x^{n+1}) that otherwise exits at once; the positive-pair terms use a first-order series in
 //     E/Den and fall back to the exact sweep C only when some row has fewer than ~170 negatives.
