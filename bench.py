@@ -140,11 +140,13 @@ def cpu_port_step(wl, data, seed):
 
 
 def reference_sample_workload(wl):
-    """Bounded sample for the CPU arm: 2 of the workload's images, max_samples scaled alike (so
-    n_view is unchanged); the reference's cost per anchor grows with the number of anchors, so
+    """Bounded sample for the CPU arm: 2 of the workload's images, max_samples scaled alike (so n_view is
+    unchanged) but capped at 4096 anchors; the reference's cost per anchor grows with the number of anchors, so
     this sample flatters the CPU number."""
     b = min(2, wl.B)
-    return dataclasses.replace(wl, name=wl.name + "_sample", B=b, max_samples=wl.max_samples * b // wl.B)
+    # at most 4096 anchors per CPU step (the dense N x N autograd of the reference grows as N^2: 16384 anchors would
+    # take ~30 s and several GB per step); for cfg2 this is the proportional 2048
+    return dataclasses.replace(wl, name=wl.name + "_sample", B=b, max_samples=min(wl.max_samples * b // wl.B, 4096))
 
 
 def run_reference(args):
