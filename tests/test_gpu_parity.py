@@ -201,6 +201,29 @@ def test_fused_step_equals_stage_by_stage(dcl, B, H, W, h, w, K, mv, ms):
         assert np.array_equal(a[3], b[3]) and a[4] == b[4]
 
 
+def test_shard_pack_unpack_roundtrip(dcl):
+    """The sharded step's one pre-backward message (dcl_shard_pack -> all-gather -> dcl_shard_unpack), exercised on
+    one GPU by playing every rank in turn: constants land in place, the loss is the rank-ordered sum / n_global."""
+    from doubly_contrastive_semseg_b200 import _lib
+    from doubly_contrastive_semseg_b200.loss import _p, _stream
+    world, n_pad, n_global = 3, 256, 700
+    g = torch.Generator(device="cuda").manual_seed(4)
+    colA = torch.randn(world * n_pad, 4, generator=g, device="cuda")
+    colB = torch.randn(world * n_pad, 4, generator=g, device="cuda")
+    parts = torch.randn(world, generator=g, device="cuda")
+    recv = torch.empty(world, 2 * n_pad * 4 + 4, device="cuda")
+    for r in range(world):
+        loss2 = torch.stack([parts[r], parts[r] * 0]).contiguous()
+        _lib.call("dcl_shard_pack", _p(colA), _p(colB), _p(loss2), r, n_pad, _p(recv[r]), _stream())
+    outA, outB = torch.zeros_like(colA), torch.zeros_like(colB)
+    loss = torch.empty(1, device="cuda")
+    _lib.call("dcl_shard_unpack", _p(recv), world, n_pad, _p(outA), _p(outB), n_global, _p(loss), _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(outA, colA) and torch.equal(outB, colB)
+    want = (parts[0] + parts[1] + parts[2]) / n_global
+    assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want)) + 1e-9
+
+
 # ------------------------------------------------------------------ whole modules vs golden
 @pytest.mark.parametrize("case", _cases("pixel"))
 def test_pixel_module_vs_reference_golden(dcl, case):
