@@ -62,8 +62,17 @@ inline void twist_words(uint32_t* s) {
 class Lookahead {
 public:
     static constexpr uint64_t kRing = 4096;                    // blocks (10 MB): ~2.5 M draws ahead
-    const uint32_t* block(uint64_t idx) {                      // blocks [floor, produced) are readable
-        while (produced_.load(std::memory_order_acquire) <= idx) std::this_thread::yield();
+    // blocks [floor, produced) are readable.  `seen` is the caller's last reading of `produced`: the worker stores to
+    // that counter all the time, so loading it once per block (a plan walks ~1700 blocks) was a cache-line transfer
+    // each time - about half of a cfg2 plan.
+    const uint32_t* block(uint64_t idx, uint64_t& seen) {
+        if (idx >= seen) {
+            seen = produced_.load(std::memory_order_acquire);
+            while (seen <= idx) {
+                std::this_thread::yield();
+                seen = produced_.load(std::memory_order_acquire);
+            }
+        }
         return ring_.data() + (idx % kRing) * kN;
     }
     // does the serialized torch state equal where the last plan left the generator?  (same process only)
@@ -148,11 +157,12 @@ struct Mt {
     uint32_t next;
     Lookahead* la = nullptr;
     uint64_t blk = 0;
+    uint64_t la_seen = 0;    // blocks known to be produced (see Lookahead::block)
 };
 
 void twist(Mt& m) {
     if (m.la) {
-        m.s = m.la->block(++m.blk);
+        m.s = m.la->block(++m.blk, m.la_seen);
     } else {
         twist_words(m.own);
         m.s = m.own;
@@ -196,6 +206,7 @@ struct Sparse {
     std::vector<Slot> tab;
     std::vector<uint32_t> used;        // slots filled by the current permutation (cleared on reset)
     std::vector<int32_t> front;
+    std::vector<double> inv;           // 1 / (n - i) of the current permutation (see randperm_prefix)
     uint32_t mask = 0;
     void reset(int64_t k) {
         size_t cap = 16;
@@ -224,11 +235,23 @@ void randperm_prefix(Mt& m, int64_t n, int64_t k, int64_t* out, Sparse& sp) {
     }
     if (k > n) k = n;
     sp.reset(k);
+    // draw % (n - i) without the integer divider (a third of the loop's time): the reciprocals of the k divisors
+    // come from one vectorisable loop, the quotient estimate x * (1 / d) is off by at most one (x < 2^32, d < 2^31,
+    // 53-bit products), and the remainder is corrected exactly.  Same value as the reference's 32-bit modulo.
+    sp.inv.resize(static_cast<size_t>(k));
+    double* inv = sp.inv.data();
+    for (int64_t i = 0; i < k; ++i) inv[i] = 1.0 / static_cast<double>(n - i);
     int64_t drawn = 0;
     for (int64_t i = 0; i < k; ++i) {
         int64_t j = i;
         if (i < n - 1) {
-            j = i + static_cast<int64_t>(draw(m) % static_cast<uint32_t>(n - i));   // n < 2^31: 32-bit modulo, same value
+            const uint32_t x = draw(m);
+            const int64_t d = n - i;
+            const int64_t q = static_cast<int64_t>(static_cast<double>(x) * inv[i]);
+            int64_t r = static_cast<int64_t>(x) - q * d;
+            r += (r < 0) ? d : 0;
+            r -= (r >= d) ? d : 0;
+            j = i + r;
             ++drawn;
         }
         const int32_t vi = sp.front[i];
@@ -383,8 +406,19 @@ void store_state(void* torch_rng_state, const Mt& m) {
 // split rule, the randperm draws and the class-sorted device row layout.  Shared by the single-process entry point
 // and the sharded one: `world` ranks own `Bl` consecutive images each; every rank replays the SAME generator stream
 // over the global batch, but only draws the permutations of its own anchors (the others just advance the state).
+static long long g_plan_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // diagnostics: sections of the last plan (dcl_host_plan_timing)
+static inline long long now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static long long g_la_stats[4] = {0, 0, 0, 0};   // plans served by the look-ahead stream, inline plans, stream starts, drops
 // Diagnostics: counters of the generator look-ahead (see Lookahead): out[4] = stream plans, inline plans, starts, drops.
+extern "C" int dcl_host_plan_timing(long long* out) {
+    if (!out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
+    for (int i = 0; i < 8; ++i) out[i] = g_plan_ns[i];
+    return 0;
+}
+
 extern "C" int dcl_host_lookahead_stats(long long* out) {
     for (int i = 0; i < 4; ++i) out[i] = g_la_stats[i];
     return 0;
@@ -395,6 +429,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
                      int32_t* req, int32_t* y_all, int64_t* ref_row, int64_t* anchor) {
     if (!counts || !info || Bl <= 0 || world <= 0 || rank < 0 || rank >= world) return dcl::fail(DCL_ERR_ARG, "bad argument");
     const int B = Bl * world;
+    const long long t_start = now_ns();
     int A = 0;
     for (int b = 0; b < B; ++b)
         for (int c = 0; c < 256; ++c) {
@@ -421,6 +456,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
         }
     }
     const int lo = rank * Bl, hi = lo + Bl;
+    g_plan_ns[0] = now_ns() - t_start;                       // anchor list + split rule
     if (n_view > 0) {
         Mt m;
         if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
@@ -441,7 +477,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             if (continuous && fits) {
                 m.la = &la;
                 m.blk = la.position();
-                m.s = la.block(m.blk);
+                m.s = la.block(m.blk, m.la_seen);
                 ++g_la_stats[0];
             } else {
                 la.stop();
@@ -449,6 +485,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             }
         }
         if (!m.la) ++g_la_stats[1];
+        g_plan_ns[1] = now_ns() - t_start;                   // + generator state, look-ahead attach
         int n_local = 0;
         for (int a = 0; a < A; ++a) {
             const int64_t kh = keep_hard[a], ke = n_view - kh;
@@ -493,6 +530,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
                 }
             }
         }
+        g_plan_ns[2] = now_ns() - t_start;                   // + permutations
         store_state(torch_rng_state, m);
         if (m.la) {
             la.commit(m.blk, raw);
@@ -508,6 +546,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             }
         }
     }
+    g_plan_ns[3] = now_ns() - t_start;                       // + state write-back, look-ahead commit
     // rows per rank -> common padded block size
     std::vector<int> per_rank(world, 0);
     for (int a = 0; a < A; ++a) per_rank[image[a] / Bl] += n_view;
@@ -558,6 +597,7 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             }
         }
     }
+    g_plan_ns[4] = now_ns() - t_start;                       // + row requests / labels
     return 0;
 }
 

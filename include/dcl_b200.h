@@ -143,6 +143,9 @@ int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int ran
  * previous plan left it): out[4] = plans served by the stream, inline plans, stream starts, drops.
  * DCL_HOST_LOOKAHEAD=0 in the environment disables the stream. */
 int dcl_host_lookahead_stats(long long* out);
+/* Diagnostics: cumulative nanoseconds of the last plan at the end of each of its sections: out[8] = anchor list,
+ * + generator state / look-ahead attach, + permutations, + state write-back / commit, + row requests, -, -, -. */
+int dcl_host_plan_timing(long long* out);
 
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
