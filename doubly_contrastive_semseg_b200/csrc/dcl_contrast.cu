@@ -253,25 +253,6 @@ __device__ __forceinline__ void for_each_chunk_loop(uint32_t taddr, Fn&& fn) {
         fn(c0, v);
     }
 }
-// Middle ground: a real loop of two trips, each with two chunk bodies, the next chunk's TMEM load in flight behind
-// the current body (half the code of for_each_chunk<4>, none of the exposed load latency of for_each_chunk_loop,
-// which costs a mixed tile about twice a plain one).
-template <class Fn>
-__device__ __forceinline__ void for_each_chunk_loop2(uint32_t taddr, Fn&& fn) {
-    uint32_t va[32], vb[32];
-    tmem_ld32(taddr, va);
-    tmem_ld_wait_on(va);
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 64) {
-        tmem_ld32(taddr + c0 + 32, vb);
-        fn(c0, va);
-        tmem_ld_wait_on(vb);
-        if (c0 == 0) tmem_ld32(taddr + 64, va);
-        fn(c0 + 32, vb);
-        if (c0 == 0) tmem_ld_wait_on(va);
-    }
-}
-
 // diagnostics: stamp (role, tile, event) for CTA 0's first 32 tiles; roles: 0 producer, 1/2 issuers, 3/4 epilogue groups
 __device__ __forceinline__ void trace_stamp(const Params& p, int role, int it, int ev) {
     if (p.trace && blockIdx.x == 0 && it < 32) p.trace[(role * 32 + it) * 8 + ev] = clock64();
@@ -1940,7 +1921,7 @@ __global__ void __launch_bounds__(128) k_blockinfo(const Params p) {
         p.binfo[J] = make_int4(b.lo, b.hi, b.n, 0);
         p.bnorm[J] = make_float2(b.cx, b.cn);
         if (J < p.nI) p.dticket[J] = 0u;
-        if (J == 0) { p.iscal[0] = 1; p.iscal[3] = 1; p.iscal[4] = 0; p.iscal[5] = 0; p.ticket[0] = 0u; p.ticket[1] = 0u; }
+        if (J == 0) { p.iscal[0] = 1; p.iscal[4] = 0; p.iscal[5] = 0; p.ticket[0] = 0u; p.ticket[1] = 0u; }
     }
 }
 
