@@ -618,21 +618,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
     const uint32_t tAcc = tmem + 128;
 
     if (warp == kProducerWarp) {
-        // ---------------------------------------------------------------------- TMA producer (column blocks only)
+        // ---------------------------------------------------------------------- TMA producer
+        // Ring entries in order: at every unit start the unit's row blocks (the issuer copies them on into TMEM with
+        // tcgen05.cp and frees the slots at once), then one entry per column block.  `pos` counts entries.
         TileIter<kSweep == SWEEP_C> iter(p, part, sInfo);
-        int U, J, it = 0;
+        int U, J, curU = -1, it = 0, pos = 0;
         bool last;
-        while (iter.next(U, J, last)) {
-            const int slot = it % kSlots;
-            if (lane == 0) trace_stamp(p, 0, it, 0);
-            mbar_wait(b_empty + 8 * slot, ((it / kSlots) & 1) ^ 1);
-            if (lane == 0) trace_stamp(p, 0, it, 1);
+        auto push = [&](int block) {
+            const int slot = pos % kSlots;
+            mbar_wait(b_empty + 8 * slot, ((pos / kSlots) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(b_full + 8 * slot, kTileBytes);
-                tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(J) * kTileBytes,
+                tma_bulk_g2s(sJ + slot * kTileBytes, p.tiles + static_cast<size_t>(block) * kTileBytes,
                              kTileBytes, b_full + 8 * slot);
             }
             __syncwarp();
+            ++pos;
+        };
+        while (iter.next(U, J, last)) {
+            if (U != curU) {
+                curU = U;
+                push(p.rb0 + 2 * U);
+                if (2 * U + 1 < p.nI) push(p.rb0 + 2 * U + 1);
+            }
+            if (lane == 0) trace_stamp(p, 0, it, 0);
+            push(J);
+            if (lane == 0) trace_stamp(p, 0, it, 1);
             ++it;
         }
     } else if (warp >= kIssuerWarp0) {
@@ -655,10 +666,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             const uint64_t dShiftA0 = umma_smem_desc_noswizzle(sShiftA, 128, 256);
             const uint64_t dShiftA1 = umma_smem_desc_noswizzle(sShiftA + 4096, 128, 256);
             const uint64_t dShiftB = umma_smem_desc_noswizzle(sShiftB, 128, 0);
-            int U, J, curU = -1, it = 0, seg = 0, turn = 0;
-            bool last, two = false;
+            int U, J, curU = -1, it = 0, seg = 0, turn = 0, pos = 0, posA = 0;
+            bool last, two = false, fresh = false;
             while (iter.next(U, J, last)) {
                 if (U != curU) {
+                    posA = pos;                          // ring entries of the unit's row blocks
+                    pos += (2 * U + 1 < p.nI) ? 2 : 1;
+                    fresh = true;                        // the issuer that owns this tile copies them into TMEM
                     // BOTH issuers wait for every unit's row blocks (a waiter that skipped a phase would alias
                     // the 1-bit parity) and acknowledge, so the epilogue never runs two phases ahead of one
                     two = 2 * U + 1 < p.nI;
@@ -669,12 +683,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     __syncwarp();
                     ++seg;
                 }
+                const int slot = pos % kSlots, slot_phase = (pos / kSlots) & 1;
+                ++pos;
+                const bool copyA = fresh;
+                fresh = false;
                 if ((it & 1) == s) {
-                    const int slot = it % kSlots;
                     const int j0 = 2 * it, j1 = 2 * it + 1;
                     const int b0 = j0 % 3, b1 = j1 % 3;
                     if (lane == 0) trace_stamp(p, 1 + s, it, 0);
-                    mbar_wait(b_full + 8 * slot, (it / kSlots) & 1);
+                    if (copyA) {
+                        mbar_wait(b_full + 8 * (posA % kSlots), (posA / kSlots) & 1);
+                        if (two) mbar_wait(b_full + 8 * ((posA + 1) % kSlots), ((posA + 1) / kSlots) & 1);
+                    }
+                    mbar_wait(b_full + 8 * slot, slot_phase);
                     if (lane == 0) trace_stamp(p, 1 + s, it, 1);
                     mbar_wait(b_tempty + 8 * b0, ((j0 / 3) & 1) ^ 1);
                     if (lane == 0) trace_stamp(p, 1 + s, it, 2);
@@ -684,6 +705,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     tc_fence_after();
                     const uint64_t soff = static_cast<uint64_t>(slot * (kTileBytes >> 4));
                     const bool run = !(p.debug & 2);
+                    if (copyA && elect_one()) {
+                        // Row blocks: shared memory -> TMEM as the A operand, eight 128 x 32-byte copies each with the
+                        // K-slice descriptors the MMA would use.  The tensor pipe runs cp and mma in issue order and
+                        // the other issuer handed the turn over only after its last MMA of the previous unit, so no
+                        // MMA that still reads the old blocks is behind these.
+                        for (int gg = 0; gg < (two ? 2 : 1); ++gg) {
+                            const int sa = (posA + gg) % kSlots;
+                            const uint64_t aoff = static_cast<uint64_t>(sa * (kTileBytes >> 4));
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) tmem_cp_128x256b(tmem + gg * 64 + k * 8, dJ0[k] + aoff);
+                            tc_commit(b_empty + 8 * sa);
+                        }
+                    }
+                    __syncwarp();
                     if (elect_one()) {
                         if (run) {
 #pragma unroll
@@ -703,7 +738,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
 #pragma unroll
                             for (int k = 0; k < 2; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, k > 0);
                         }
-                        mbar_arrive(b_turn + 8 * (s ^ 1));            // six MMAs (~400 clk, the other issuer's wake-up) early
+                        // six MMAs (~400 clk, the other issuer's wake-up) early - unless the next tile starts a new
+                        // unit: its row-block copies must queue behind every MMA of this one
+                        if (!last) mbar_arrive(b_turn + 8 * (s ^ 1));
                         if (run && two) {
 #pragma unroll
                             for (int k = 2; k < 8; ++k) umma_ts(tAcc + b1 * 128, tmem + 64 + k * 8, dJ0[k] + soff, idesc, true);
@@ -711,6 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                         }
                         tc_commit(b_tfull + 8 * b1);
                         tc_commit(b_empty + 8 * slot);
+                        if (last) mbar_arrive(b_turn + 8 * (s ^ 1));
                     }
                     __syncwarp();
                     if (lane == 0) trace_stamp(p, 1 + s, it, 3);
@@ -790,34 +828,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
             curU = nU;
             Iloc = 2 * nU + g;
             valid = Iloc < p.nI;
-            // Row block -> TMEM as the A operand (bf16 pairs, channel order).  Every MMA that read the previous
-            // block has completed: this group has consumed the accumulators of all its earlier jobs.
+            // The row block itself reaches TMEM through the ring (TMA) and tcgen05.cp, issued by the MMA warps; this
+            // group only needs its rows' labels and shifts.  Every MMA that read the previous unit's shift operand
+            // has completed: the group has consumed the accumulators of all its earlier jobs.
             if (valid) {
-                const uint8_t* trow = p.tiles + static_cast<size_t>(p.rb0 + Iloc) * kTileBytes + r * 128;
                 gi = (p.rb0 + Iloc) * 128 + r;
-                // all loads first (one round trip), then the four TMEM stores
                 const int yload = __ldg(p.y + gi);
                 const float cload = (kSweep == SWEEP_A || kSweep == SWEEP_P || kSweep == SWEEP_H) ? __ldg(p.sqnorm + gi) : 0.f;
-                uint4 xw[16];
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        xw[h * 8 + c] = __ldg(reinterpret_cast<const uint4*>(trow + h * kHalfBytes + ((c ^ (r & 7)) << 4)));
                 yi = yload;
                 cshift = cload;
-                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 0);     // loads issued
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const uint4 x = xw[qq * 4 + cc];
-                        w[cc * 4 + 0] = x.x; w[cc * 4 + 1] = x.y; w[cc * 4 + 2] = x.z; w[cc * 4 + 3] = x.w;
-                    }
-                    tmem_st16(tmem + lane_off + g * 64 + qq * 16, w);
-                }
-                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 1);     // loads arrived, stores issued
                 if (kSweep == SWEEP_P) {
                     // -c_i as three bf16 (hi + mid + lo reproduces the fp32 value to 2^-24): row r of group g's A'
                     const __nv_bfloat16 hi = __float2bfloat16_rn(cload);
@@ -832,8 +851,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_sweep(const Params p) {
                     *reinterpret_cast<uint4*>(arow + 128) = make_uint4(0u, 0u, 0u, 0u);
                     fence_proxy_async_smem();
                 }
-                tmem_st_wait();
-                if ((threadIdx.x & 127) == 0 && nunits == 0) trace_stamp(p, 3 + g, 31, 2);     // stores done
             }
             tc_fence_before();
             if (nunits > 0) mbar_wait(b_aseen, (nunits - 1) & 1);   // both issuers are past the previous unit's wait
