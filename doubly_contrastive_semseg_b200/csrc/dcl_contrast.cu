@@ -29,7 +29,8 @@
 // round trip costs ~150-200 clocks, so a single issuer thread leaves the tensor pipe idle half of the time
 // (profiles/r01f_*): with two issuers one thread's waits overlap the other's MMAs.
 //   sweeps  : a CTA owns a PAIR of row blocks (M = 256): every F_J tile fetched from L2 feeds two 128x128 S tiles,
-//             one per epilogue group / issuer; TMEM = 2 stages x 2 groups x 128 columns.
+//             one per epilogue group.  The row blocks are the A operand in TMEM (2 x 64 columns; they arrive through
+//             the TMA ring and tcgen05.cp issued by the MMA warps), three 128-column accumulators rotate over the jobs.
 //   backward: a CTA owns one row block; issuer 0 produces S tiles (3 TMEM stages), issuer 1 the G.F_J products; the
 //             two epilogue groups alternate column tiles.
 // Work = the flattened list of (row unit, column block) tiles cut into gridDim.x equal contiguous ranges; a range
