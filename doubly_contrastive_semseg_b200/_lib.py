@@ -21,6 +21,7 @@ SIGNATURES = {
     "dcl_debug_trace": (_i, [_vp]),
     "dcl_debug_cta_times": (_i, [_vp]),
     "dcl_contrast_launches": (_i, [_i, _i]),
+    "dcl_debug_partition": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_sample_classify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "dcl_host_sample_ranks": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),

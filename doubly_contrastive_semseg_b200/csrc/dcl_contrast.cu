@@ -2191,6 +2191,25 @@ extern "C" int dcl_contrast_launches(int mode, int backward) {
     return 7;
 }
 
+// Diagnostics / tests (host only): the tile partition a sweep (backward == 0: units = pairs of row blocks) or the
+// backward (units = row blocks) would use for nI local row blocks, nJ column blocks and `ctas` CTAs.
+//   begin [ctas + 1] out : first flat tile index (unit * nJ + k) of every CTA, begin[G] = units * nJ
+//   unit_first, unit_nseg [units] out : first CTA and number of CTAs of every unit
+//   meta [4] out : G, exclusive mode (0/1), maxseg (segments the workspace is sized for), units
+extern "C" int dcl_debug_partition(int nI, int nJ, int ctas, int backward, long long* begin, int* unit_first,
+                                   int* unit_nseg, int* meta) {
+    if (nI <= 0 || nJ <= 0 || ctas <= 0 || !begin || !unit_first || !unit_nseg || !meta)
+        return fail(DCL_ERR_ARG, "bad argument");
+    Part part;
+    int maxseg = 0;
+    const int units = backward ? nI : (nI + 1) / 2;
+    make_part(part, maxseg, units, nJ, ctas, backward ? 12 : 4);
+    for (int c = 0; c <= part.G; ++c) begin[c] = part.begin(c);
+    for (int u = 0; u < units; ++u) { unit_first[u] = part.first_cta(u); unit_nseg[u] = part.nseg(u); }
+    meta[0] = part.G; meta[1] = part.excl; meta[2] = maxseg; meta[3] = units;
+    return 0;
+}
+
 extern "C" size_t dcl_contrast_workspace_bytes(int nI, int nJ) {
     if (nI <= 0 || nJ <= 0) return 0;
     return make_layout(nI, nJ).bytes;

@@ -58,6 +58,12 @@ int dcl_debug_trace(void* device_buffer);
 /* Diagnostics only: device buffer of 4*256*4 int64; every CTA of the sweep-P, backward and k_rows kernels
  * records (globaltimer ns, clock64) at entry and exit.  NULL switches it off. */
 int dcl_debug_cta_times(void* device_buffer);
+/* Diagnostics / tests (host only, no device needed): the tile partition a sweep (backward == 0: units = pairs of row
+ * blocks) or the backward (units = row blocks) uses for nI local row blocks, nJ column blocks and `ctas` CTAs.
+ * begin [ctas+1]: first flat tile index (unit*nJ + k) of every CTA (begin[G] = units*nJ); unit_first / unit_nseg
+ * [units]: first CTA and number of CTAs of every unit; meta [4]: G, exclusive mode, maxseg, units. */
+int dcl_debug_partition(int nI, int nJ, int ctas, int backward, long long* begin, int* unit_first,
+                        int* unit_nseg, int* meta);
 /* Number of kernels one dcl_contrast_fwd (backward == 0) or dcl_contrast_bwd call launches for `mode`. */
 int dcl_contrast_launches(int mode, int backward);
 

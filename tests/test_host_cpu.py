@@ -96,3 +96,39 @@ def test_c_rng_replay_matches_torch_randperm(built_lib):
         tail_t = torch.randperm(11)
         assert np.array_equal(got, want)
         assert torch.equal(tail_c, tail_t)
+
+
+def test_tile_partition_invariants(built_lib):
+    """The flat and the exclusive (whole CTAs per unit) partitions of the tile list: every tile belongs to exactly one
+    CTA, every CTA of a non-empty grid has work, a unit's CTAs are the contiguous range [first, first + nseg), and no
+    unit needs more segment slots than the workspace provides (maxseg)."""
+    import ctypes
+    from doubly_contrastive_semseg_b200 import _lib
+    lib = _lib.load()
+    shapes = [(nI, nJ) for nJ in (1, 2, 3, 5, 8, 13, 31, 32, 33, 64, 65, 100, 128, 147, 148, 149, 200, 256, 512, 1024)
+              for nI in sorted({1, 2, 3, nJ // 8, nJ // 4, nJ // 2, nJ - 1, nJ} - {0}) if nI <= nJ]
+    seen_excl = {0: 0, 1: 0}
+    for ctas in (148, 132, 7):
+        for nI, nJ in shapes:
+            for backward in (0, 1):
+                begin = (ctypes.c_longlong * (ctas + 1))()
+                units_cap = nI if backward else (nI + 1) // 2
+                first = (ctypes.c_int * units_cap)()
+                nseg = (ctypes.c_int * units_cap)()
+                meta = (ctypes.c_int * 4)()
+                assert lib.dcl_debug_partition(nI, nJ, ctas, backward, begin, first, nseg, meta) == 0
+                G, excl, maxseg, units = meta[0], meta[1], meta[2], meta[3]
+                seen_excl[excl] += 1
+                total = units * nJ
+                assert units == units_cap and 1 <= G <= ctas and G <= total
+                b = [begin[c] for c in range(G + 1)]
+                assert b[0] == 0 and b[G] == total
+                assert all(b[c] < b[c + 1] for c in range(G)), (nI, nJ, ctas, backward)      # every CTA has >= 1 tile
+                for u in range(units):
+                    lo, hi = u * nJ, (u + 1) * nJ
+                    touching = [c for c in range(G) if b[c] < hi and b[c + 1] > lo]
+                    assert touching == list(range(first[u], first[u] + nseg[u])), (nI, nJ, ctas, backward, u)
+                    assert nseg[u] <= maxseg, (nI, nJ, ctas, backward, u, nseg[u], maxseg)
+                if excl:
+                    assert all(b[c] // nJ == (b[c + 1] - 1) // nJ for c in range(G))         # no CTA crosses a unit
+    assert seen_excl[0] > 0 and seen_excl[1] > 0
