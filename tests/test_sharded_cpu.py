@@ -183,3 +183,54 @@ def test_consecutive_plans_use_the_lookahead_stream_and_stay_exact(world, thread
             % (root, os.path.join(root, "tests"), world))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_c_plan_equals_numpy_plan_on_random_tables():
+    """dcl_host_plan_rows(_sharded) == the numpy / torch.randperm plan on random count tables: classes below the
+    max_views threshold, hard-only / easy-only classes, capped n_view, single image, many ranks."""
+    from doubly_contrastive_semseg_b200.loss import shard_plan, shard_plan_c
+    rng = np.random.default_rng(2024)
+    done = 0
+    for trial in range(40):
+        world = int(rng.choice([1, 1, 2, 3, 4]))
+        bl = int(rng.integers(1, 4))
+        B = world * bl
+        K = int(rng.integers(1, 12))
+        mv = int(rng.integers(1, 70))
+        ms = int(rng.choice([64, 200, 1024, 4096]))
+        counts = np.zeros((B, 256, 2), dtype=np.int32)
+        for b in range(B):
+            for c in rng.choice(19, size=K, replace=False):
+                kind = rng.integers(0, 4)
+                nh = int(rng.integers(0, 3000)) if kind != 1 else 0
+                ne = int(rng.integers(0, 3000)) if kind != 2 else 0
+                if kind == 3:
+                    nh, ne = int(rng.integers(0, mv + 2)), int(rng.integers(0, mv + 2))     # around the threshold
+                counts[b, c] = (nh, ne)
+        counts[:, 255] = rng.integers(0, 500, size=(B, 2))                                    # ignored label
+        rank = int(rng.integers(0, world))
+        torch.manual_seed(1000 + trial)
+        try:
+            ref = shard_plan(counts, rank, world, bl, 255, ms, mv)
+        except Exception:                      # the reference's unreachable split branch: both sides must agree
+            torch.manual_seed(1000 + trial)
+            with pytest.raises(Exception):
+                shard_plan_c(counts, rank, world, bl, 255, ms, mv)
+            continue
+        end_ref = torch.get_rng_state().clone()
+        torch.manual_seed(1000 + trial)
+        got = shard_plan_c(counts, rank, world, bl, 255, ms, mv)
+        assert (ref is None) == (got is None)
+        assert torch.equal(torch.get_rng_state(), end_ref)
+        if ref is None:
+            continue
+        got, y_all = got
+        assert (got.plan.A, got.plan.n_view, got.n_pad, got.n_global) == (ref.plan.A, ref.plan.n_view, ref.n_pad, ref.n_global)
+        if ref.plan.n_view == 0:
+            continue
+        mine = (ref.plan.image // bl) == rank
+        assert np.array_equal(got.plan.ranks[mine], ref.plan.ranks[mine])
+        for name in ("req", "y", "ref_row", "anchor"):
+            assert np.array_equal(getattr(got.layout, name), getattr(ref.layout, name)), (trial, name)
+        done += 1
+    assert done >= 15
