@@ -104,8 +104,8 @@ class ClockSampler:
 
 def ncu_traffic(workload, world):
     """DRAM bytes per step of the similarity kernels (sweep P + backward) from the committed `ncu --set full`
-    capture of this workload on one GPU (profiles/r01o_ncu_dram_traffic.json); None where none was taken."""
-    path = os.path.join(ROOT, "profiles", "r01o_ncu_dram_traffic.json")
+    capture of this workload on one GPU (profiles/r01r_ncu_dram_traffic.json); None where none was taken."""
+    path = os.path.join(ROOT, "profiles", "r01r_ncu_dram_traffic.json")
     if world != 1 or not os.path.exists(path):
         return None
     try:
