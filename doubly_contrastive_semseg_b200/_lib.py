@@ -27,6 +27,7 @@ SIGNATURES = {
     "dcl_host_sample_ranks": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_host_plan_rows": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcl_host_plan_rows_sharded": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dcl_debug_plan_device": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz] + [_vp] * 16),
     "dcl_host_lookahead_stats": (_i, [_vp]),
     "dcl_host_plan_timing": (_i, [_vp]),
     "dcl_gather_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -40,29 +41,40 @@ SIGNATURES = {
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "dcl_shard_pack": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "dcl_shard_unpack": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "dcl_pixel_fwd": (_i, [_vp, _vp]),
-    "dcl_pixel_begin": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "dcl_pixel_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dcl_step_plan_bytes": (_sz, [_i, _i]),
+    "dcl_step_begin": (_i, [_vp, _vp]),
+    "dcl_step_fwd": (_i, [_vp, _vp]),
+    "dcl_step_timing": (_i, [_vp]),
+    "dcl_step_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "dcl_comm_unique_id": (_i, [_vp]),
+    "dcl_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "dcl_comm_destroy": (_i, [_vp]),
+    "dcl_comm_all_gather": (_i, [_vp, _vp, _vp, _sz, _vp]),
 }
 
 
-class PixelStep(ctypes.Structure):
-    """dcl_pixel_step_t of include/dcl_b200.h, field for field."""
+class Step(ctypes.Structure):
+    """dcl_step_t of include/dcl_b200.h, field for field."""
     _fields_ = [
         ("labels", _vp), ("predict", _vp), ("feats", _vp),
         ("B", _i), ("H", _i), ("W", _i), ("h", _i), ("w", _i), ("C_cls", _i), ("ignore_label", _i),
         ("max_samples", _i), ("max_views", _i),
         ("temperature", _f), ("base_temperature", _f),
         ("torch_rng_state", _vp), ("state_bytes", _sz),
+        ("world", _i), ("rank", _i), ("comm", _vp),
+        ("cap", _i),
         ("code", _vp), ("chunk_hist", _vp), ("counts_dev", _vp),
-        ("counts_host", _vp), ("stage_host", _vp), ("cap", _i),
-        ("info", _vp), ("image", _vp), ("cls", _vp), ("num_hard", _vp), ("num_easy", _vp), ("keep_hard", _vp),
-        ("ranks", _vp), ("ref_row", _vp), ("anchor", _vp),
-        ("stage_dev", _vp), ("pix", _vp), ("tiles", _vp), ("sqnorm", _vp), ("colA", _vp), ("colB", _vp),
-        ("rowloss", _vp), ("loss_sum", _vp),
+        ("req_dev", _vp), ("y_dev", _vp), ("pix", _vp), ("plan_dev", _vp),
+        ("tiles", _vp), ("sqnorm", _vp), ("colA", _vp), ("colB", _vp), ("rowloss", _vp), ("loss_sum", _vp),
+        ("loss", _vp),
+        ("xchg_send", _vp), ("xchg_recv", _vp), ("dF", _vp),
         ("workspace", _vp), ("workspace_bytes", _sz),
-        ("zero_fill", _vp), ("zero_fill_bytes", _sz),
-        ("ev_begin", _vp), ("ev_end", _vp),
+        ("counts_host", _vp), ("plan_host", _vp), ("plan_bytes", _sz), ("stage_host", _vp),
+        ("info", _vp), ("image", _vp), ("cls", _vp), ("num_hard", _vp), ("num_easy", _vp), ("keep_hard", _vp),
+        ("ranks", _vp),
+        ("zero_fill", _vp), ("zero_fill_bytes", _sz), ("side_stream", _vp),
+        ("device_plan", _i),
+        ("ev_fwd_begin", _vp), ("ev_fwd_end", _vp), ("ev_bwd_begin", _vp), ("ev_bwd_end", _vp),
         ("begun", _i),
     ]
 
@@ -77,6 +89,9 @@ _lib = None
 
 class DclError(RuntimeError):
     pass
+
+
+DCL_ERR_COMM, DCL_ERR_LABEL = -4, -5      # enum dcl_status, include/dcl_b200.h
 
 
 def load():

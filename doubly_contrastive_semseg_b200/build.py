@@ -11,8 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcl_b200.so")
-SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_sampler.cu", "dcl_step.cu", "dcl_host_rng.cpp"]
-HEADERS = ["dcl_ptx.cuh", "dcl_common.cuh", os.path.join("..", "..", "include", "dcl_b200.h")]
+SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_sampler.cu", "dcl_plan.cu", "dcl_step.cu", "dcl_host_rng.cpp", "dcl_comm.cpp"]
+HEADERS = ["dcl_ptx.cuh", "dcl_common.cuh", "dcl_plan.h", os.path.join("..", "..", "include", "dcl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3", "--use_fast_math", "-Xptxas", "-v"]
 
@@ -55,7 +55,7 @@ def _build_to(LIB, extra, verbose):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (s, r.stdout, r.stderr))
         objs.append(o)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -17,17 +17,26 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// Per-device caches (a process may drive several GPUs): indexed by the device ordinal.
+constexpr int kMaxDev = 64;
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
 int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    static int cached[kMaxDev] = {0};
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDev && cached[dev] > 0) return cached[dev];
+    int n = 0;
+    if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return 148;     // B200; only reached when sizing a workspace without a device
     }
-    cached = n;
-    return cached;
+    if (dev < kMaxDev) cached[dev] = n;
+    return n;
 }
 
 }  // namespace dcl
@@ -37,10 +46,10 @@ extern "C" int dcl_version(void) { return 100; }
 extern "C" const char* dcl_last_error(void) { return dcl::last_error_buf(); }
 
 extern "C" int dcl_check_device(void) {
-    static int ok = -1;
-    if (ok == 1) return 0;
+    static bool ok[dcl::kMaxDev] = {false};
     int dev = 0, major = 0;
     cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev >= 0 && dev < dcl::kMaxDev && ok[dev]) return 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -48,6 +57,6 @@ extern "C" int dcl_check_device(void) {
     }
     if (major != 10)
         return dcl::fail(DCL_ERR_ARCH, "libdcl_b200 is built for sm_100a only; device has compute capability %d.x", major);
-    ok = 1;
+    if (dev >= 0 && dev < dcl::kMaxDev) ok[dev] = true;
     return 0;
 }

@@ -9,7 +9,8 @@ namespace dcl {
 
 char* last_error_buf();                       // thread-local, 512 bytes
 int fail(int code, const char* fmt, ...);     // records message, returns code
-int sm_count();                               // SMs of the current device (148 on B200), cached
+int sm_count();                               // SMs of the current device (148 on B200), cached per device
+int current_device();                         // ordinal of the current device, -1 without one
 
 #define DCL_CUDA(expr)                                                                     \
     do {                                                                                   \

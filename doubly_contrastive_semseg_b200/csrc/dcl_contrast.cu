@@ -2102,11 +2102,20 @@ static int set_smem(K kernel, int bytes) {
     DCL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return 0;
 }
+// The shared-memory opt-in is a per-device (per-context) attribute: one flag per device ordinal and kernel family.
+struct Configured {
+    bool done[64] = {false};
+    bool& here() {
+        const int dev = current_device();
+        return done[(dev >= 0 && dev < 64) ? dev : 0];
+    }
+};
 
 // v3 pixel forward: block info, one power-sum sweep, per-row combination; the higher-moment sweep and the exact
 // positive-pair sweep C are launched too but leave at once unless k_rows raised their triggers
 static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
-    static bool configured = false;
+    static Configured cfgd;
+    bool& configured = cfgd.here();
     if (!configured) {
         if (int e = set_smem(k_sweep<SWEEP_P, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
         if (int e = set_smem(k_sweep<SWEEP_H, DCL_MODE_PIXEL>, SmemSweep::kBytes)) return e;
@@ -2126,7 +2135,8 @@ static int run_fwd_v3(Params p, const Layout& L, cudaStream_t st) {
 
 template <int kMode>
 static int run_fwd_legacy(Params p, const Layout& L, cudaStream_t st) {
-    static bool configured = false;
+    static Configured cfgd;
+    bool& configured = cfgd.here();
     if (!configured) {
         if (int e = set_smem(k_sweep<SWEEP_A, kMode>, SmemSweep::kBytes)) return e;
         if (int e = set_smem(k_sweep<SWEEP_B, kMode>, SmemSweep::kBytes)) return e;
@@ -2145,7 +2155,8 @@ static int run_fwd_legacy(Params p, const Layout& L, cudaStream_t st) {
 
 template <int kMode>
 static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
-    static bool configured = false;
+    static Configured cfgd;
+    bool& configured = cfgd.here();
     if (!configured) {
         if (int e = set_smem(k_backward<kMode>, SmemBwd::kBytes)) return e;
         configured = true;

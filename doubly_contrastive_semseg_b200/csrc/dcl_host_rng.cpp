@@ -23,6 +23,7 @@
 #include <vector>
 #include <unistd.h>
 #include "dcl_common.cuh"
+#include "dcl_plan.h"
 
 namespace {
 
@@ -61,7 +62,7 @@ inline void twist_words(uint32_t* s) {
 // (manual_seed, torch.rand, ...) is detected by comparing the serialized state and the stream restarts from it.
 class Lookahead {
 public:
-    static constexpr uint64_t kRing = 4096;                    // blocks (10 MB): ~2.5 M draws ahead
+    static constexpr uint64_t kRing = 16384;                   // blocks (41 MB): ~10 M draws ahead
     // blocks [floor, produced) are readable.  `seen` is the caller's last reading of `produced`: the worker stores to
     // that counter all the time, so loading it once per block (a plan walks ~1700 blocks) was a cache-line transfer
     // each time - about half of a cfg2 plan.
@@ -86,10 +87,20 @@ public:
         epid_ = getpid();
     }
     uint64_t position() const { return pos_block_; }
+    uint64_t epoch() const { return epoch_; }
+    uint64_t produced() const { return produced_.load(std::memory_order_acquire); }
+    const uint32_t* ring() const { return ring_.data(); }
     // restart from the state words `s` as block 0
     void restart(const uint32_t* s) {
         stop();
-        if (ring_.empty()) ring_.resize(kRing * kN);
+        ++epoch_;
+        if (ring_.empty()) {
+            ring_.resize(kRing * kN);
+            // page-locked so the device mirror of the stream (dcl_step.cu) can be filled by asynchronous copies;
+            // without a CUDA device (CPU tests) the registration simply fails and nothing depends on it
+            if (cudaHostRegister(ring_.data(), sizeof(uint32_t) * kRing * kN, cudaHostRegisterPortable) != cudaSuccess)
+                cudaGetLastError();
+        }
         std::memcpy(ring_.data(), s, sizeof(uint32_t) * kN);
         std::memcpy(last_, s, sizeof(uint32_t) * kN);
         produced_.store(1, std::memory_order_release);
@@ -100,11 +111,13 @@ public:
         worker_ = std::thread([this] { run(); });
         active_ = true;
     }
-    // the plan ended in block `idx`; remember the serialized state torch now holds
-    void commit(uint64_t idx, const uint8_t* raw) {
+    // the plan ended in block `idx`; remember the serialized state torch now holds.  Blocks from `keep_from` on stay
+    // readable (the worker only reuses slots of older blocks): a device-mode plan passes the first block its
+    // permutations read, because the upload of that window to the GPU reads the ring after the plan has returned.
+    void commit(uint64_t idx, const uint8_t* raw, uint64_t keep_from) {
         pos_block_ = idx;
         expect(raw);
-        floor_.store(idx, std::memory_order_release);
+        floor_.store(keep_from < idx ? keep_from : idx, std::memory_order_release);
         cv_.notify_one();
     }
     void stop() {
@@ -146,7 +159,7 @@ private:
     std::thread worker_;
     bool quit_ = false, active_ = false, have_expected_ = false;
     pid_t pid_ = 0, epid_ = 0;
-    uint64_t pos_block_ = 0;
+    uint64_t pos_block_ = 0, epoch_ = 0;
     uint8_t expected_[24 + 8 * kN] = {0};
 };
 
@@ -411,7 +424,9 @@ static inline long long now_ns() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static long long g_la_stats[4] = {0, 0, 0, 0};   // plans served by the look-ahead stream, inline plans, stream starts, drops
+static long long g_la_stats[4] = {0, 0, 0, 0};
+static Lookahead g_la;
+static std::mutex g_la_mu;   // plans served by the look-ahead stream, inline plans, stream starts, drops
 // Diagnostics: counters of the generator look-ahead (see Lookahead): out[4] = stream plans, inline plans, starts, drops.
 extern "C" int dcl_host_plan_timing(long long* out) {
     if (!out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
@@ -423,10 +438,11 @@ extern "C" int dcl_host_lookahead_stats(long long* out) {
     for (int i = 0; i < 4; ++i) out[i] = g_la_stats[i];
     return 0;
 }
-static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignore_label, int max_samples,
-                     int max_views, void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
-                     int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard, int64_t* ranks,
-                     int32_t* req, int32_t* y_all, int64_t* ref_row, int64_t* anchor) {
+int dcl::plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignore_label, int max_samples,
+                   int max_views, void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                   int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard, int64_t* ranks,
+                   int32_t* req, int32_t* y_all, int64_t* ref_row, int64_t* anchor, DevicePlan* dp) {
+    if (dp) dp->taken = 0;
     if (!counts || !info || Bl <= 0 || world <= 0 || rank < 0 || rank >= world) return dcl::fail(DCL_ERR_ARG, "bad argument");
     const int B = Bl * world;
     const long long t_start = now_ns();
@@ -457,16 +473,16 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
     }
     const int lo = rank * Bl, hi = lo + Bl;
     g_plan_ns[0] = now_ns() - t_start;                       // anchor list + split rule
+    bool device_mode = false;
     if (n_view > 0) {
         Mt m;
         if (int e = load_state(torch_rng_state, state_bytes, m)) return e;
         // Look-ahead policy: the stream is used while the generator is exactly where the previous plan left it.
         // A mismatch (manual_seed, other draws) drops to the inline replay; the stream is (re)started after a plan
         // that found the generator untouched, so loops that reseed every step never pay for a useless worker.
-        static Lookahead la;
-        static std::mutex la_mu;
+        Lookahead& la = g_la;
         static const bool la_enabled = [] { const char* e = std::getenv("DCL_HOST_LOOKAHEAD"); return !(e && e[0] == '0'); }();
-        std::lock_guard<std::mutex> la_lock(la_mu);
+        std::lock_guard<std::mutex> la_lock(g_la_mu);
         const uint8_t* raw = static_cast<const uint8_t*>(torch_rng_state);
         const bool continuous = la_enabled && la.matches(raw);
         // the ring is only refilled when a plan commits: a plan longer than the ring has to run inline
@@ -495,11 +511,56 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
                                  (long long)kh, (long long)ke, (long long)num_hard[a], (long long)num_easy[a]);
             n_local += image[a] >= lo && image[a] < hi;
         }
-        const int threads = m.la ? std::min(n_local, host_threads(static_cast<int64_t>(n_local) * n_view)) : 1;
-        if (threads > 1) {
-            // Stream mode: randperm(n) consumes n - 1 draws whatever its outcome, so every anchor's position in the
-            // stream is known up front.  One cheap pass records the generator at the start of each local anchor
-            // (and leaves `m` where the whole plan ends); the permutations themselves then run in parallel.
+        // Device mode: with the stream attached every permutation's position in the generator's output is known
+        // without drawing it (randperm(n) consumes n - 1 draws whatever its outcome), so the host only records
+        // where each local permutation starts and advances the generator; k_plan (dcl_plan.cu) replays the kept
+        // prefixes on the GPU from its mirror of the same stream blocks.
+        device_mode = dp && m.la && n_view <= dcl::kMaxDeviceViews;
+        const int threads = (m.la && !device_mode) ? std::min(n_local, host_threads(static_cast<int64_t>(n_local) * n_view)) : 1;
+        // draw index of the generator's next output, counted from word 0 of stream block 0
+        auto gabs = [](const Mt& g) -> uint64_t {
+            return g.left > 1 ? g.blk * static_cast<uint64_t>(kN) + g.next : (g.blk + 1) * static_cast<uint64_t>(kN);
+        };
+        if (device_mode) {
+            int li = 0;
+            uint64_t g_first = ~0ull, g_last = 0;
+            for (int a = 0; a < A; ++a) {
+                const bool local = image[a] >= lo && image[a] < hi;
+                const uint64_t gh = gabs(m);
+                if (num_hard[a] > 1) skip(m, num_hard[a] - 1);
+                const uint64_t ge = gabs(m);
+                if (num_easy[a] > 1) skip(m, num_easy[a] - 1);
+                if (local) {
+                    dcl::PlanAnchor& pa = dp->anchors[li++];
+                    pa.g_hard = gh;
+                    pa.g_easy = ge;
+                    pa.num_hard = static_cast<int32_t>(num_hard[a]);
+                    pa.num_easy = static_cast<int32_t>(num_easy[a]);
+                    pa.keep_hard = static_cast<int32_t>(keep_hard[a]);
+                    pa.keep_easy = static_cast<int32_t>(n_view - keep_hard[a]);
+                    pa.row0 = 0;                               // set with the layout below
+                    pa.image = static_cast<int32_t>(image[a] - lo);
+                    pa.cls = static_cast<int32_t>(cls[a]);
+                    pa.reserved = a;                           // anchor id, resolved to row0 below
+                    if (gh < g_first) g_first = gh;
+                    const uint64_t end = ge + static_cast<uint64_t>(pa.keep_easy > 0 ? pa.keep_easy : 0);
+                    const uint64_t endh = gh + static_cast<uint64_t>(pa.keep_hard > 0 ? pa.keep_hard : 0);
+                    if (end > g_last) g_last = end;
+                    if (endh > g_last) g_last = endh;
+                }
+            }
+            dp->n_local_anchors = li;
+            dp->first_block = li ? g_first / kN : la.position();
+            dp->last_block = li ? g_last / kN : la.position();
+            uint64_t seen = 0;
+            la.block(dp->last_block, seen);                    // the worker has produced every block the device reads
+            dp->epoch = la.epoch();
+            dp->host_ring = la.ring();
+            dp->ring_blocks = Lookahead::kRing;
+            dp->taken = 1;
+        } else if (threads > 1) {
+            // Stream mode: one cheap pass records the generator at the start of each local anchor (and leaves `m`
+            // where the whole plan ends); the permutations themselves then run in parallel.
             std::vector<Mt> at(static_cast<size_t>(n_local));
             std::vector<int> which(static_cast<size_t>(n_local));
             int li = 0;
@@ -533,18 +594,19 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
         g_plan_ns[2] = now_ns() - t_start;                   // + permutations
         store_state(torch_rng_state, m);
         if (m.la) {
-            la.commit(m.blk, raw);
+            la.commit(m.blk, raw, device_mode ? dp->first_block : m.blk);
         } else {
             if (continuous && fits) {
                 uint32_t words[kN];
                 for (int i = 0; i < kN; ++i) words[i] = m.s[i];
                 la.restart(words);                 // generator untouched since the last plan: stream from here on
                 ++g_la_stats[2];
-                la.commit(0, raw);
+                la.commit(0, raw, 0);
             } else {
                 la.expect(raw);
             }
         }
+        if (dp) dp->produced = la.active() ? la.produced() : 0;
     }
     g_plan_ns[3] = now_ns() - t_start;                       // + state write-back, look-ahead commit
     // rows per rank -> common padded block size
@@ -555,10 +617,12 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
     int n_pad = (n_max + 127) / 128 * 128;
     if (n_pad < 128) n_pad = 128;
     info[2] = per_rank[rank]; info[3] = n_pad; info[4] = n_global;
-    if (!y_all) y_all = req + static_cast<size_t>(4) * n_pad;      // compact form: labels right behind the requests
+    if (!y_all && req) y_all = req + static_cast<size_t>(4) * n_pad;      // compact form: labels right behind the requests
     // rows of every rank block: anchors of that rank stably sorted by class (counting sort), views contiguous;
     // labels for all blocks (y_all), requests / bookkeeping for the local block only
     std::vector<int> start(257), order(A);
+    std::vector<int> row0_of(device_mode ? A : 0);
+    int yo = 0;
     for (int r = 0; r < world; ++r) {
         std::fill(start.begin(), start.end(), 0);
         const int rlo = r * Bl, rhi = rlo + Bl;
@@ -568,6 +632,19 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
         for (int c = 0; c < 256; ++c) start[c + 1] += start[c];
         for (int a = 0; a < A; ++a)
             if (image[a] >= rlo && image[a] < rhi) order[start[cls[a]]++] = a;
+        if (dp) {
+            // the class-sorted anchor order of every rank block (what k_plan needs for the labels, and what the
+            // caller needs to map device rows back to the reference's row order)
+            dp->ycnt[r] = cnt;
+            dp->yoff[r] = yo;
+            for (int o = 0; o < cnt; ++o) {
+                dp->ycls[yo + o] = static_cast<int32_t>(cls[order[o]]);
+                dp->yanchor[yo + o] = order[o];
+                if (device_mode && r == rank) row0_of[order[o]] = o * n_view;
+            }
+            yo += cnt;
+        }
+        if (device_mode) continue;                           // k_plan writes the rows
         int32_t* yb = y_all + static_cast<size_t>(r) * n_pad;
         auto fill_anchor = [&](int o) {
             const int a = order[o];
@@ -580,8 +657,8 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
                     req[row * 4 + 1] = static_cast<int32_t>(cls[a]);
                     req[row * 4 + 2] = v >= keep_hard[a];
                     req[row * 4 + 3] = static_cast<int32_t>(rk[v]);
-                    ref_row[row] = static_cast<int64_t>(v) * A + a;
-                    anchor[row] = a;
+                    if (ref_row) ref_row[row] = static_cast<int64_t>(v) * A + a;
+                    if (anchor) anchor[row] = a;
                 }
             }
         };
@@ -592,11 +669,17 @@ static int plan_rows(const int32_t* counts, int Bl, int world, int rank, int ign
             yb[row] = -1;
             if (r == rank) {
                 req[row * 4 + 0] = req[row * 4 + 1] = req[row * 4 + 2] = req[row * 4 + 3] = -1;
-                ref_row[row] = -1;
-                anchor[row] = -1;
+                if (ref_row) ref_row[row] = -1;
+                if (anchor) anchor[row] = -1;
             }
         }
     }
+    if (device_mode)
+        for (int i = 0; i < dp->n_local_anchors; ++i) {
+            dcl::PlanAnchor& pa = dp->anchors[i];
+            pa.row0 = row0_of[pa.reserved];
+            pa.reserved = 0;
+        }
     g_plan_ns[4] = now_ns() - t_start;                       // + row requests / labels
     return 0;
 }
@@ -614,8 +697,8 @@ extern "C" int dcl_host_plan_rows(const int32_t* counts, int B, int ignore_label
                                   int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard,
                                   int64_t* ranks, int32_t* req, int32_t* y, int64_t* ref_row, int64_t* anchor) {
     int32_t inf[6];
-    const int rc = plan_rows(counts, B, 1, 0, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, inf,
-                             image, cls, num_hard, num_easy, keep_hard, ranks, req, y, ref_row, anchor);
+    const int rc = dcl::plan_rows(counts, B, 1, 0, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, inf,
+                                  image, cls, num_hard, num_easy, keep_hard, ranks, req, y, ref_row, anchor, nullptr);
     if (info) for (int i = 0; i < 4; ++i) info[i] = inf[i];
     return rc;
 }
@@ -628,8 +711,33 @@ extern "C" int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int wor
                                           int32_t* info, int64_t* image, int64_t* cls, int64_t* num_hard,
                                           int64_t* num_easy, int64_t* keep_hard, int64_t* ranks, int32_t* req,
                                           int32_t* y_all, int64_t* ref_row, int64_t* anchor) {
-    return plan_rows(counts, Bl, world, rank, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, info,
-                     image, cls, num_hard, num_easy, keep_hard, ranks, req, y_all, ref_row, anchor);
+    return dcl::plan_rows(counts, Bl, world, rank, ignore_label, max_samples, max_views, torch_rng_state, state_bytes, info,
+                          image, cls, num_hard, num_easy, keep_hard, ranks, req, y_all, ref_row, anchor, nullptr);
+}
+
+// Diagnostics / tests (host only): plan_rows with the device-plan descriptors requested, as dcl_step_fwd calls it.
+// When meta[0] comes back 1 the host did not draw the permutations: `anchors` (48-byte PlanAnchor records, see
+// dcl_plan.h) place them in the look-ahead stream, whose ring (raw mt19937 state blocks, block b at
+// ring + (b % ring_blocks) * 624 words) is returned through ring_out.  meta [8]: taken, local anchors, epoch,
+// first block, last block, ring blocks, produced, -.
+extern "C" int dcl_debug_plan_device(const int32_t* counts, int Bl, int world, int rank, int ignore_label,
+                                     int max_samples, int max_views, void* torch_rng_state, size_t state_bytes,
+                                     int32_t* info, int64_t* image, int64_t* cls, int64_t* num_hard,
+                                     int64_t* num_easy, int64_t* keep_hard, int64_t* ranks, int32_t* req,
+                                     int32_t* y_all, void* anchors, int32_t* ycls, int32_t* yanchor, int32_t* ycnt,
+                                     int32_t* yoff, long long* meta, const void** ring_out) {
+    if (!anchors || !ycls || !yanchor || !ycnt || !yoff || !meta || !ring_out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
+    dcl::DevicePlan dp{};
+    dp.anchors = static_cast<dcl::PlanAnchor*>(anchors);
+    dp.ycls = ycls; dp.yanchor = yanchor; dp.ycnt = ycnt; dp.yoff = yoff;
+    const int rc = dcl::plan_rows(counts, Bl, world, rank, ignore_label, max_samples, max_views, torch_rng_state,
+                                  state_bytes, info, image, cls, num_hard, num_easy, keep_hard, ranks, req, y_all,
+                                  nullptr, nullptr, &dp);
+    meta[0] = dp.taken; meta[1] = dp.n_local_anchors; meta[2] = static_cast<long long>(dp.epoch);
+    meta[3] = static_cast<long long>(dp.first_block); meta[4] = static_cast<long long>(dp.last_block);
+    meta[5] = static_cast<long long>(dp.ring_blocks); meta[6] = static_cast<long long>(dp.produced); meta[7] = 0;
+    *ring_out = dp.host_ring;
+    return rc;
 }
 
 extern "C" int dcl_host_sample_ranks(void* torch_rng_state, size_t state_bytes, int A, int n_view,

@@ -154,7 +154,7 @@ __device__ __forceinline__ void tmem_st_wait() {
 
 // smem -> TMEM copy of 128 rows x 32 bytes described by a matrix descriptor.  With the K-slice descriptors of an
 // F-tile (ftile_desc_kmajor) eight of these produce exactly the TS-form A operand layout (lane = row, 32-bit
-// column c = bf16 pair 2c, 2c+1): csrc/probe_tmem_cp.cu.  Executes in issue order with tcgen05.mma.
+// column c = bf16 pair 2c, 2c+1): tools/probes/probe_tmem_cp.cu.  Executes in issue order with tcgen05.mma.
 __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }

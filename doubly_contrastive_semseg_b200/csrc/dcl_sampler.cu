@@ -209,6 +209,7 @@ k_gather(const float* __restrict__ src, int hw, const int32_t* __restrict__ pix,
     if (lane == 0) sqnorm[n] = sq;
 }
 
+template <bool kAdd>
 __global__ void __launch_bounds__(256)
 k_scatter(const float* __restrict__ dF, const int32_t* __restrict__ pix, int n_rows,
           const float* __restrict__ grad_out, float* __restrict__ dfeats, int hw) {
@@ -221,10 +222,20 @@ k_scatter(const float* __restrict__ dF, const int32_t* __restrict__ pix, int n_r
     const float4 v = __ldg(reinterpret_cast<const float4*>(dF + static_cast<size_t>(n) * kDim + lane * 4));
     const int b = pid / hw, p = pid - b * hw;
     float* o = dfeats + (static_cast<size_t>(b) * kDim + lane * 4) * hw + p;
-    o[0] = v.x * g;
-    o[static_cast<size_t>(hw)] = v.y * g;
-    o[static_cast<size_t>(hw) * 2] = v.z * g;
-    o[static_cast<size_t>(hw) * 3] = v.w * g;
+    if (kAdd) {
+        // sampled pixels are distinct: every (pixel, channel) element has one writer
+        const float a0 = o[0], a1 = o[static_cast<size_t>(hw)], a2 = o[static_cast<size_t>(hw) * 2],
+                    a3 = o[static_cast<size_t>(hw) * 3];
+        o[0] = fmaf(v.x, g, a0);
+        o[static_cast<size_t>(hw)] = fmaf(v.y, g, a1);
+        o[static_cast<size_t>(hw) * 2] = fmaf(v.z, g, a2);
+        o[static_cast<size_t>(hw) * 3] = fmaf(v.w, g, a3);
+    } else {
+        o[0] = v.x * g;
+        o[static_cast<size_t>(hw)] = v.y * g;
+        o[static_cast<size_t>(hw) * 2] = v.z * g;
+        o[static_cast<size_t>(hw) * 3] = v.w * g;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -361,10 +372,11 @@ extern "C" int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows,
     if (int e = dcl_check_device()) return e;
     if (!dF || !pix || !grad_out || !dfeats) return fail(DCL_ERR_ARG, "null pointer argument");
     if (n_rows < 0 || B <= 0 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
-    if (zero_fill)
+    if (zero_fill == 1)
         DCL_CUDA(cudaMemsetAsync(dfeats, 0, static_cast<size_t>(B) * kDim * hw * sizeof(float), as_stream(stream)));
     if (n_rows == 0) return 0;
-    k_scatter<<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(dF, pix, n_rows, grad_out, dfeats, hw);
+    if (zero_fill == 2) k_scatter<true><<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(dF, pix, n_rows, grad_out, dfeats, hw);
+    else k_scatter<false><<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(dF, pix, n_rows, grad_out, dfeats, hw);
     DCL_LAUNCH_CHECK("k_scatter");
     return 0;
 }

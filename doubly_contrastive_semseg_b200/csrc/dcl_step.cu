@@ -1,102 +1,298 @@
-// One-call forms of the pixel term's forward and backward (host glue only: every stage is one of the entry points
-// of dcl_sampler.cu / dcl_host_rng.cpp / dcl_contrast.cu).  At the headline size the step is bound by the host's
-// issue time, and most of that was the interpreter walking from one entry point to the next; here the whole chain
-//   classify -> count table D2H -> (zero-fill || host plan) -> requests H2D -> select -> gather -> N x N forward
-// is issued from C with a single wait (the count table), reference utils/loss.py:391-415 -> :250-389.
+// PixelContrastLoss.forward (+ its gradient) as ONE host call, single GPU or one rank of a sharded job
+// (reference utils/loss.py:391-415 -> :250-389; the sharding has no reference counterpart):
+//
+//   classify -> [all-gather of the count tables] -> count table D2H          (side stream: zero-fill of d feats)
+//   -> the one host wait -> plan on the host (anchor list, n_view, split rule; O(#anchors)) -> permutations:
+//        k_plan on the GPU from the mirrored generator stream, or the host replay when the generator was touched
+//   -> select -> gather -> [all-gather of the F-tiles] -> N x N forward -> [all-gather of the row constants]
+//   -> N x N backward (dF of the local rows, for an upstream gradient of 1)
+//
+// The backward of the similarity is issued here, eagerly: the gradient is linear in the upstream scalar, so the
+// autograd backward only has to scale dF while scattering it (dcl_step_bwd).  The GPU therefore always has the
+// whole chain queued while the host goes through the autograd hand-over, which at the headline size used to cost
+// more than the kernels themselves.
+#include <chrono>
 #include <cstdint>
+#include <cstring>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "dcl_common.cuh"
+#include "dcl_plan.h"
 
 using namespace dcl;
 
-namespace {
-cudaEvent_t count_event() {
-    static thread_local cudaEvent_t ev = nullptr;
-    static thread_local int ev_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (ev && ev_dev != dev) { cudaEventDestroy(ev); ev = nullptr; }
-    if (!ev) {
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
-        ev_dev = dev;
-    }
-    return ev;
+namespace dcl {
+int comm_all_gather(void* comm, const void* send, void* recv, size_t bytes, cudaStream_t st);
 }
-}  // namespace
 
-// First half: everything that does not depend on the host plan.  Issued as early as possible so that the caller's
-// remaining preparation (allocations, generator state, descriptor) overlaps the classification on the GPU.
-extern "C" int dcl_pixel_begin(const int64_t* labels, const float* predict, int B, int H, int W, int h, int w, int C_cls,
-                               uint16_t* code, int32_t* chunk_hist, int32_t* counts_dev, int32_t* counts_host,
-                               void* zero_fill, size_t zero_fill_bytes, void* stream) {
-    if (int e = dcl_check_device()) return e;
-    if (!counts_host) return fail(DCL_ERR_ARG, "null pointer argument");
-    cudaStream_t st = as_stream(stream);
-    cudaEvent_t ev = count_event();
-    if (!ev) return fail(DCL_ERR_ARG, "cannot create a CUDA event");
-    if (int e = dcl_sample_classify(labels, predict, B, H, W, h, w, C_cls, code, chunk_hist, counts_dev, stream)) return e;
-    DCL_CUDA(cudaMemcpyAsync(counts_host, counts_dev, sizeof(int32_t) * 512 * B, cudaMemcpyDeviceToHost, st));
-    DCL_CUDA(cudaEventRecord(ev, st));
-    if (zero_fill && zero_fill_bytes)                  // runs on the GPU while the host plans
-        DCL_CUDA(cudaMemsetAsync(zero_fill, 0, zero_fill_bytes, st));
+namespace {
+
+constexpr int kMaxDevices = 64;
+
+struct PerDevice {
+    cudaEvent_t ev_counts = nullptr;      // count table has reached the host
+    cudaEvent_t ev_fork = nullptr;        // main stream position at the start of a step (side stream waits for it)
+    cudaEvent_t ev_zero = nullptr;        // zero-fill done (main stream waits for it before the step ends)
+    // device mirror of the host generator look-ahead (raw mt19937 state blocks)
+    uint32_t* d_ring = nullptr;
+    uint64_t ring_blocks = 0, epoch = ~0ull, up_hi = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_used = nullptr;
+    bool used_recorded = false;
+    uint64_t last_window = 0;
+};
+PerDevice g_dev[kMaxDevices];
+std::mutex g_mu;
+// diagnostics: host nanoseconds of the last dcl_step_fwd at the end of each of its sections (dcl_step_timing)
+long long g_step_ns[12] = {0};
+inline long long now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int device_slot(PerDevice*& pd) {
+    int dev = 0;
+    DCL_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(DCL_ERR_ARG, "device ordinal %d out of range", dev);
+    pd = &g_dev[dev];
+    if (!pd->ev_counts) {
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_counts, cudaEventDisableTiming));
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_fork, cudaEventDisableTiming));
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_zero, cudaEventDisableTiming));
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_up, cudaEventDisableTiming));
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_used, cudaEventDisableTiming));
+        DCL_CUDA(cudaStreamCreateWithFlags(&pd->copy, cudaStreamNonBlocking));
+    }
     return 0;
 }
 
-extern "C" int dcl_pixel_fwd(const dcl_pixel_step_t* s, void* stream) {
+// Make stream blocks [first, last] of the look-ahead readable on the device before anything later on `st`, and
+// push the blocks the next step will probably need behind them (the upload then overlaps this step's kernels).
+// Block b lives in slot b % ring_blocks on both sides.  A slot is overwritten only by block b + ring_blocks, i.e.
+// never by anything the current window needs; kernels of earlier steps that may still read the old content are
+// ordered before the copy through ev_used.
+int mirror_window(PerDevice& pd, const DevicePlan& dp, cudaStream_t st) {
+    if (!pd.d_ring) {
+        pd.ring_blocks = dp.ring_blocks;
+        DCL_CUDA(cudaMalloc(&pd.d_ring, sizeof(uint32_t) * kMtWords * pd.ring_blocks));
+    }
+    if (pd.ring_blocks != dp.ring_blocks) return fail(DCL_ERR_ARG, "generator ring size changed");
+    if (pd.epoch != dp.epoch || dp.first_block > pd.up_hi || dp.first_block + pd.ring_blocks <= pd.up_hi) {
+        pd.epoch = dp.epoch;                              // stream restarted (or a gap): nothing uploaded is usable
+        pd.up_hi = dp.first_block;
+    }
+    const uint64_t window = dp.last_block - dp.first_block + 1;
+    uint64_t target = dp.last_block + 1 + window + window / 4 + 16;          // this window and a guess at the next
+    if (target > dp.produced) target = dp.produced;
+    if (target < dp.last_block + 1) target = dp.last_block + 1;
+    if (target > dp.first_block + pd.ring_blocks - 8) target = dp.first_block + pd.ring_blocks - 8;
+    if (target < dp.last_block + 1) return fail(DCL_ERR_ARG, "plan window of %llu blocks exceeds the generator ring",
+                                                static_cast<unsigned long long>(window));
+    if (target > pd.up_hi) {
+        if (pd.used_recorded) DCL_CUDA(cudaStreamWaitEvent(pd.copy, pd.ev_used, 0));
+        uint64_t b = pd.up_hi;
+        while (b < target) {
+            const uint64_t slot = b % pd.ring_blocks;
+            uint64_t n = target - b;
+            if (n > pd.ring_blocks - slot) n = pd.ring_blocks - slot;
+            DCL_CUDA(cudaMemcpyAsync(pd.d_ring + slot * kMtWords, dp.host_ring + slot * kMtWords,
+                                     sizeof(uint32_t) * kMtWords * n, cudaMemcpyHostToDevice, pd.copy));
+            b += n;
+        }
+        DCL_CUDA(cudaEventRecord(pd.ev_up, pd.copy));
+        pd.up_hi = target;
+    }
+    DCL_CUDA(cudaStreamWaitEvent(st, pd.ev_up, 0));
+    pd.last_window = window;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t dcl_step_plan_bytes(int B_local, int world) {
+    if (B_local <= 0 || world <= 0) return 0;
+    const size_t A_cap = static_cast<size_t>(B_local) * world * 256;
+    // [ycnt world][yoff world][ycls A_cap] | [anchors B_local*256] | [yanchor A_cap] (host only)
+    size_t o = sizeof(int32_t) * (2 * static_cast<size_t>(world) + A_cap);
+    o = (o + 63) / 64 * 64;
+    o += sizeof(PlanAnchor) * static_cast<size_t>(B_local) * 256;
+    o = (o + 63) / 64 * 64;
+    o += sizeof(int32_t) * A_cap;
+    return o;
+}
+
+extern "C" int dcl_step_begin(const dcl_step_t* s, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!s) return fail(DCL_ERR_ARG, "null step descriptor");
-    if (!s->labels || !s->predict || !s->feats || !s->code || !s->chunk_hist || !s->counts_dev || !s->counts_host ||
-        !s->stage_host || !s->stage_dev || !s->info || !s->pix || !s->tiles || !s->sqnorm || !s->colA || !s->colB ||
-        !s->rowloss || !s->loss_sum || !s->workspace)
+    if (!s->labels || !s->predict || !s->code || !s->chunk_hist || !s->counts_dev || !s->counts_host)
         return fail(DCL_ERR_ARG, "null pointer in step descriptor");
+    if (s->world <= 0 || s->rank < 0 || s->rank >= s->world || (s->world > 1 && !s->comm))
+        return fail(DCL_ERR_ARG, "bad sharding (world=%d rank=%d)", s->world, s->rank);
+    std::lock_guard<std::mutex> lock(g_mu);
+    PerDevice* pd = nullptr;
+    if (int e = device_slot(pd)) return e;
+    cudaStream_t st = as_stream(stream);
+    const size_t table = static_cast<size_t>(512) * s->B;                       // ints per rank
+    int32_t* mine = s->counts_dev + table * s->rank;
+    if (s->zero_fill && s->zero_fill_bytes) {
+        // the dense gradient buffer is cleared off the critical path: on the side stream when there is one (the
+        // buffer was allocated on `st`, so the side stream first waits for st's current position)
+        if (s->side_stream) {
+            cudaStream_t side = as_stream(s->side_stream);
+            DCL_CUDA(cudaEventRecord(pd->ev_fork, st));
+            DCL_CUDA(cudaStreamWaitEvent(side, pd->ev_fork, 0));
+            DCL_CUDA(cudaMemsetAsync(s->zero_fill, 0, s->zero_fill_bytes, side));
+            DCL_CUDA(cudaEventRecord(pd->ev_zero, side));
+        }
+    }
+    if (int e = dcl_sample_classify(s->labels, s->predict, s->B, s->H, s->W, s->h, s->w, s->C_cls, s->code, s->chunk_hist,
+                                    mine, stream))
+        return e;
+    if (s->world > 1)
+        if (int e = comm_all_gather(s->comm, mine, s->counts_dev, table * sizeof(int32_t), st)) return e;
+    DCL_CUDA(cudaMemcpyAsync(s->counts_host, s->counts_dev, sizeof(int32_t) * table * s->world, cudaMemcpyDeviceToHost, st));
+    DCL_CUDA(cudaEventRecord(pd->ev_counts, st));
+    if (s->zero_fill && s->zero_fill_bytes && !s->side_stream)
+        DCL_CUDA(cudaMemsetAsync(s->zero_fill, 0, s->zero_fill_bytes, st));    // still overlaps the host's plan
+    return 0;
+}
+
+extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!s) return fail(DCL_ERR_ARG, "null step descriptor");
+    if (!s->feats || !s->req_dev || !s->y_dev || !s->pix || !s->plan_dev || !s->plan_host || !s->stage_host || !s->tiles ||
+        !s->sqnorm || !s->colA || !s->colB || !s->rowloss || !s->loss_sum || !s->loss || !s->workspace || !s->info ||
+        !s->image || !s->cls || !s->num_hard || !s->num_easy || !s->keep_hard || !s->ranks || !s->torch_rng_state)
+        return fail(DCL_ERR_ARG, "null pointer in step descriptor");
+    if (s->world > 1 && (!s->xchg_send || !s->xchg_recv)) return fail(DCL_ERR_ARG, "sharded step without exchange buffers");
     const int cap_min = (s->max_samples + DCL_TILE_ROWS - 1) / DCL_TILE_ROWS * DCL_TILE_ROWS;
     if (s->B <= 0 || s->h <= 0 || s->w <= 0 || s->cap < cap_min || s->cap < DCL_TILE_ROWS || s->cap % DCL_TILE_ROWS)
         return fail(DCL_ERR_ARG, "bad step shape (B=%d h=%d w=%d cap=%d max_samples=%d)", s->B, s->h, s->w, s->cap, s->max_samples);
+    if (s->plan_bytes < dcl_step_plan_bytes(s->B, s->world)) return fail(DCL_ERR_ARG, "plan buffer too small");
     cudaStream_t st = as_stream(stream);
-    cudaEvent_t ev = count_event();
-    if (!ev) return fail(DCL_ERR_ARG, "cannot create a CUDA event");
-    const int hw = s->h * s->w;
-    if (!s->begun) {
-        if (int e = dcl_pixel_begin(s->labels, s->predict, s->B, s->H, s->W, s->h, s->w, s->C_cls, s->code, s->chunk_hist,
-                                    s->counts_dev, s->counts_host, s->zero_fill, s->zero_fill_bytes, stream))
-            return e;
+    const long long t0 = now_ns();
+    if (!s->begun)
+        if (int e = dcl_step_begin(s, stream)) return e;
+    g_step_ns[0] = now_ns() - t0;                            // classify, count table copy, zero-fill issued
+    std::lock_guard<std::mutex> lock(g_mu);
+    PerDevice* pd = nullptr;
+    if (int e = device_slot(pd)) return e;
+    const int world = s->world, rank = s->rank, hw = s->h * s->w;
+    const int Bg = s->B * world;
+    DCL_CUDA(cudaEventSynchronize(pd->ev_counts));           // the one unavoidable wait: the count table
+    // the previous step's upload of generator blocks has left the host ring (it completed before that step's
+    // k_plan ran, which precedes this step's classify on the same stream; a caller that switched streams waits here)
+    DCL_CUDA(cudaEventSynchronize(pd->ev_up));
+    g_step_ns[1] = now_ns() - t0;                            // + wait for the count table
+    // labels outside 0..255 cannot be coded (the reference would treat them as classes of their own): refuse
+    // instead of silently dropping them.  Every pixel lands in exactly one of the 512 bins otherwise.
+    for (int b = 0; b < Bg; ++b) {
+        long long tot = 0;
+        const int32_t* c = s->counts_host + static_cast<size_t>(b) * 512;
+        for (int i = 0; i < 512; ++i) tot += c[i];
+        if (tot != hw) return fail(DCL_ERR_LABEL, "image %d has %lld pixels whose label is outside 0..255", b, hw - tot);
     }
-    DCL_CUDA(cudaEventSynchronize(ev));                // the one unavoidable wait: the count table
-    int32_t* req = s->stage_host;
-    int32_t* y = s->stage_host + static_cast<size_t>(s->cap) * 4;
-    const int rc = dcl_host_plan_rows(s->counts_host, s->B, s->ignore_label, s->max_samples, s->max_views,
-                                      s->torch_rng_state, s->state_bytes, s->info, s->image, s->cls, s->num_hard,
-                                      s->num_easy, s->keep_hard, s->ranks, req, y, s->ref_row, s->anchor);
-    if (rc != 0) return rc;                            // 1: no class qualifies, 2: the reference's unreachable branch
-    const int n_view = s->info[1], n = s->info[2], n_pad = s->info[3];
-    if (n_view <= 0) return 3;                         // max_samples // total_classes == 0 (reference fails in torch.cat)
-    if (n_pad > s->cap) return fail(DCL_ERR_ARG, "plan needs %d rows, capacity is %d", n_pad, s->cap);
-    int32_t* req_dev = s->stage_dev;
-    int32_t* y_dev = s->stage_dev + static_cast<size_t>(s->cap) * 4;
-    DCL_CUDA(cudaMemcpyAsync(req_dev, req, sizeof(int32_t) * 4 * n_pad, cudaMemcpyHostToDevice, st));
-    DCL_CUDA(cudaMemcpyAsync(y_dev, y, sizeof(int32_t) * n_pad, cudaMemcpyHostToDevice, st));
-    if (int e = dcl_sample_select(s->code, s->chunk_hist, s->B, hw, req_dev, n_pad, s->pix, stream)) return e;
-    if (int e = dcl_gather_tiles(s->feats, s->B, hw, s->pix, n_pad, s->tiles, s->sqnorm, stream)) return e;
-    const int nJ = n_pad / DCL_TILE_ROWS;
-    if (s->ev_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_begin), st));
-    if (int e = dcl_contrast_fwd(s->tiles, y_dev, s->sqnorm, nJ, 0, nJ, n, DCL_MODE_PIXEL, s->temperature,
+    // plan buffer: [ycnt | yoff | ycls] [anchors] [yanchor]
+    const size_t A_cap = static_cast<size_t>(Bg) * 256;
+    uint8_t* ph = static_cast<uint8_t*>(s->plan_host);
+    uint8_t* pdv = static_cast<uint8_t*>(s->plan_dev);
+    size_t o_anchor = sizeof(int32_t) * (2 * static_cast<size_t>(world) + A_cap);
+    o_anchor = (o_anchor + 63) / 64 * 64;
+    size_t o_yanchor = o_anchor + sizeof(PlanAnchor) * static_cast<size_t>(s->B) * 256;
+    o_yanchor = (o_yanchor + 63) / 64 * 64;
+    DevicePlan dp{};
+    dp.ycnt = reinterpret_cast<int32_t*>(ph);
+    dp.yoff = dp.ycnt + world;
+    dp.ycls = dp.yoff + world;
+    dp.anchors = reinterpret_cast<PlanAnchor*>(ph + o_anchor);
+    dp.yanchor = reinterpret_cast<int32_t*>(ph + o_yanchor);
+    int32_t* req_h = s->stage_host;
+    int32_t* y_h = s->stage_host + static_cast<size_t>(s->cap) * 4;
+    int32_t inf[6] = {0, 0, 0, 0, 0, 0};
+    const int rc = plan_rows(s->counts_host, s->B, world, rank, s->ignore_label, s->max_samples, s->max_views,
+                             s->torch_rng_state, s->state_bytes, inf, s->image, s->cls, s->num_hard, s->num_easy,
+                             s->keep_hard, s->ranks, req_h, y_h, nullptr, nullptr, s->device_plan ? &dp : nullptr);
+    for (int i = 0; i < 5; ++i) s->info[i] = inf[i];
+    s->info[5] = dp.taken;
+    g_step_ns[2] = now_ns() - t0;                            // + host plan
+    if (rc != 0) return rc;                                  // 1: no class qualifies, 2: the reference's unreachable branch
+    const int A = inf[0], n_view = inf[1], n_pad = inf[3], n_global = inf[4];
+    if (n_view <= 0) return 3;                               // max_samples // total_classes == 0 (reference fails in torch.cat)
+    if (n_pad > s->cap) return fail(DCL_ERR_ARG, "plan needs %d rows per rank, capacity is %d", n_pad, s->cap);
+    if (dp.taken) {
+        if (int e = mirror_window(*pd, dp, st)) return e;
+        g_step_ns[3] = now_ns() - t0;                        // + generator blocks queued for upload
+        DCL_CUDA(cudaMemcpyAsync(pdv, ph, sizeof(int32_t) * (2 * static_cast<size_t>(world) + A), cudaMemcpyHostToDevice, st));
+        if (dp.n_local_anchors)
+            DCL_CUDA(cudaMemcpyAsync(pdv + o_anchor, ph + o_anchor, sizeof(PlanAnchor) * dp.n_local_anchors,
+                                     cudaMemcpyHostToDevice, st));
+        const int32_t* d_ycnt = reinterpret_cast<const int32_t*>(pdv);
+        if (int e = launch_plan(pd->d_ring, pd->ring_blocks, reinterpret_cast<const PlanAnchor*>(pdv + o_anchor),
+                                dp.n_local_anchors, d_ycnt + 2 * world, d_ycnt, d_ycnt + world, world, rank, n_view,
+                                n_pad, s->req_dev, s->y_dev, stream))
+            return e;
+        DCL_CUDA(cudaEventRecord(pd->ev_used, st));
+        pd->used_recorded = true;
+    } else {
+        DCL_CUDA(cudaMemcpyAsync(s->req_dev, req_h, sizeof(int32_t) * 4 * n_pad, cudaMemcpyHostToDevice, st));
+        DCL_CUDA(cudaMemcpyAsync(s->y_dev, y_h, sizeof(int32_t) * static_cast<size_t>(world) * n_pad, cudaMemcpyHostToDevice, st));
+    }
+    g_step_ns[4] = now_ns() - t0;                            // + plan kernel / row copies issued
+    if (int e = dcl_sample_select(s->code, s->chunk_hist, s->B, hw, s->req_dev, n_pad, s->pix, stream)) return e;
+    const size_t tile_bytes = static_cast<size_t>(n_pad) * DCL_DIM * 2;
+    uint8_t* tl = static_cast<uint8_t*>(s->tiles) + tile_bytes * rank;
+    if (int e = dcl_gather_tiles(s->feats, s->B, hw, s->pix, n_pad, tl, s->sqnorm + static_cast<size_t>(rank) * n_pad, stream))
+        return e;
+    if (world > 1)
+        if (int e = comm_all_gather(s->comm, tl, s->tiles, tile_bytes, st)) return e;
+    const int nI = n_pad / DCL_TILE_ROWS, nJ = nI * world, rb0 = nI * rank;
+    if (s->ev_fwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_begin), st));
+    if (int e = dcl_contrast_fwd(s->tiles, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
                                  s->base_temperature, s->workspace, s->workspace_bytes, s->colA, s->colB, s->rowloss,
                                  s->loss_sum, stream))
         return e;
-    if (s->ev_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_end), st));
+    if (s->ev_fwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_end), st));
+    g_step_ns[5] = now_ns() - t0;                            // + select, gather, forward issued
+    if (world > 1) {
+        // every rank's row constants (32 B per row: the dS_ki terms of the backward) and loss partial, one message
+        if (int e = dcl_shard_pack(s->colA, s->colB, s->loss_sum, rank, n_pad, s->xchg_send, stream)) return e;
+        const size_t msg = sizeof(float) * 4 * (2 * static_cast<size_t>(n_pad) + 1);
+        if (int e = comm_all_gather(s->comm, s->xchg_send, s->xchg_recv, msg, st)) return e;
+        if (int e = dcl_shard_unpack(s->xchg_recv, world, n_pad, s->colA, s->colB, n_global, s->loss, stream)) return e;
+    } else {
+        DCL_CUDA(cudaMemcpyAsync(s->loss, s->loss_sum + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (s->dF) {
+        if (s->ev_bwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_begin), st));
+        if (int e = dcl_contrast_bwd(s->tiles, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
+                                     s->workspace_bytes, s->dF, stream))
+            return e;
+        if (s->ev_bwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_end), st));
+    }
+    if (s->zero_fill && s->zero_fill_bytes && s->side_stream)
+        DCL_CUDA(cudaStreamWaitEvent(st, pd->ev_zero, 0));   // the cleared buffer is ordered before anything later on st
+    g_step_ns[6] = now_ns() - t0;                            // + exchange, backward issued
     return 0;
 }
 
-extern "C" int dcl_pixel_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB, int n_pad,
-                             void* workspace, size_t workspace_bytes, float* dF, const int32_t* pix,
-                             const float* grad_out, float* dfeats, int B, int hw, int zero_fill, void* ev_begin,
-                             void* ev_end, void* stream) {
-    cudaStream_t st = as_stream(stream);
-    const int nJ = n_pad / DCL_TILE_ROWS;
+// Diagnostics: cumulative host nanoseconds of the last dcl_step_fwd at the end of each section: out[8] = classify etc.
+// issued, + count-table wait, + host plan, + generator upload queued, + plan kernel issued, + select / gather /
+// forward issued, + exchange / backward issued, -.
+extern "C" int dcl_step_timing(long long* out) {
+    if (!out) return fail(DCL_ERR_ARG, "null pointer argument");
+    for (int i = 0; i < 8; ++i) out[i] = g_step_ns[i];
+    return 0;
+}
+
+// Autograd backward of the step: d feats = upstream * scatter(dF) [+ the image-level term's pooled gradient
+// broadcast over the pixels, written in the same pass: `gap_g` [gap_rows] = d loss / d pooled, one value per
+// (image, channel) row of d feats; the dense tensor is then written once and needs no zero-fill].
+extern "C" int dcl_step_bwd(const float* dF, const int32_t* pix, int n_pad, const float* grad_out, float* dfeats, int B,
+                            int hw, int zero_fill, const float* gap_g, int gap_rows, void* stream) {
     if (n_pad <= 0 || n_pad % DCL_TILE_ROWS) return fail(DCL_ERR_ARG, "n_pad must be a positive multiple of %d", DCL_TILE_ROWS);
-    if (ev_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_begin), st));
-    if (int e = dcl_contrast_bwd(tiles, y, colA, colB, nJ, 0, nJ, DCL_MODE_PIXEL, workspace, workspace_bytes, dF, stream))
-        return e;
-    if (ev_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_end), st));
+    if (gap_g) {
+        if (gap_rows < B * DCL_DIM) return fail(DCL_ERR_ARG, "pooled gradient covers %d rows, the pixel term %d", gap_rows, B * DCL_DIM);
+        if (int e = dcl_gap_bwd(gap_g, gap_rows, hw, dfeats, 0, stream)) return e;
+        return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, 2, stream);
+    }
     return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, zero_fill, stream);
 }

@@ -86,6 +86,16 @@ def _require_cuda(t: torch.Tensor, name: str):
         raise _lib.DclError("%s must be a CUDA tensor: this library has no CPU path" % name)
 
 
+def _on_device(t: torch.Tensor, dev: torch.device, name: str):
+    """Side inputs (labels, predict, class_labels) must live where the embeddings live: the kernels take raw
+    pointers, so a CPU tensor or one on another GPU would be an illegal address, not a Python exception."""
+    if not t.is_cuda:
+        raise _lib.DclError("%s must be a CUDA tensor on %s: this library has no CPU path" % (name, dev))
+    if t.device != dev:
+        raise _lib.DclError("%s is on %s but the embeddings are on %s" % (name, t.device, dev))
+    return t
+
+
 # ----------------------------------------------------------------------------------------------
 # host-side sampling plan (the part of loss.py:264-337 that is Python control flow + CPU RNG)
 # ----------------------------------------------------------------------------------------------
@@ -306,12 +316,15 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 
 
 # ----------------------------------------------------------------------------------------------
-# lean single-GPU step: one device allocation per direction, cached sizes, raw pointers into it
+# the one-call step (dcl_step_fwd / dcl_step_bwd): cached sizes, persistent scratch, raw pointers
 # ----------------------------------------------------------------------------------------------
 _FUSED_STEP = os.environ.get("DCL_FUSED_STEP", "1") != "0"     # 0: the stage-by-stage Python path (same results)
+_DEVICE_PLAN = os.environ.get("DCL_DEVICE_PLAN", "1") != "0"   # 0: always replay the generator on the host (same results)
+_SIDE_STREAM_FILL = os.environ.get("DCL_SIDE_STREAM_FILL", "1") != "0"
 _WS_BYTES = {}
 _WS_CACHE = {}
 _LAUNCHES_CACHE = {}
+_SIDE_STREAMS = {}
 
 
 def _ws_bytes(nI, nJ):
@@ -344,16 +357,145 @@ def _carve(dev, sizes):
     for sz in sizes:
         offs.append(o)
         o += (sz + 255) // 256 * 256
-    buf = torch.empty(o, dtype=torch.uint8, device=dev)
+    buf = torch.empty(max(o, 256), dtype=torch.uint8, device=dev)
     base = buf.data_ptr()
     return buf, [ctypes.c_void_p(base + x) for x in offs]
+
+
+def _side_stream(dev):
+    """Second stream of a device: the dense gradient buffer is cleared there, next to the step's kernels."""
+    s = _SIDE_STREAMS.get(dev.index)
+    if s is None:
+        s = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+_WS_CAP_BYTES = {}
+
+
+def _ws_cap_bytes(cap, world):
+    """Workspace that serves every row count up to `cap` per rank (the row count is only known after the plan)."""
+    v = _WS_CAP_BYTES.get((cap, world))
+    if v is None:
+        v = _WS_CAP_BYTES[(cap, world)] = max(_ws_bytes(n, n * world) for n in range(1, cap // _TILE + 1))
+    return v
+
+
+_COMMS = {}
+
+
+def _shard_comm(group):
+    """(world, rank, ncclComm_t handle) of a torch.distributed group: the library talks to NCCL itself on the step's
+    stream (csrc/dcl_comm.cpp); torch.distributed only carries the 128-byte id, once per group."""
+    import torch.distributed as dist
+    key = id(group) if group is not None else 0
+    ent = _COMMS.get(key)
+    if ent is None:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _lib.call("dcl_comm_unique_id", buf)
+        box = [bytes(buf) if rank == 0 else None]
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=group)
+        comm = ctypes.c_void_p()
+        _lib.call("dcl_comm_init", box[0], world, rank, ctypes.byref(comm))
+        ent = _COMMS[key] = (world, rank, comm)
+    return ent
+
+
+class _StepResult:
+    """What one dcl_step_fwd left behind: the loss, and for the backward the sampled pixels and the eager dF."""
+    __slots__ = ("loss", "keep", "p_pix", "p_dF", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info")
+
+
+def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
+    """Issue one pixel-term step on feats [B,128,h,w] (contiguous f32) through dcl_step_fwd.  `shard` is None or
+    (world, rank, comm).  `zero_fill`: allocate and clear the dense gradient buffer next to the step."""
+    B, C, h, w = feats.shape
+    dev = feats.device
+    hw = h * w
+    world, rank, comm = shard if shard is not None else (1, 0, None)
+    sb = crit._step_buffers(B, h, w, dev, world)
+    cap = sb["cap"]
+    res = _StepResult()
+    res.shape = (B, C, h, w)
+    res.dzero = torch.empty_like(feats) if (want_grad and zero_fill) else None
+    # what outlives the call: sampled pixels, eager gradient of the rows, the loss
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    res.keep, (p_pix, p_dF) = _carve(dev, (cap * 4, cap * _DIM * 4 if want_grad else 0))
+    st = torch.get_rng_state()
+    sbuf = st.numpy()
+    step = sb["step"]
+    step.labels, step.predict, step.feats = labels.data_ptr(), predict.data_ptr(), feats.data_ptr()
+    step.H, step.W, step.C_cls = labels.shape[1], labels.shape[2], predict.shape[1]
+    step.ignore_label, step.max_samples, step.max_views = int(crit.ignore_label), int(crit.max_samples), int(crit.max_views)
+    step.temperature, step.base_temperature = float(crit.temperature), float(crit.base_temperature)
+    step.torch_rng_state, step.state_bytes = sbuf.ctypes.data, sbuf.nbytes
+    step.rank, step.comm = rank, comm
+    step.pix, step.dF, step.loss = p_pix, (p_dF if want_grad else None), loss.data_ptr()
+    ws = _workspace(dev, sb["ws_bytes"])
+    step.workspace, step.workspace_bytes = ws.data_ptr(), sb["ws_bytes"]
+    if res.dzero is not None:
+        step.zero_fill, step.zero_fill_bytes = res.dzero.data_ptr(), res.dzero.numel() * 4
+        step.side_stream = _side_stream(dev).cuda_stream if _SIDE_STREAM_FILL else None
+    else:
+        step.zero_fill, step.zero_fill_bytes, step.side_stream = None, 0, None
+    step.device_plan = 1 if _DEVICE_PLAN else 0
+    ev = None
+    if _PROFILE_HOOK is not None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in ev:
+            e.record()                                    # materialise the handles; the library re-records them
+        step.ev_fwd_begin, step.ev_fwd_end = ev[0].cuda_event, ev[1].cuda_event
+        step.ev_bwd_begin, step.ev_bwd_end = (ev[2].cuda_event, ev[3].cuda_event) if want_grad else (None, None)
+    else:
+        step.ev_fwd_begin = step.ev_fwd_end = step.ev_bwd_begin = step.ev_bwd_end = None
+    lib = _lib.load()
+    rc = lib.dcl_step_fwd(ctypes.byref(step), _stream())
+    info = sb["info"]
+    if rc == 2:
+        print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
+        raise Exception
+    if rc == 3:
+        raise RuntimeError("max_samples // total_classes == 0: no views to sample "
+                           "(the reference fails in torch.cat at loss.py:345)")
+    if rc == _lib.DCL_ERR_LABEL:
+        raise ValueError("labels must lie in 0..255 (ACDC train ids + the ignore label): %s"
+                         % lib.dcl_last_error().decode("utf-8", "replace"))
+    if rc < 0 or rc > 3:
+        raise _lib.DclError("dcl_step_fwd failed with status %d: %s" % (rc, lib.dcl_last_error().decode("utf-8", "replace")))
+    res.empty = rc == 1
+    res.info = tuple(int(v) for v in info)
+    if res.empty:                                          # no class qualifies: zero loss, zero gradient
+        _count(2)
+        crit.last_plan = None
+        res.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        res.n = res.n_pad = res.n_global = 0
+        return res
+    torch.set_rng_state(st)
+    if ev is not None:
+        _PROFILE_HOOK("contrast_fwd", ev[0], ev[1])
+        if want_grad:
+            _PROFILE_HOOK("contrast_bwd", ev[2], ev[3])
+    A, n_view, n, n_pad, n_global, on_device = res.info[:6]
+    res.n, res.n_pad, res.n_global = n, n_pad, n_global
+    res.p_pix, res.p_dF = p_pix, p_dF
+    res.loss = loss.reshape(())
+    # last_plan / last_layout / last_pix are built on first access (device buffers of this step: valid until the
+    # next forward of this module)
+    crit.__dict__["_last_step"] = (res.info, sb, res.keep, rank, world)
+    crit.__dict__["last_n_global"] = n_global
+    # classify + prefix, plan or 2 copies, select, gather, forward (+ backward) [+ pack / unpack when sharded]
+    _count(2 + 1 + 1 + 1 + _launches(MODE_PIXEL, 0) + (_launches(MODE_PIXEL, 1) if want_grad else 0) + (2 if world > 1 else 0))
+    return res
 
 
 # ----------------------------------------------------------------------------------------------
 # autograd glue
 # ----------------------------------------------------------------------------------------------
 class _PixelContrastFn(torch.autograd.Function):
-    """loss(feats) for a fixed set of sampled anchor pixels; gradient only w.r.t. feats."""
+    """loss(feats) for a fixed set of sampled anchor pixels; gradient only w.r.t. feats.  (Stage-by-stage path.)"""
 
     @staticmethod
     def forward(ctx, feats, pix, y_dev, n_valid, T, Tb, dzero=None):
@@ -401,141 +543,76 @@ class _PixelContrastFn(torch.autograd.Function):
         return dfeats, None, None, None, None, None, None
 
 
-_WS_CAP_BYTES = {}
+def _grad_scalar(grad_out):
+    return grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
+        grad_out.to(torch.float32).contiguous()
 
 
-def _ws_cap_bytes(cap):
-    """Workspace that serves every row count up to `cap` (the fused step learns its row count only after the plan)."""
-    v = _WS_CAP_BYTES.get(cap)
-    if v is None:
-        v = _WS_CAP_BYTES[cap] = max(_ws_bytes(n, n) for n in range(1, cap // _TILE + 1))
-    return v
-
-
-class _PixelStepFn(torch.autograd.Function):
-    """The pixel term through dcl_pixel_fwd / dcl_pixel_bwd: sampling, gather and the N x N forward are issued by
-    one C call (same stages, same results as _sample_fast + _PixelContrastFn; the interpreter no longer walks from
-    one entry point to the next, which was most of a cfg2 step's host time)."""
+class _StepFn(torch.autograd.Function):
+    """The pixel term through dcl_step_fwd / dcl_step_bwd, single GPU or one rank of a sharded job: sampling,
+    gather, the N x N forward AND its backward are issued by one C call (reference utils/loss.py:391-415); the
+    autograd backward only scales and scatters the eager row gradients."""
 
     @staticmethod
-    def forward(ctx, feats, labels, predict, crit):
-        B, C, h, w = feats.shape
-        dev = feats.device
-        hw = h * w
-        n_chunks = (hw + _CHUNK - 1) // _CHUNK
-        hb = crit._host_buffers(B, dev)
-        cap, an, rows, info = hb["cap"], hb["anchors"], hb["rows"], hb["info"]
-        # per-step device state, one allocation: code | chunk prefixes | counts | requests+labels | pix | tiles |
-        # sqnorm | colA | colB | rowloss
-        keep, (p_code, p_chunk, p_cnt, p_stage, p_pix, p_tiles, p_sq, p_cA, p_cB, p_rl) = _carve(
-            dev, (B * hw * 2, B * n_chunks * _BINS * 4, B * _BINS * 4, cap * 20, cap * 4, cap * _DIM * 2, cap * 4,
-                  cap * 16, cap * 16, cap * 4))
-        want_grad = ctx.needs_input_grad[0]
-        dzero = torch.empty_like(feats) if want_grad else None     # cleared on the stream while the host plans
-        lib = _lib.load()
-        strm = _stream()
-        H, W, C_cls = labels.shape[1], labels.shape[2], predict.shape[1]
-        zp = dzero.data_ptr() if dzero is not None else None
-        zb = dzero.numel() * 4 if dzero is not None else 0
-        # first half at once (classify, count table D2H, zero-fill): everything below overlaps it
-        rc = lib.dcl_pixel_begin(labels.data_ptr(), predict.data_ptr(), B, H, W, h, w, C_cls, p_code, p_chunk, p_cnt,
-                                 hb["counts"].data_ptr(), zp, zb, strm)
-        if rc != 0:
-            raise _lib.DclError("dcl_pixel_begin failed with status %d: %s"
-                                % (rc, lib.dcl_last_error().decode("utf-8", "replace")))
-        loss2 = torch.empty(2, dtype=torch.float32, device=dev)
-        nbytes = _ws_cap_bytes(cap)
-        ws = _workspace(dev, nbytes)
-        st = torch.get_rng_state()
-        sbuf = st.numpy()
-        step = hb.get("step")
-        if step is None:
-            step = hb["step"] = _lib.PixelStep()
-            step.counts_host = hb["counts"].data_ptr()
-            step.stage_host = hb["stage"].data_ptr()
-            step.cap = cap
-            step.info = info.ctypes.data
-            step.image, step.cls, step.num_hard, step.num_easy, step.keep_hard = (an[i].ctypes.data for i in range(5))
-            step.ranks = hb["ranks"].ctypes.data
-            step.ref_row, step.anchor = rows[0].ctypes.data, rows[1].ctypes.data
-            step.begun = 1
-        step.labels, step.predict, step.feats = labels.data_ptr(), predict.data_ptr(), feats.data_ptr()
-        step.B, step.H, step.W, step.h, step.w, step.C_cls = B, H, W, h, w, C_cls
-        step.ignore_label, step.max_samples, step.max_views = int(crit.ignore_label), int(crit.max_samples), int(crit.max_views)
-        step.temperature, step.base_temperature = float(crit.temperature), float(crit.base_temperature)
-        step.torch_rng_state, step.state_bytes = sbuf.ctypes.data, sbuf.nbytes
-        step.code, step.chunk_hist, step.counts_dev = p_code, p_chunk, p_cnt
-        step.stage_dev, step.pix, step.tiles, step.sqnorm = p_stage, p_pix, p_tiles, p_sq
-        step.colA, step.colB, step.rowloss, step.loss_sum = p_cA, p_cB, p_rl, loss2.data_ptr()
-        step.workspace, step.workspace_bytes = ws.data_ptr(), nbytes
-        step.zero_fill, step.zero_fill_bytes = zp, zb
-        ev = None
-        if _PROFILE_HOOK is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-            ev[1].record()                                # materialise the handles; the library re-records them
-            step.ev_begin, step.ev_end = ev[0].cuda_event, ev[1].cuda_event
-        else:
-            step.ev_begin = step.ev_end = None
-        rc = lib.dcl_pixel_fwd(ctypes.byref(step), strm)
-        if rc == 2:
-            print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
-            raise Exception
-        if rc == 3:
-            raise RuntimeError("max_samples // total_classes == 0: no views to sample "
-                               "(the reference fails in torch.cat at loss.py:345)")
-        if rc < 0 or rc > 3:
-            raise _lib.DclError("dcl_pixel_fwd failed with status %d: %s"
-                                % (rc, _lib.load().dcl_last_error().decode("utf-8", "replace")))
-        ctx.empty = rc == 1
-        ctx.shape = (B, C, h, w)
-        if rc == 1:                                        # no class qualifies: zero loss, zero gradient
-            _count(2)
-            crit.last_plan = None
-            return torch.zeros((), dtype=torch.float32, device=dev)
-        torch.set_rng_state(st)
-        if ev is not None:
-            _PROFILE_HOOK("contrast_fwd", ev[0], ev[1])
-        n_pad = int(info[3])
-        # last_plan / last_layout / last_pix are built on first access (views into the persistent host buffers and
-        # this step's device state: valid until the next forward of this module)
-        crit.__dict__["_last_step"] = (tuple(int(v) for v in info), hb, keep, p_pix.value - keep.data_ptr())
-        _count(2 + 1 + 1 + _launches(MODE_PIXEL, 0))
-        ctx.save_for_backward(keep)
-        ctx.meta = (n_pad, cap, (p_stage, p_pix, p_tiles, p_cA, p_cB), nbytes)
-        ctx.dzero = dzero
-        return loss2[1]
+    def forward(ctx, feats, labels, predict, crit, shard):
+        res = _run_step(crit, feats, labels, predict, shard, ctx.needs_input_grad[0], True)
+        ctx.res = res
+        return res.loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        B, C, h, w = ctx.shape
-        if ctx.empty:
-            return torch.zeros((B, C, h, w), dtype=torch.float32, device=grad_out.device), None, None, None
-        (keep,) = ctx.saved_tensors
-        n_pad, cap, (p_stage, p_pix, p_tiles, p_cA, p_cB), nbytes = ctx.meta
-        dev = keep.device
-        dF = torch.empty((n_pad, _DIM), dtype=torch.float32, device=dev)
-        ws = _workspace(dev, nbytes)
-        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
-            grad_out.to(torch.float32).contiguous()
-        dfeats, ctx.dzero = ctx.dzero, None
+        res = ctx.res
+        B, C, h, w = res.shape
+        dev = grad_out.device
+        if res.empty:
+            return torch.zeros((B, C, h, w), dtype=torch.float32, device=dev), None, None, None, None
+        if res.p_dF is None:
+            raise RuntimeError("backward through a pixel-contrast step that was run without requires_grad")
+        dfeats, res.dzero = res.dzero, None
         zero_fill = 0
-        if dfeats is None:
+        if dfeats is None:                                 # a second backward through the same graph
             dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
             zero_fill = 1
-        ev = None
-        eb = ee = None
-        if _PROFILE_HOOK is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-            ev[1].record()
-            eb, ee = ev[0].cuda_event, ev[1].cuda_event
-        _lib.call("dcl_pixel_bwd", p_tiles, ctypes.c_void_p(p_stage.value + cap * 16), p_cA, p_cB, n_pad, _p(ws), nbytes,
-                  _p(dF), p_pix, _p(g), _p(dfeats), B, h * w, zero_fill, eb, ee, _stream())
-        if ev is not None:
-            _PROFILE_HOOK("contrast_bwd", ev[0], ev[1])
-        _count(_launches(MODE_PIXEL, 1) + 1)
-        return dfeats, None, None, None
+        _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.n_pad, _p(_grad_scalar(grad_out)), _p(dfeats), B, h * w,
+                  zero_fill, None, 0, _stream())
+        _count(1 + zero_fill)
+        return dfeats, None, None, None, None
+
+
+class _DoublyFn(torch.autograd.Function):
+    """Both terms' touch points on the shared embedding tensor in one autograd node (the reference
+    applies SupConLoss to `fine_feat` [2B,...] and PixelContrastLoss to `fine_feat[:B]`, trainer.py:143-158,
+    network/weathernet.py:76-82): forward = global average pool of all 2B images + the pixel step on the first B;
+    backward = ONE pass over the dense gradient: pooled gradient broadcast, anchor gradients added."""
+
+    @staticmethod
+    def forward(ctx, feats2, labels, predict, crit):
+        B2, C, h, w = feats2.shape
+        B = labels.shape[0]
+        pooled = torch.empty((B2, C), dtype=torch.float32, device=feats2.device)
+        _lib.call("dcl_gap_fwd", _p(feats2), B2 * C, h * w, _p(pooled), _stream())
+        _count(1)
+        res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False)
+        ctx.res = res
+        ctx.shape2 = (B2, C, h, w)
+        return pooled, res.loss
+
+    @staticmethod
+    def backward(ctx, g_pooled, g_pixel):
+        res = ctx.res
+        B2, C, h, w = ctx.shape2
+        B = res.shape[0]
+        dev = g_pooled.device
+        dx = torch.empty((B2, C, h, w), dtype=torch.float32, device=dev)
+        gp = g_pooled.contiguous().to(torch.float32)
+        if res.empty or res.p_dF is None:
+            _lib.call("dcl_gap_bwd", _p(gp), B2 * C, h * w, _p(dx), 0, _stream())
+            _count(1)
+        else:
+            _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.n_pad, _p(_grad_scalar(g_pixel)), _p(dx), B, h * w, 0,
+                      _p(gp), B2 * C, _stream())
+            _count(2)
+        return dx, None, None, None
 
 
 class _ContrastRowsFn(torch.autograd.Function):
@@ -608,8 +685,9 @@ class PixelContrastLoss(nn.Module):
     Same constructor (`device=None`) and the same mutable attributes (loss.py:255-262); call as
     `crit(feats, labels=labels, predict=predict)` like trainer.py:135-136.  The sampled pixel
     indices are bit-exact with the reference for the same state of torch's global CPU generator.
-    Deviation (documented in DESIGN.md): when no class qualifies the reference crashes
-    (loss.py:287-288 then :341); this returns a zero loss that still back-propagates zeros.
+    Deviations (documented in DESIGN.md): when no class qualifies the reference crashes
+    (loss.py:287-288 then :341); this returns a zero loss that still back-propagates zeros.  Labels must lie in
+    0..255 (ACDC train ids + ignore label 255): anything else raises ValueError instead of becoming a class.
     """
 
     def __init__(self, device=None):
@@ -625,18 +703,35 @@ class PixelContrastLoss(nn.Module):
         self.last_plan: Optional[AnchorPlan] = None       # exposed for tests / diagnostics
         self.last_layout: Optional[RowLayout] = None
         self.last_pix: Optional[torch.Tensor] = None
+        self.last_n_global = 0
 
     # ---- what the last forward sampled (tests / diagnostics), built lazily after a fused step -------------
     def _last(self, key):
         d = self.__dict__
         if d.get("_last_step") is not None:
-            (A, n_view, n, n_pad), hb, keep, o_pix = d["_last_step"]
-            an, rows, stage, cap = hb["anchors"], hb["rows"], hb["stage_np"], hb["cap"]
-            d["_last_plan"] = AnchorPlan(A, n_view, an[0, :A], an[1, :A], an[2, :A], an[3, :A], an[4, :A],
-                                         hb["ranks"][: A * n_view].reshape(A, n_view))
-            d["_last_layout"] = RowLayout(n, n_pad, stage[: n_pad * 4].reshape(n_pad, 4),
-                                          stage[cap * 4: cap * 4 + n_pad], rows[0, :n_pad], rows[1, :n_pad])
-            d["_last_pix"] = keep[o_pix:o_pix + n_pad * 4].view(torch.int32)
+            (A, n_view, n, n_pad, n_global, on_device, _, _), sb, keep, rank, world = d["_last_step"]
+            an, cap = sb["anchors"], sb["cap"]
+            torch.cuda.synchronize(keep.device)
+            req = sb["req_dev"][: n_pad * 4].cpu().numpy().reshape(n_pad, 4).copy()
+            y = sb["y_dev"][rank * n_pad:(rank + 1) * n_pad].cpu().numpy().copy()
+            # class-sorted anchor order of this rank's block -> reference row / anchor of every device row
+            plan_np = sb["plan_np"]
+            ycnt, yoff = plan_np["ycnt"], plan_np["yoff"]
+            order = plan_np["yanchor"][int(yoff[rank]): int(yoff[rank]) + int(ycnt[rank])].astype(np.int64)
+            ref_row = np.full(n_pad, -1, dtype=np.int64)
+            anchor = np.full(n_pad, -1, dtype=np.int64)
+            if n:
+                a_rep = np.repeat(order, n_view)
+                v_rep = np.tile(np.arange(n_view, dtype=np.int64), order.shape[0])
+                ref_row[:n] = v_rep * A + a_rep
+                anchor[:n] = a_rep
+            ranks = np.zeros((A, n_view), dtype=np.int64)
+            if n:
+                ranks[anchor[:n], v_rep] = req[:n, 3]
+            d["_last_plan"] = AnchorPlan(A, n_view, an[0, :A].copy(), an[1, :A].copy(), an[2, :A].copy(),
+                                         an[3, :A].copy(), an[4, :A].copy(), ranks)
+            d["_last_layout"] = RowLayout(n, n_pad, req, y, ref_row, anchor)
+            d["_last_pix"] = keep[: n_pad * 4].view(torch.int32)
             d["_last_step"] = None
         return d.get("_last_" + key)
 
@@ -648,10 +743,67 @@ class PixelContrastLoss(nn.Module):
     last_layout = property(lambda self: self._last("layout"), lambda self, v: self._set_last("layout", v))
     last_pix = property(lambda self: self._last("pix"), lambda self, v: self._set_last("pix", v))
 
-    # ---- sampling front end ------------------------------------------------------------------
+    # ---- buffers of the one-call step ----------------------------------------------------------
+    def _step_buffers(self, B, h, w, dev, world):
+        """Persistent buffers of dcl_step_fwd: pinned staging (count tables, plan descriptors, host-plan rows), the
+        host arrays the plan fills, and the device scratch that does not outlive the call (everything the eager
+        backward has consumed by the time the call returns).  Re-made when the batch, the embedding size,
+        max_samples' capacity class, the device, the stream or the world size changes."""
+        cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
+        stream_id = torch._C._cuda_getCurrentRawStream(dev.index)
+        key = (B, h, w, cap, dev.index, stream_id, world)
+        sb = self.__dict__.get("_sb")
+        if sb is not None and sb["key"] == key:
+            return sb
+        hw = h * w
+        n_chunks = (hw + _CHUNK - 1) // _CHUNK
+        A_cap = B * world * 256
+        plan_bytes = int(_lib.load().dcl_step_plan_bytes(B, world))
+        msg = (2 * cap + 1) * 16
+        scratch, ptrs = _carve(dev, (
+            B * hw * 2, B * n_chunks * _BINS * 4, world * B * _BINS * 4,          # code, chunk_hist, counts_dev
+            cap * 16, world * cap * 4, plan_bytes,                                 # req_dev, y_dev, plan_dev
+            world * cap * _DIM * 2, world * cap * 4, world * cap * 16, world * cap * 16, world * cap * 4,   # tiles .. rowloss
+            16, msg if world > 1 else 0, world * msg if world > 1 else 0))         # loss_sum, xchg_send, xchg_recv
+        (p_code, p_chunk, p_cnt, p_req, p_y, p_plan, p_tiles, p_sq, p_cA, p_cB, p_rl, p_ls, p_xs, p_xr) = ptrs
+        base = scratch.data_ptr()
+        counts = torch.empty(world * B * _BINS, dtype=torch.int32).pin_memory()
+        plan_host = torch.empty(plan_bytes, dtype=torch.uint8).pin_memory()
+        stage = torch.empty(cap * 4 + world * cap, dtype=torch.int32).pin_memory()
+        info = np.zeros(8, dtype=np.int32)
+        anchors = np.empty((5, A_cap), dtype=np.int64)
+        ranks = np.empty(cap, dtype=np.int64)
+        # views of the plan blob: [ycnt | yoff | ycls] [anchors] [yanchor]
+        pn = plan_host.numpy()
+        o_anchor = (4 * (2 * world + A_cap) + 63) // 64 * 64
+        o_yanchor = (o_anchor + 48 * B * 256 + 63) // 64 * 64
+        plan_np = dict(ycnt=pn[: 4 * world].view(np.int32), yoff=pn[4 * world: 8 * world].view(np.int32),
+                       yanchor=pn[o_yanchor: o_yanchor + 4 * A_cap].view(np.int32))
+        step = _lib.Step()
+        step.B, step.h, step.w = B, h, w
+        step.world, step.cap = world, cap
+        step.code, step.chunk_hist, step.counts_dev = p_code, p_chunk, p_cnt
+        step.req_dev, step.y_dev, step.plan_dev = p_req, p_y, p_plan
+        step.tiles, step.sqnorm, step.colA, step.colB, step.rowloss, step.loss_sum = p_tiles, p_sq, p_cA, p_cB, p_rl, p_ls
+        step.xchg_send, step.xchg_recv = (p_xs, p_xr) if world > 1 else (None, None)
+        step.counts_host, step.plan_host, step.plan_bytes = counts.data_ptr(), plan_host.data_ptr(), plan_bytes
+        step.stage_host = stage.data_ptr()
+        step.info = info.ctypes.data
+        step.image, step.cls, step.num_hard, step.num_easy, step.keep_hard = (anchors[i].ctypes.data for i in range(5))
+        step.ranks = ranks.ctypes.data
+        step.begun = 0
+        i32 = scratch.view(torch.int32)
+        sb = dict(key=key, cap=cap, scratch=scratch, counts=counts, plan_host=plan_host, stage=stage, info=info,
+                  anchors=anchors, ranks=ranks, plan_np=plan_np, step=step, ws_bytes=_ws_cap_bytes(cap, world),
+                  req_dev=i32[(p_req.value - base) // 4: (p_req.value - base) // 4 + cap * 4],
+                  y_dev=i32[(p_y.value - base) // 4: (p_y.value - base) // 4 + world * cap])
+        self.__dict__["_sb"] = sb
+        return sb
+
+    # ---- sampling front end (stage-by-stage path) ----------------------------------------------
     def _host_buffers(self, B, dev):
-        """Persistent pinned staging for the one D2H (count table) and the one H2D (row requests) of a step, plus
-        the host arrays dcl_host_plan_rows fills; re-made only when the batch or max_samples grows."""
+        """Persistent pinned staging for the one D2H (count table) and the one H2D (row requests) of the
+        stage-by-stage path, plus the host arrays dcl_host_plan_rows fills."""
         cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
         key = (B, cap, str(dev))
         hb = getattr(self, "_hb", None)
@@ -662,7 +814,7 @@ class PixelContrastLoss(nn.Module):
                       stage=torch.empty(cap * 5, dtype=torch.int32).pin_memory(),       # req [cap*4] | y [cap]
                       info=np.zeros(4, dtype=np.int32),
                       anchors=np.empty((5, A_cap), dtype=np.int64),
-                      ranks=np.empty(max(int(self.max_samples), 1), dtype=np.int64),
+                      ranks=np.empty(cap, dtype=np.int64),     # cap >= any max_samples that maps to this key
                       rows=np.empty((2, cap), dtype=np.int64),
                       event=torch.cuda.Event())
             hb["stage_np"] = hb["stage"].numpy()
@@ -684,6 +836,7 @@ class PixelContrastLoss(nn.Module):
             dzero = torch.zeros_like(feats)            # runs on the GPU while the host plans below
             _count(1)
         hb["event"].synchronize()                      # the one unavoidable sync: the count table
+        _check_label_range(hb["counts_np"], B, h * w)
         st = torch.get_rng_state()
         sbuf = st.numpy()
         cap, stage, an, rows, info = hb["cap"], hb["stage_np"], hb["anchors"], hb["rows"], hb["info"]
@@ -721,8 +874,9 @@ class PixelContrastLoss(nn.Module):
     def _sample(self, feats, labels, predict):
         B, C, h, w = feats.shape
         code, chunk, counts = classify(labels, predict, h, w)
-        counts_host = counts.cpu().numpy().reshape(B, 256, 2)      # the one unavoidable D2H sync
-        plan = plan_anchors(counts_host, int(self.ignore_label), int(self.max_samples),
+        counts_np = counts.cpu().numpy()                           # the one unavoidable D2H sync
+        _check_label_range(counts_np.reshape(-1), B, h * w)
+        plan = plan_anchors(counts_np.reshape(B, 256, 2), int(self.ignore_label), int(self.max_samples),
                             int(self.max_views))
         return code, chunk, plan
 
@@ -747,37 +901,69 @@ class PixelContrastLoss(nn.Module):
         self.last_pix = pix
         return pix, y_dev, lay.n
 
-    def forward(self, feats, labels=None, predict=None):
+    def _check_inputs(self, feats, labels, predict):
         _require_cuda(feats, "feats")
         if labels is None or predict is None:
-            raise TypeError("PixelContrastLoss needs labels and predict (trainer.py:135-136)")
+            raise TypeError("%s needs labels and predict (trainer.py:135-136)" % type(self).__name__)
         if feats.dim() != 4 or feats.shape[1] != _DIM:
             raise ValueError("feats must be [B,128,h,w] (SwiftNet decoder width); got %s"
                              % (tuple(feats.shape),))
         B, C, h, w = feats.shape
         assert predict.shape[-1] == feats.shape[-1], "{} {}".format(predict.shape, feats.shape)
-        if labels.dim() != 3 or labels.shape[0] != B or predict.shape[0] != B or \
+        if labels.dim() != 3 or labels.shape[0] != B or predict.dim() != 4 or predict.shape[0] != B or \
                 tuple(predict.shape[2:]) != (h, w):
             raise ValueError("labels must be [B,H,W] and predict [B,C,h,w] matching feats")
+        dev = feats.device
+        _on_device(labels, dev, "labels")
+        _on_device(predict, dev, "predict")
         feats_c = feats.contiguous().to(torch.float32)
         labels_c = labels.contiguous().to(torch.int64)
         predict_c = predict.detach().contiguous().to(torch.float32)
-        if _verify_host_rng() and _FUSED_STEP:
-            return _PixelStepFn.apply(feats_c, labels_c, predict_c, self)
-        if _verify_host_rng():
-            sampled = self._sample_fast(feats_c, labels_c, predict_c,
-                                        feats_c.requires_grad and torch.is_grad_enabled())
+        return feats_c, labels_c, predict_c
+
+    def forward(self, feats, labels=None, predict=None):
+        feats_c, labels_c, predict_c = self._check_inputs(feats, labels, predict)
+        with torch.cuda.device(feats_c.device):
+            if _verify_host_rng() and _FUSED_STEP:
+                return _StepFn.apply(feats_c, labels_c, predict_c, self, None)
+            if _verify_host_rng():
+                sampled = self._sample_fast(feats_c, labels_c, predict_c,
+                                            feats_c.requires_grad and torch.is_grad_enabled())
+                if sampled is None:
+                    return feats_c.sum() * 0.0
+                pix, y_dev, n_valid, dzero = sampled
+                return _PixelContrastFn.apply(feats_c, pix, y_dev, n_valid, self.temperature,
+                                              self.base_temperature, dzero)
+            sampled = self.sample(feats_c, labels_c, predict_c)
             if sampled is None:
                 return feats_c.sum() * 0.0
-            pix, y_dev, n_valid, dzero = sampled
+            pix, y_dev, n_valid = sampled
             return _PixelContrastFn.apply(feats_c, pix, y_dev, n_valid, self.temperature,
-                                          self.base_temperature, dzero)
-        sampled = self.sample(feats_c, labels_c, predict_c)
-        if sampled is None:
-            return feats_c.sum() * 0.0
-        pix, y_dev, n_valid = sampled
-        return _PixelContrastFn.apply(feats_c, pix, y_dev, n_valid, self.temperature,
-                                      self.base_temperature)
+                                          self.base_temperature)
+
+
+def _check_label_range(counts_flat, B, hw):
+    """Every pixel lands in one of the 512 (label, hard/easy) bins unless its label is outside 0..255."""
+    tot = np.asarray(counts_flat).reshape(B, -1).sum(axis=1)
+    if not bool(np.all(tot == hw)):
+        b = int(np.nonzero(tot != hw)[0][0])
+        raise ValueError("labels must lie in 0..255 (ACDC train ids + the ignore label): image %d has %d pixels "
+                         "outside that range" % (b, hw - int(tot[b])))
+
+
+def _mask_to_labels(mask: torch.Tensor, batch_size: int) -> torch.Tensor:
+    """SupConLoss's explicit `mask` [bsz,bsz] (loss.py:158-159) for the masks the kernels can express: a 0/1 mask
+    that is an equivalence relation (mask[i,j] = 1 iff i and j belong to the same group; what `eq(labels, labels.T)`
+    and `eye` produce).  Returns group ids; anything else is rejected."""
+    if mask.dim() != 2 or mask.shape[0] != batch_size or mask.shape[1] != batch_size:
+        raise ValueError("`mask` must be [bsz, bsz]")
+    m = mask.float()
+    ident = (m > 0).to(torch.int32).argmax(dim=1).to(torch.int32)        # first member of each row's group
+    rebuilt = (ident[:, None] == ident[None, :]).float()
+    if not bool(torch.equal(rebuilt, m)):
+        raise NotImplementedError("only 0/1 masks that form an equivalence relation (same-group masks, as "
+                                  "eq(labels, labels.T) or eye produce) are supported by the CUDA path")
+    return ident
 
 
 class SupConLoss(nn.Module):
@@ -807,7 +993,16 @@ class SupConLoss(nn.Module):
         _require_cuda(features, "features")
         if features.dim() != 4:
             raise ValueError("features must be [2*bsz, C, h, w]")
-        pooled = _GapFn.apply(features.to(torch.float32))                    # loss.py:115-116
+        with torch.cuda.device(features.device):
+            pooled = _GapFn.apply(features.to(torch.float32))                # loss.py:115-116
+            return self.forward_pooled(pooled, class_labels, mask)
+
+    def forward_pooled(self, pooled, class_labels=None, mask=None):
+        """Everything after the global average pool (loss.py:117-204) on pooled [2*bsz, C]."""
+        if pooled.shape[0] % 2:
+            # torch.split(features, [bsz, bsz]) with bsz = n // 2 fails on an odd batch (loss.py:118)
+            raise ValueError("features must hold two crops per image: the leading dimension must be even, got %d"
+                             % pooled.shape[0])
         bsz = pooled.shape[0] // 2
         z = torch.stack([pooled[:bsz], pooled[bsz:2 * bsz]], dim=1)          # loss.py:117-119
         z = self.projection(z)                                               # loss.py:120
@@ -824,18 +1019,59 @@ class SupConLoss(nn.Module):
             labels = labels.contiguous().view(-1, 1)
             if labels.shape[0] != batch_size:
                 raise ValueError("Num of labels does not match num of features")
-            y = labels.view(-1).to(device=z.device, dtype=torch.int32)
-            if bool((y < 0).any()):
-                raise ValueError("class_labels must be non-negative integers")
+            labels = _on_device(labels, z.device, "class_labels")
+            # mask = eq(labels, labels.T) on the raw values (loss.py:157): group id = first row with an equal label,
+            # so float or negative labels compare exactly as they do in the reference
+            y = torch.eq(labels, labels.T).to(torch.int32).argmax(dim=1).to(torch.int32)
         else:
-            raise NotImplementedError("an explicit `mask` is not supported by the CUDA path "
-                                      "(trainer.py always passes mask=None)")
+            y = _mask_to_labels(_on_device(mask, z.device, "mask"), batch_size)
         if self.contrast_mode != "all":
             raise ValueError("Unknown mode: {}".format(self.contrast_mode))
         n_views = z.shape[1]
         Z = torch.cat(torch.unbind(z, dim=1), dim=0)                         # loss.py:161
         yy = y.repeat(n_views)
         return _ContrastRowsFn.apply(Z, yy, MODE_SUPCON, self.temperature, self.base_temperature)
+
+
+class DoublyContrastiveLoss(nn.Module):
+    """Both contrastive terms of the `supcon_pixelcontrast_*` criteria (trainer.py:143-158) with their touch points
+    on the shared embedding tensor fused: one read of `fine_feat` for the global average pool, one write of its
+    dense gradient (pooled gradient broadcast + anchor gradients).  Numerically the same as calling the
+    two modules separately, which keeps working.
+
+        crit = DoublyContrastiveLoss(pixel_crit, supcon_crit)
+        supcon_loss, pixelcontrast_loss = crit(fine_feat, labels=labels, predict=left_seg_beforeup,
+                                               class_labels=weather)          # fine_feat [2B,128,h,w]
+        total = (supcon_loss + pixelcontrast_loss) / batch_size + 1.2 * seg_loss   # trainer.py:158
+
+    The pixel term sees fine_feat[:B] (network/weathernet.py:77: `fine_feat0`), B = labels.shape[0].
+    """
+
+    def __init__(self, pixel: Optional[PixelContrastLoss] = None, supcon: Optional[SupConLoss] = None, device=None,
+                 opts=None):
+        super().__init__()
+        self.pixel = pixel if pixel is not None else PixelContrastLoss(device=device)
+        self.supcon = supcon if supcon is not None else SupConLoss(device=device, opts=opts)
+
+    def forward(self, fine_feat, labels=None, predict=None, class_labels=None, mask=None):
+        _require_cuda(fine_feat, "fine_feat")
+        if labels is None or predict is None:
+            raise TypeError("DoublyContrastiveLoss needs labels and predict")
+        if fine_feat.dim() != 4 or fine_feat.shape[1] != _DIM:
+            raise ValueError("fine_feat must be [2B,128,h,w]; got %s" % (tuple(fine_feat.shape),))
+        B = labels.shape[0]
+        if fine_feat.shape[0] != 2 * B:
+            raise ValueError("fine_feat must hold two crops per labelled image: got %d images for %d label maps"
+                             % (fine_feat.shape[0], B))
+        x = fine_feat.contiguous().to(torch.float32)
+        _, labels_c, predict_c = self.pixel._check_inputs(x[:B], labels, predict)
+        if not (_verify_host_rng() and _FUSED_STEP):
+            return (self.supcon(fine_feat, class_labels=class_labels, mask=mask),
+                    self.pixel(fine_feat[:B], labels=labels, predict=predict))
+        with torch.cuda.device(x.device):
+            pooled, pixel_loss = _DoublyFn.apply(x, labels_c, predict_c, self.pixel)
+            supcon_loss = self.supcon.forward_pooled(pooled, class_labels, mask)
+        return supcon_loss, pixel_loss
 
 
 # ----------------------------------------------------------------------------------------------
@@ -880,7 +1116,7 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
     counts = np.ascontiguousarray(counts_all, dtype=np.int32).reshape(-1)
     info = np.zeros(6, dtype=np.int32)
     an = np.empty((5, B * 256), dtype=np.int64)
-    ranks = np.empty(max(int(max_samples), 1), dtype=np.int64)
+    ranks = np.empty(cap, dtype=np.int64)
     compact = stage_req is not None and stage_y is None     # labels right behind the requests (one H2D copy)
     req = stage_req if stage_req is not None else np.empty(cap * 4, dtype=np.int32)
     y_all = None if compact else (stage_y if stage_y is not None else np.empty(world * cap, dtype=np.int32))
@@ -914,73 +1150,6 @@ def shard_plan_c(counts_all: np.ndarray, rank: int, world: int, images_per_rank:
     return ShardPlan(plan, lay, n_pad, n_global, rpr), y_all[: world * n_pad]
 
 
-class _ShardedPixelContrastFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, feats, pix, y_all, n_global, T, Tb, group, dzero=None):
-        import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        B, C, h, w = feats.shape
-        n_pad = pix.shape[0]
-        dev = feats.device
-        st = _stream()
-        nJ, nI, rb0 = world * n_pad // _TILE, n_pad // _TILE, rank * n_pad // _TILE
-        N = world * n_pad
-        m4 = n_pad * 4
-        # the one real exchange step: the contrast set, gathered straight into place (the norms of the other ranks'
-        # rows are recomputed from their tiles by the library, so only the local slice of `sqnorm` is filled)
-        tiles = torch.empty(N * _DIM * 2, dtype=torch.uint8, device=dev)
-        tl = tiles[rank * n_pad * _DIM * 2:(rank + 1) * n_pad * _DIM * 2]
-        # sqnorm | colA | colB | rowloss | loss(2) | send (colA_l | colB_l | loss part), one allocation
-        keep, (p_sq, p_cA, p_cB, p_rl, p_loss, p_send) = _carve(dev, (N * 4, N * 16, N * 16, N * 4, 8, (2 * m4 + 4) * 4))
-        base = keep.data_ptr()
-        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tl), ctypes.c_void_p(p_sq.value + rank * n_pad * 4), st)
-        dist.all_gather_into_tensor(tiles, tl, group=group)
-        nbytes = _ws_bytes(nI, nJ)
-        ws = _workspace(dev, nbytes)
-        with _Timed("contrast_fwd"):
-            _lib.call("dcl_contrast_fwd", _p(tiles), _p(y_all), p_sq, nJ, rb0, nI, n_global, MODE_PIXEL, float(T), float(Tb),
-                      _p(ws), nbytes, p_cA, p_cB, p_rl, p_loss, st)
-        _count(1 + _launches(MODE_PIXEL, 0))
-        # backward needs every row's constants (the dS_ki terms, 32 B per row) and the loss is the sum over ranks:
-        # one all-gather of [colA | colB | local loss sum] per rank, unpacked with two strided copies
-        kf = keep.view(torch.float32)
-        o_send = (p_send.value - base) // 4
-        send = kf[o_send:o_send + 2 * m4 + 4]
-        _lib.call("dcl_shard_pack", p_cA, p_cB, p_loss, rank, n_pad, p_send, st)
-        recv = torch.empty((world, 2 * m4 + 4), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.call("dcl_shard_unpack", _p(recv), world, n_pad, p_cA, p_cB, int(n_global), _p(loss), st)
-        _count(2)
-        ctx.save_for_backward(tiles, y_all, keep, pix)
-        ctx.meta = (nJ, rb0, nI, n_pad, (B, C, h, w), (p_cA, p_cB))
-        ctx.dzero = dzero
-        return loss.reshape(())
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        tiles, y_all, keep, pix = ctx.saved_tensors
-        nJ, rb0, nI, n_pad, (B, C, h, w), (p_cA, p_cB) = ctx.meta
-        dev = tiles.device
-        st = _stream()
-        dF = torch.empty((n_pad, _DIM), dtype=torch.float32, device=dev)
-        nbytes = _ws_bytes(nI, nJ)
-        ws = _workspace(dev, nbytes)
-        with _Timed("contrast_bwd"):
-            _lib.call("dcl_contrast_bwd", _p(tiles), _p(y_all), p_cA, p_cB, nJ, rb0, nI, MODE_PIXEL, _p(ws), nbytes,
-                      _p(dF), st)
-        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else \
-            grad_out.to(torch.float32).contiguous()
-        dfeats, ctx.dzero = ctx.dzero, None
-        zero_fill = 0
-        if dfeats is None:
-            dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
-            zero_fill = 1
-        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfeats), B, h * w, zero_fill, st)
-        _count(_launches(MODE_PIXEL, 1) + 1 + zero_fill)
-        return dfeats, None, None, None, None, None, None, None
-
-
 class ShardedPixelContrastLoss(PixelContrastLoss):
     """Data-parallel form of PixelContrastLoss for one process per GPU (torch.distributed, NCCL).
 
@@ -989,75 +1158,19 @@ class ShardedPixelContrastLoss(PixelContrastLoss):
     every rank; backward yields d(global loss)/d(local feats) exactly, including the terms that
     come from other ranks' rows.  All ranks must hold the same torch CPU RNG state on entry
     (e.g. `torch.manual_seed(step)` everywhere), because each replays the full host RNG stream.
+    The whole step is issued by dcl_step_fwd (csrc/dcl_step.cu), which calls NCCL itself on the step's stream:
+    all-gather of the count tables, of the F-tiles (the contrast set) and of the 32-byte row constants.
     The reference has no multi-GPU path; this is new design, not a port.
     """
 
     def __init__(self, device=None, process_group=None):
         super().__init__(device=device)
         self.process_group = process_group
-        self.last_n_global = 0
 
     def forward(self, feats, labels=None, predict=None):
-        import torch.distributed as dist
-        _require_cuda(feats, "feats")
-        if labels is None or predict is None:
-            raise TypeError("ShardedPixelContrastLoss needs labels and predict")
-        if feats.dim() != 4 or feats.shape[1] != _DIM:
-            raise ValueError("feats must be [B,128,h,w]; got %s" % (tuple(feats.shape),))
-        group = self.process_group
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        B, C, h, w = feats.shape
-        feats_c = feats.contiguous().to(torch.float32)
-        labels_c = labels.contiguous().to(torch.int64)
-        predict_c = predict.detach().contiguous().to(torch.float32)
-        code, chunk, counts = classify(labels_c, predict_c, h, w)
-        counts_all = torch.empty((world * B, _BINS), dtype=torch.int32, device=feats.device)
-        dist.all_gather_into_tensor(counts_all, counts, group=group)
-        hc = getattr(self, "_shard_counts", None)
-        if hc is None or hc[0].numel() != world * B * _BINS:
-            t = torch.empty(world * B * _BINS, dtype=torch.int32).pin_memory()
-            hc = self._shard_counts = (t, t.numpy(), torch.cuda.Event())
-        hc[0].copy_(counts_all.view(-1), non_blocking=True)
-        hc[2].record()
-        dzero = None
-        if feats_c.requires_grad and torch.is_grad_enabled():
-            dzero = torch.zeros_like(feats_c)              # runs on the GPU while the host plans below
-            _count(1)
-        hc[2].synchronize()
-        counts_host = hc[1].reshape(world * B, 256, 2)
-        if _verify_host_rng():
-            cap = max(_TILE, (int(self.max_samples) + _TILE - 1) // _TILE * _TILE) + _TILE
-            key = (world, cap)
-            stg = getattr(self, "_shard_stage", None)
-            if stg is None or stg[0] != key:
-                t = torch.empty(cap * 4 + world * cap, dtype=torch.int32).pin_memory()
-                stg = self._shard_stage = (key, t, t.numpy())
-            _, stage_t, stage_np = stg
-            out = shard_plan_c(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
-                               int(self.max_views), stage_np, None)
-            sp = None if out is None else out[0]
-        else:
-            sp = shard_plan(counts_host, rank, world, B, int(self.ignore_label), int(self.max_samples),
-                            int(self.max_views))
-            stage_t = None
-        self.last_plan = None if sp is None else sp.plan
-        if sp is None:
-            return feats_c.sum() * 0.0
-        if sp.plan.n_view <= 0:
-            raise RuntimeError("max_samples // total_classes == 0: no views to sample")
-        lay = sp.layout
-        self.last_layout, self.last_n_global = lay, sp.n_global
-        if stage_t is not None:
-            # one small H2D copy: the local requests with every rank's labels right behind them
-            packed = stage_t[: (4 + world) * lay.n_pad].to(feats.device, non_blocking=True)
-            req_dev, y_all = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
-        else:
-            host = torch.from_numpy(np.concatenate([lay.req.reshape(-1), lay.y])).pin_memory()
-            packed = host.to(feats.device, non_blocking=True)
-            req_dev, y_dev = packed[: lay.n_pad * 4], packed[lay.n_pad * 4:]
-            y_all = torch.empty(world * lay.n_pad, dtype=torch.int32, device=feats.device)
-            dist.all_gather_into_tensor(y_all, y_dev.contiguous(), group=group)
-        pix = select_pixels(code, chunk, B, h * w, req_dev, lay.n_pad)
-        self.last_pix = pix
-        return _ShardedPixelContrastFn.apply(feats_c, pix, y_all, sp.n_global, self.temperature,
-                                             self.base_temperature, group, dzero)
+        feats_c, labels_c, predict_c = self._check_inputs(feats, labels, predict)
+        if not _verify_host_rng():
+            raise _lib.DclError("the C replay of torch's CPU generator does not match this torch build")
+        with torch.cuda.device(feats_c.device):
+            shard = _shard_comm(self.process_group)
+            return _StepFn.apply(feats_c, labels_c, predict_c, self, shard)

@@ -39,7 +39,9 @@ enum dcl_status {
     DCL_OK = 0,
     DCL_ERR_ARG = -1,       /* bad argument (shape, alignment, null) */
     DCL_ERR_WORKSPACE = -2, /* workspace too small */
-    DCL_ERR_ARCH = -3       /* device is not sm_100 */
+    DCL_ERR_ARCH = -3,      /* device is not sm_100 */
+    DCL_ERR_COMM = -4,      /* NCCL missing or failed (sharded step only) */
+    DCL_ERR_LABEL = -5      /* a label outside 0..255 (the sampler codes labels in one byte) */
 };
 
 int dcl_version(void);
@@ -153,6 +155,19 @@ int dcl_host_lookahead_stats(long long* out);
  * + generator state / look-ahead attach, + permutations, + state write-back / commit, + row requests, -, -, -. */
 int dcl_host_plan_timing(long long* out);
 
+/* Diagnostics / tests (host only, no device needed): the host plan exactly as dcl_step_fwd requests it, with the
+ * device-plan descriptors.  meta [8]: 1 if the permutations were left to the GPU, local anchors, stream epoch, first
+ * and last stream block the permutations read, ring blocks, blocks produced so far, -.  `anchors`: 48-byte records
+ * (u64 g_hard, u64 g_easy, i32 num_hard, num_easy, keep_hard, keep_easy, row0, image, cls, -): g_* = position of the
+ * permutation's first draw in the generator's output stream, counted from word 0 of stream block 0.  ring_out: the
+ * look-ahead ring of raw (untempered) mt19937 state blocks, block b at ring + (b % ring_blocks) * 624 u32 words.
+ * ycls / yanchor: class and anchor id of the o-th class-sorted anchor of rank r at [yoff[r] + o], o < ycnt[r]. */
+int dcl_debug_plan_device(const int32_t* counts, int Bl, int world, int rank, int ignore_label, int max_samples,
+                          int max_views, void* torch_rng_state, size_t state_bytes, int32_t* info, int64_t* image,
+                          int64_t* cls, int64_t* num_hard, int64_t* num_easy, int64_t* keep_hard, int64_t* ranks,
+                          int32_t* req, int32_t* y_all, void* anchors, int32_t* ycls, int32_t* yanchor,
+                          int32_t* ycnt, int32_t* yoff, long long* meta, const void** ring_out);
+
 /* ---------------------------------------------------------------- N x N contrast
  * Forward of _contrastive (loss.py:339-389) / SupConLoss.forward (loss.py:175-204) for the local
  * row blocks [rb0, rb0+nI) against ALL nJ column blocks, N x N never materialised.
@@ -182,8 +197,9 @@ int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, con
 
 /* ---------------------------------------------------------------- gradient back to NCHW
  * Replaces autograd of the gather (index_put into a zero tensor per class):
- * dfeats [B,128,h*w] f32 is zero-filled, then row n's gradient * (*grad_out) is written at
- * pixel pix[n] (pix < 0 skipped).  grad_out: device scalar (upstream dL/dloss). */
+ * row n's gradient * (*grad_out) is written at pixel pix[n] of dfeats [B,128,h*w] f32 (pix < 0 skipped).
+ * zero_fill: 0 = dfeats is already clear, 1 = clear it first, 2 = ADD to what dfeats holds (sampled pixels are
+ * distinct, so no atomics are needed).  grad_out: device scalar (upstream dL/dloss). */
 int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const float* grad_out,
                      float* dfeats, int B, int hw, int zero_fill, void* stream);
 /* dZ [n,128] = dF[:n] * (*grad_out)  (image-level term). */
@@ -207,50 +223,84 @@ int dcl_gap_fwd(const float* x, int R, int hw, float* pooled, void* stream);
 int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------- the pixel term in one call
- * PixelContrastLoss.forward (loss.py:391-415 -> 250-389) issued from C: dcl_sample_classify -> count table to
- * the host -> (optional zero-fill on the stream || dcl_host_plan_rows on the host) -> row requests to the device ->
- * dcl_sample_select -> dcl_gather_tiles -> dcl_contrast_fwd.  Same results as calling the stages one by one; the
- * only wait is for the count table.  All buffers are the caller's:
- *   device scratch  code [B*h*w] u16, chunk_hist [B*n_chunks*512] i32, counts_dev [B*512] i32
- *   pinned host     counts_host [B*512] i32, stage_host [5*cap] i32 (row requests [4*cap] | labels [cap])
- *   host plan       info [4], image/cls/num_hard/num_easy/keep_hard [>= B*256], ranks [>= max_samples],
- *                   ref_row/anchor [cap]   (as dcl_host_plan_rows)
- *   device outputs  stage_dev [5*cap] i32 (requests | labels y at +4*cap), pix [cap], tiles [cap*256 B],
- *                   sqnorm [cap], colA/colB [cap*4] f32, rowloss [cap], loss_sum [2]
- *   workspace       >= dcl_contrast_workspace_bytes(n, n) for every n <= cap/128 (the row count is only known
- *                   after the plan)
- *   cap             multiple of 128, >= max_samples rounded up to 128
- *   zero_fill       optional device buffer cleared on the stream while the host plans (the dense gradient)
- *   ev_begin/ev_end optional cudaEvent_t recorded around the N x N forward (measurement)
- * Returns 0; 1 when no class qualifies; 2 for the reference's "never touched" branch; 3 when
- * max_samples / total_classes == 0; negative dcl_status on errors.  info = (A, n_view, n, n_pad). */
-typedef struct dcl_pixel_step {
+ * PixelContrastLoss.forward (loss.py:391-415 -> 250-389) AND the gradient of its N x N part, issued from C with one
+ * host wait (the count table), for a single GPU (world == 1) or one rank of a row-sharded job (one process per GPU;
+ * new design, the reference has no multi-GPU path):
+ *   dcl_sample_classify -> [NCCL all-gather of the count tables] -> count table to the host
+ *   (side stream: zero-fill of the dense gradient buffer) -> host: anchor list, n_view, split rule ->
+ *   permutations on the GPU from a mirror of torch's CPU generator stream (k_plan; exact) or on the host when the
+ *   generator was touched since the last step -> dcl_sample_select -> dcl_gather_tiles ->
+ *   [NCCL all-gather of the F-tiles] -> dcl_contrast_fwd -> [NCCL all-gather of the row constants] ->
+ *   dcl_contrast_bwd (eager: dF for an upstream gradient of 1; pass dF = NULL for a forward-only step).
+ * The autograd backward is dcl_step_bwd: scale and scatter dF.  All buffers are the caller's:
+ *   B                images of THIS rank; every rank passes the same B
+ *   cap              rows per rank block the buffers hold: multiple of 128, >= max_samples rounded up to 128
+ *   device scratch   code [B*h*w] u16, chunk_hist [B*n_chunks*512] i32, counts_dev [world*B*512] i32,
+ *                    req_dev [4*cap] i32, y_dev [world*cap] i32, pix [cap] i32, plan_dev [plan_bytes]
+ *   device state     tiles [world*cap*256 B], sqnorm [world*cap], colA/colB [world*cap*4] f32, rowloss [world*cap],
+ *                    loss_sum [2], loss [1] (the step's result), dF [cap*128] f32 or NULL,
+ *                    xchg_send [(2*cap+1)*4] f32 and xchg_recv [world*(2*cap+1)*4] f32 (world > 1 only)
+ *   workspace        >= dcl_contrast_workspace_bytes(n, world*n) for every n <= cap/128
+ *   pinned host      counts_host [world*B*512] i32, plan_host [plan_bytes = dcl_step_plan_bytes(B, world)],
+ *                    stage_host [4*cap + world*cap] i32 (rows of a host-side plan)
+ *   host outputs     info [8]: A (anchors = reference `total_classes`), n_view, n (valid local rows), n_pad (rows per
+ *                    rank block), n_global, 1 if the permutations ran on the GPU, -, -;
+ *                    image / cls / num_hard / num_easy / keep_hard [>= world*B*256] i64: the anchors in reference
+ *                    order; ranks [>= cap] i64: randperm prefixes (host-side plan only)
+ *   comm             dcl_comm_init handle (world > 1)
+ *   zero_fill        optional device buffer cleared off the critical path (side_stream: optional second stream)
+ *   device_plan      0: always replay the generator on the host
+ *   ev_*             optional cudaEvent_t recorded around the N x N forward / backward (measurement)
+ * Returns 0; 1 when no class qualifies (reference: `return None, None`, loss.py:287-288); 2 for the reference's
+ * "this shoud be never touched" branch (info = num_hard, num_easy, n_view); 3 when max_samples / total_classes == 0;
+ * negative dcl_status on errors. */
+typedef struct dcl_step {
     const int64_t* labels; const float* predict; const float* feats;
     int B, H, W, h, w, C_cls, ignore_label, max_samples, max_views;
     float temperature, base_temperature;
     void* torch_rng_state; size_t state_bytes;
+    int world, rank; void* comm;
+    int cap;
     uint16_t* code; int32_t* chunk_hist; int32_t* counts_dev;
-    int32_t* counts_host; int32_t* stage_host; int cap;
-    int32_t* info; int64_t* image; int64_t* cls; int64_t* num_hard; int64_t* num_easy; int64_t* keep_hard;
-    int64_t* ranks; int64_t* ref_row; int64_t* anchor;
-    int32_t* stage_dev; int32_t* pix; void* tiles; float* sqnorm; float* colA; float* colB; float* rowloss;
-    float* loss_sum;
+    int32_t* req_dev; int32_t* y_dev; int32_t* pix; void* plan_dev;
+    void* tiles; float* sqnorm; float* colA; float* colB; float* rowloss; float* loss_sum; float* loss;
+    float* xchg_send; float* xchg_recv; float* dF;
     void* workspace; size_t workspace_bytes;
-    void* zero_fill; size_t zero_fill_bytes;
-    void* ev_begin; void* ev_end;
-    int begun;          /* != 0: dcl_pixel_begin was already issued for this step on the same stream and thread */
-} dcl_pixel_step_t;
-int dcl_pixel_fwd(const dcl_pixel_step_t* step, void* stream);
-/* Optional first half of dcl_pixel_fwd (classify, count table D2H, zero-fill): issue it as soon as the inputs are
- * known, prepare the rest of the descriptor while the GPU classifies, then call dcl_pixel_fwd with begun = 1. */
-int dcl_pixel_begin(const int64_t* labels, const float* predict, int B, int H, int W, int h, int w, int C_cls,
-                    uint16_t* code, int32_t* chunk_hist, int32_t* counts_dev, int32_t* counts_host,
-                    void* zero_fill, size_t zero_fill_bytes, void* stream);
-/* Backward of the same: dcl_contrast_bwd (all rows local) -> dcl_scatter_grad. */
-int dcl_pixel_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB, int n_pad,
-                  void* workspace, size_t workspace_bytes, float* dF, const int32_t* pix,
-                  const float* grad_out, float* dfeats, int B, int hw, int zero_fill, void* ev_begin,
-                  void* ev_end, void* stream);
+    int32_t* counts_host; void* plan_host; size_t plan_bytes; int32_t* stage_host;
+    int32_t* info; int64_t* image; int64_t* cls; int64_t* num_hard; int64_t* num_easy; int64_t* keep_hard;
+    int64_t* ranks;
+    void* zero_fill; size_t zero_fill_bytes; void* side_stream;
+    int device_plan;
+    void* ev_fwd_begin; void* ev_fwd_end; void* ev_bwd_begin; void* ev_bwd_end;
+    int begun;          /* != 0: dcl_step_begin was already issued for this step on the same stream and thread */
+} dcl_step_t;
+size_t dcl_step_plan_bytes(int B_local, int world);
+/* Optional first half of dcl_step_fwd (classify, count tables, zero-fill): issue it as soon as the inputs are known,
+ * prepare the rest of the descriptor while the GPU classifies, then call dcl_step_fwd with begun = 1. */
+int dcl_step_begin(const dcl_step_t* step, void* stream);
+int dcl_step_fwd(const dcl_step_t* step, void* stream);
+/* Autograd backward of the step: dfeats [B(+),128,hw] = (*grad_out) * scatter(dF at pix).  zero_fill != 0 clears
+ * dfeats first (0: the caller already did, e.g. through dcl_step_t.zero_fill).  gap_g != NULL fuses the image-level
+ * term's gradient into the same pass (both losses hit the same `fine_feat`, trainer.py:144-152):
+ * dfeats has gap_rows/128 >= B images, every (image, channel) row r is first written with gap_g[r] / hw (the
+ * AdaptiveAvgPool2d backward, loss.py:115), then the anchor gradients are added - the dense tensor is written once. */
+int dcl_step_bwd(const float* dF, const int32_t* pix, int n_pad, const float* grad_out, float* dfeats, int B, int hw,
+                 int zero_fill, const float* gap_g, int gap_rows, void* stream);
+
+/* Diagnostics: cumulative host nanoseconds of the last dcl_step_fwd at the end of each of its sections: out[8] =
+ * classify / count-table copy / zero-fill issued, + wait for the count table, + host plan, + generator blocks queued
+ * for upload, + plan kernel (or row copies) issued, + select / gather / forward issued, + exchange / backward issued, -. */
+int dcl_step_timing(long long* out);
+
+/* ---------------------------------------------------------------- NCCL plumbing of the sharded step
+ * libnccl.so.2 is taken from the process (torch has it mapped) or dlopen'ed; nothing is linked.  Rank 0 creates the
+ * 128-byte id, every rank receives it out of band (e.g. one torch.distributed broadcast) and calls dcl_comm_init on
+ * its own device.  dcl_comm_all_gather: `bytes_per_rank` from send into recv [world*bytes_per_rank], in place when
+ * send == recv + rank*bytes_per_rank. */
+int dcl_comm_unique_id(void* out128);
+int dcl_comm_init(const void* id128, int world, int rank, void** comm);
+int dcl_comm_destroy(void* comm);
+int dcl_comm_all_gather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
 
 #ifdef __cplusplus
 }

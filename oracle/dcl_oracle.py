@@ -228,7 +228,7 @@ def _row_chunks(n: int, chunk: int):
 
 
 def contrast_closed_form(F, y, temperature=0.07, base_temperature=0.07, mode=PIXEL,
-                         want_grad=True, chunk=2048, dtype=torch.float64):
+                         want_grad=True, chunk=2048, dtype=torch.float64, device=None):
     """Loss and dLoss/dF for the row-normalised contrast.
 
     mode=PIXEL  : loss.py:339-389   lp_ij = l_ij - log(exp(l_ij) + sum_{neg k} exp(l_ik))
@@ -236,21 +236,23 @@ def contrast_closed_form(F, y, temperature=0.07, base_temperature=0.07, mode=PIX
     Common part : a = F F^T / T, m_i = row max (detached), l = normalize(a - m) (L2 over the
     row, eps 1e-12), positives = same label minus the diagonal, loss = mean_i
     [-(T/T_b) * mean_{j in pos(i)} lp_ij].
-    Returns (loss float, dF [N,D] or None, stats dict of per-row tensors).
+    Returns (loss float, dF [N,D] or None, stats dict of per-row tensors).  `device`: where the (plain torch)
+    arithmetic runs; tests pass a CUDA device for N = 65536, where the fp64 chunks take minutes on host cores.
     """
-    F = torch.as_tensor(F).to(dtype)
-    y = torch.as_tensor(y).to(torch.int64)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    F = torch.as_tensor(F).to(device=dev, dtype=dtype)
+    y = torch.as_tensor(y).to(device=dev, dtype=torch.int64)
     N = F.shape[0]
     T, Tb = float(temperature), float(base_temperature)
     c = (T / Tb) / N
-    m = torch.empty(N, dtype=dtype)
-    r = torch.empty(N, dtype=dtype)
-    neg = torch.empty(N, dtype=dtype)       # PIXEL: sum over negatives; SUPCON: sum over k != i
-    P = torch.empty(N, dtype=dtype)
-    rowloss = torch.empty(N, dtype=dtype)
-    Q = torch.empty(N, dtype=dtype)
-    R = torch.empty(N, dtype=dtype)
-    ar = torch.arange(N)
+    m = torch.empty(N, dtype=dtype, device=dev)
+    r = torch.empty(N, dtype=dtype, device=dev)
+    neg = torch.empty(N, dtype=dtype, device=dev)       # PIXEL: sum over negatives; SUPCON: sum over k != i
+    P = torch.empty(N, dtype=dtype, device=dev)
+    rowloss = torch.empty(N, dtype=dtype, device=dev)
+    Q = torch.empty(N, dtype=dtype, device=dev)
+    R = torch.empty(N, dtype=dtype, device=dev)
+    ar = torch.arange(N, device=dev)
     for s, e in _row_chunks(N, chunk):
         a = (F[s:e] @ F.T) / T
         mi = a.max(dim=1).values

@@ -88,6 +88,32 @@ def run_contrast(ref, name, seed, A, V, K, offset):
     print(f"contrast_{name}: N={A * V} loss={loss.item():.6f}")
 
 
+def contrast_inputs(seed, A, V, K):
+    """Inputs of the large contrast fixtures, regenerated from the seed by the tests (torch's CPU generator is
+    deterministic for a given torch build; the fixture stores a digest of the bytes to prove it)."""
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randint(0, K, (A,), generator=g).float()
+    cent = torch.randn(K, 128, generator=g)
+    X = 0.5 * torch.randn(A, V, 128, generator=g) + 0.5 * cent[y.long()][:, None, :]
+    return X, y
+
+
+def run_contrast_large(ref, name, seed, A, V, K):
+    """Reference `_contrastive` (loss.py:339-389) at N = A*V in the thousands: the size class where the CUDA path
+    takes its degree-1 polynomial / positive-pair series route, pinned to the reference's own output."""
+    import hashlib
+    X, y = contrast_inputs(seed, A, V, K)
+    digest = hashlib.sha256(X.numpy().tobytes()).hexdigest()
+    X = X.clone().requires_grad_(True)
+    crit = ref.PixelContrastLoss(device="cpu")
+    loss = crit._contrastive(X, y)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, f"contrastL_{name}.npz"), seed=seed, A=A, V=V, K=K,
+                        x_sha256=np.frombuffer(bytes.fromhex(digest), dtype=np.uint8),
+                        y=y.numpy().astype(np.int64), loss=loss.item(), dX=X.grad.numpy())
+    print(f"contrastL_{name}: N={A * V} loss={loss.item():.6f}")
+
+
 def run_supcon(ref, name, seed, B, h, w, use_labels):
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)                       # projection init (nn.Linear default init)
@@ -118,6 +144,8 @@ def main():
     run_contrast(ref, "n192", 21, 24, 8, 5, 0.0)
     run_contrast(ref, "n130_offset", 22, 26, 5, 4, 1.5)
     run_contrast(ref, "n40_twoclass", 23, 20, 2, 2, 0.0)
+    run_contrast_large(ref, "n2048", 41, 64, 32, 16)
+    run_contrast_large(ref, "n8192", 42, 128, 64, 16)
     run_supcon(ref, "labels_b4", 31, 4, 4, 6, True)
     run_supcon(ref, "simclr_b3", 32, 3, 4, 6, False)
     run_supcon(ref, "labels_b16", 33, 16, 2, 3, True)

@@ -84,6 +84,65 @@ def test_contrast_rows_vs_reference_golden(dcl, case):
     assert _relmax(dX, g["dX"]) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("case", ["contrastL_n2048.npz", "contrastL_n8192.npz"])
+def test_contrast_rows_vs_reference_golden_large(dcl, case):
+    """The reference's own `_contrastive` (utils/loss.py:339-389, fp32 CPU autograd) at N = 2048 / 8192: the sizes
+    where the CUDA path runs its degree-1 polynomial exp and the positive-pair series (the small fixtures only reach
+    the exact fallback), so the fast path is pinned to the reference and not only to the oracle."""
+    from test_oracle_golden import _large_contrast_case
+    F, yy, loss_ref, dX_ref, (A, V) = _large_contrast_case(case)
+    Zd = F.cuda().requires_grad_(True)
+    loss = dcl.contrast_rows(Zd, yy.cuda(), 0)
+    loss.backward()
+    assert abs(loss.item() - loss_ref) <= LOSS_RTOL * abs(loss_ref)
+    dX = Zd.grad.cpu().numpy().reshape(V, A, 128).transpose(1, 0, 2)
+    assert _relmax(dX, dX_ref) <= GRAD_RTOL
+    # the rows in class-sorted order (what the sampler hands the kernels): same numbers, permuted
+    order = torch.argsort(yy, stable=True)
+    Zs = F[order].cuda().requires_grad_(True)
+    loss_s = dcl.contrast_rows(Zs, yy[order].cuda(), 0)
+    loss_s.backward()
+    assert abs(loss_s.item() - loss_ref) <= LOSS_RTOL * abs(loss_ref)
+    back = torch.empty_like(Zs.grad)
+    back[order.cuda()] = Zs.grad
+    assert _relmax(back.cpu().numpy().reshape(V, A, 128).transpose(1, 0, 2), dX_ref) <= GRAD_RTOL
+
+
+def test_contrast_n65536_vs_fp64_closed_form(dcl):
+    """cfg4's size (65536 anchors, the size every multi-GPU number is quoted on).  The reference cannot allocate
+    N x N there; the chunked fp64 closed form - pinned to the reference at N <= 8192 by
+    tests/test_oracle_golden.py - runs on the GPU in plain torch as the checker."""
+    n, K = 65536, 16
+    g = torch.Generator().manual_seed(65536)
+    y = torch.randint(0, K, (n,), generator=g).sort().values
+    cent = 0.5 * torch.randn(19, 128, generator=g)
+    Z = 0.5 * torch.randn(n, 128, generator=g) + cent[y]
+    Zd = Z.cuda().requires_grad_(True)
+    loss = dcl.contrast_rows(Zd, y.cuda(), 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    loss_o, dZ_o, _ = O.contrast_closed_form(Z, y, 0.07, 0.07, 0, chunk=2048, device="cuda")
+    assert abs(loss.item() - loss_o) <= LOSS_RTOL * abs(loss_o)
+    err = float((Zd.grad.double() - dZ_o).abs().max() / dZ_o.abs().max())
+    assert err <= GRAD_RTOL, err
+    # and against the same bf16-rounded rows the tensor cores see: only kernel arithmetic differs
+    loss_b, dZ_b, _ = O.contrast_closed_form(Z.to(torch.bfloat16).float(), y, 0.07, 0.07, 0, chunk=2048, device="cuda")
+    assert abs(loss.item() - loss_b) <= 2e-5 * abs(loss_b)
+    assert float((Zd.grad.double() - dZ_b).abs().max() / dZ_b.abs().max()) <= 5e-3
+
+
+def test_single_view_rows_give_nan_like_reference(dcl):
+    """n_view == 1: no row has a positive pair, the reference divides by zero (loss.py:383) and returns NaN."""
+    g = torch.Generator().manual_seed(3)
+    Z = torch.randn(12, 128, generator=g)
+    y = torch.arange(12)
+    loss = dcl.contrast_rows(Z.cuda(), y.cuda(), 0)
+    assert torch.isnan(loss).item()
+    port = O.PixelContrastPort()
+    ref = port._contrastive(Z[:, None, :], y.float())
+    assert torch.isnan(ref).item()
+
+
 def test_temperature_and_upstream_gradient(dcl):
     g = torch.Generator().manual_seed(5)
     y = torch.randint(0, 4, (200,), generator=g).sort().values
@@ -186,7 +245,8 @@ def test_fused_step_equals_stage_by_stage(dcl, B, H, W, h, w, K, mv, ms):
             x = feats.clone().requires_grad_(True)
             torch.manual_seed(5)
             res = []
-            for _ in range(3):                       # consecutive steps: the second and third use the look-ahead stream
+            for _ in range(5):                       # consecutive steps: from the third on the look-ahead stream runs and
+                                                     # the fused step replays the permutations on the GPU (k_plan)
                 x.grad = None
                 loss = crit(x, labels=labels, predict=predict)
                 (loss * 1.5).backward()
@@ -262,6 +322,122 @@ def test_supcon_module_vs_reference_golden(dcl, case):
     # tensor-core operands, so they get their own (looser, stated) bound.
     for k, p in crit.projection.named_parameters():
         assert _relmax(p.grad.cpu(), g["g_" + k.replace(".", "_")]) <= 3e-2
+
+
+def _doubly_inputs(B, H, W, h, w, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    bh = max(1, H // 6)
+    coarse = torch.randint(0, K, (B, (H + bh - 1) // bh, (W + bh - 1) // bh), generator=g)
+    labels = coarse.repeat_interleave(bh, 1).repeat_interleave(bh, 2)[:, :H, :W].contiguous().long()
+    labels[torch.rand(B, H, W, generator=g) < 0.05] = 255
+    predict = torch.randn(B, 19, h, w, generator=g)
+    feats = torch.randn(2 * B, 128, h, w, generator=g) + 0.3 * torch.randn(2 * B, 128, 1, 1, generator=g)
+    weather = torch.randint(0, 4, (B, 1), generator=g)
+    return feats, labels, predict, weather
+
+
+@pytest.mark.parametrize("B,H,W,h,w,K,mv,ms", [(2, 64, 128, 16, 32, 5, 8, 1024), (3, 48, 80, 12, 20, 4, 5, 64)])
+def test_doubly_combination_vs_ports(dcl, B, H, W, h, w, K, mv, ms):
+    """The `supcon_pixelcontrast_focal` combination of trainer.py:143-158: SupConLoss on fine_feat [2B,...],
+    PixelContrastLoss on fine_feat[:B], total = (supcon + pixel) / batch_size, ONE backward into the shared tensor.
+    (a) the two drop-in modules called the trainer's way, (b) DoublyContrastiveLoss (fused touch points) and (c) the
+    CPU ports must agree on both losses and on the summed gradient."""
+    feats, labels, predict, weather = _doubly_inputs(B, H, W, h, w, K, seed=B * 100 + h)
+    opts = types.SimpleNamespace(deeplab=False)
+    torch.manual_seed(17)
+    sup = dcl.SupConLoss(device="cuda", opts=opts)
+    pix = dcl.PixelContrastLoss(device="cuda")
+    pix.max_samples, pix.max_views = ms, mv
+    lab_d, pred_d, w_d = labels.cuda(), predict.cuda(), weather.cuda()
+    # (a) trainer's way
+    xa = feats.cuda().requires_grad_(True)
+    torch.manual_seed(5)
+    la_s = sup(xa, class_labels=w_d)
+    la_p = pix(xa[:B], labels=lab_d, predict=pred_d)
+    ((la_s + la_p) / B).backward()
+    ga = xa.grad.clone()
+    wa = [p.grad.clone() for p in sup.projection.parameters()]
+    for p in sup.projection.parameters():
+        p.grad = None
+    # (b) fused
+    both = dcl.DoublyContrastiveLoss(pix, sup)
+    xb = feats.cuda().requires_grad_(True)
+    torch.manual_seed(5)
+    lb_s, lb_p = both(xb, labels=lab_d, predict=pred_d, class_labels=w_d)
+    ((lb_s + lb_p) / B).backward()
+    assert lb_s.item() == la_s.item() and lb_p.item() == la_p.item()
+    assert torch.allclose(xb.grad, ga, rtol=1e-5, atol=1e-7 * float(ga.abs().max()))
+    for p, q in zip(sup.projection.parameters(), wa):
+        assert torch.allclose(p.grad, q, rtol=1e-5, atol=1e-9)
+    # (c) ports
+    sup_o = O.SupConPort(opts=opts)
+    sup_o.projection.load_state_dict({k: v.detach().cpu() for k, v in sup.projection.state_dict().items()})
+    pix_o = O.PixelContrastPort()
+    pix_o.max_samples, pix_o.max_views = ms, mv
+    xc = feats.clone().requires_grad_(True)
+    torch.manual_seed(5)
+    lc_s = sup_o(xc, class_labels=weather)
+    lc_p = pix_o(xc[:B], labels=labels, predict=predict)
+    ((lc_s + lc_p) / B).backward()
+    assert abs(lb_s.item() - lc_s.item()) <= LOSS_RTOL * abs(lc_s.item())
+    assert abs(lb_p.item() - lc_p.item()) <= LOSS_RTOL * abs(lc_p.item())
+    assert _relmax(xb.grad.cpu(), xc.grad) <= GRAD_RTOL
+
+
+def test_supcon_mask_odd_batch_and_float_labels(dcl):
+    """SupConLoss's remaining call forms (loss.py:149-159): an explicit same-group `mask`, float labels compared by
+    value, and the failure on an odd number of crops."""
+    opts = types.SimpleNamespace(deeplab=False)
+    torch.manual_seed(3)
+    sup = dcl.SupConLoss(device="cuda", opts=opts)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(8, 128, 4, 6, generator=g).cuda()
+    y = torch.tensor([[2], [0], [2], [1]])
+    l_lab = sup(x, class_labels=y.cuda())
+    mask = torch.eq(y, y.T).float().cuda()
+    l_mask = sup(x, mask=mask)
+    assert l_mask.item() == l_lab.item()
+    l_float = sup(x, class_labels=torch.tensor([[0.5], [-1.25], [0.5], [7.0]]).cuda())
+    assert l_float.item() == l_lab.item()
+    assert sup(x, mask=torch.eye(4).cuda()).item() == sup(x).item()
+    bad = mask.clone()
+    bad[0, 1] = 1.0                                     # not an equivalence relation
+    with pytest.raises(NotImplementedError):
+        sup(x, mask=bad)
+    with pytest.raises(ValueError):
+        sup(torch.randn(7, 128, 4, 6).cuda())
+    sup_o = O.SupConPort(opts=opts)
+    sup_o.projection.load_state_dict({k: v.detach().cpu() for k, v in sup.projection.state_dict().items()})
+    ref = sup_o(x.cpu(), mask=mask.cpu())
+    assert abs(l_mask.item() - ref.item()) <= LOSS_RTOL * abs(ref.item())
+
+
+def test_labels_outside_byte_range_raise(dcl):
+    crit = dcl.PixelContrastLoss(device="cuda")
+    labels = torch.zeros(1, 16, 16, dtype=torch.long)
+    labels[0, 4, 8] = 300                      # a pixel the legacy-nearest down-sampling picks (rows/cols 0, 4, 8, 12)
+    with pytest.raises(ValueError):
+        crit(torch.randn(1, 128, 4, 4).cuda(), labels=labels.cuda(), predict=torch.randn(1, 19, 4, 4).cuda())
+    with pytest.raises(dcl.loss._lib.DclError):
+        crit(torch.randn(1, 128, 4, 4).cuda(), labels=labels, predict=torch.randn(1, 19, 4, 4).cuda())
+
+
+def test_max_samples_raised_on_live_module(dcl):
+    """`max_samples` is a public mutable attribute (loss.py:258): raising it between calls must re-size the buffers."""
+    from doubly_contrastive_semseg_b200.synthetic import WORKLOADS, make_inputs
+    wl = WORKLOADS["small"]
+    d = make_inputs(wl, seed=4, device="cuda")
+    crit = dcl.PixelContrastLoss(device="cuda")
+    crit.max_views = 64
+    for ms in (1000, 1024, 1100, 2048):
+        crit.max_samples = ms
+        x = d["feats"].clone().requires_grad_(True)
+        torch.manual_seed(1)
+        loss = crit(x, labels=d["labels"], predict=d["predict"])
+        loss.backward()
+        plan = crit.last_plan
+        assert plan.n_view == min(ms // plan.A, 64) and crit.last_layout.n == plan.A * plan.n_view
+        assert int((x.grad.abs().sum(1) != 0).sum()) == crit.last_layout.n
 
 
 def test_gap_matches_torch(dcl):
@@ -340,6 +516,49 @@ def test_full_size_cfg2_properties_and_oracle(dcl):
     loss_o, dF_o, _ = O.pixel_contrast_closed_form(rows_f.cpu(), torch.from_numpy(lay.y[: lay.n]).long())
     assert abs(loss.item() - loss_o) <= LOSS_RTOL * abs(loss_o)
     assert _relmax(rows_g.cpu(), dF_o) <= GRAD_RTOL
+
+
+def test_full_size_cfg3_doubly_step(dcl):
+    """BASELINE configs[2] at full size: the doubly contrastive step on one [32,128,256,512] tensor (2.15 GB) -
+    image-level term on all 32 crops, pixel term on the first 16, (supcon + pixel) / batch_size, one backward
+    (trainer.py:143-158).  Checked against the CPU port of the image-level term (dense part of the gradient) and the
+    fp64 closed form of the pixel term on the gathered rows (the part at the sampled pixels)."""
+    from doubly_contrastive_semseg_b200.synthetic import WORKLOADS, make_inputs
+    wl = WORKLOADS["cfg3"]
+    d = make_inputs(wl, seed=3, device="cuda")
+    opts = types.SimpleNamespace(deeplab=False)
+    torch.manual_seed(23)
+    crit = dcl.DoublyContrastiveLoss(device="cuda", opts=opts)
+    crit.pixel.max_samples, crit.pixel.max_views = wl.max_samples, wl.max_views
+    x = d["feats"].requires_grad_(True)
+    torch.manual_seed(3)
+    l_sup, l_pix = crit(x, labels=d["labels"], predict=d["predict"], class_labels=d["weather"])
+    ((l_sup + l_pix) / wl.B).backward()
+    lay = crit.pixel.last_layout
+    assert lay.n == 8192 and crit.pixel.last_plan.A == 256 and crit.pixel.last_plan.n_view == 32
+    hw = wl.h * wl.w
+    pixi = crit.pixel.last_pix[: lay.n].long()
+    b, p = pixi // hw, pixi % hw
+    assert int(b.max()) < wl.B and torch.unique(pixi).numel() == lay.n
+    # image-level term: port on the CPU with the same projection
+    sup_o = O.SupConPort(opts=opts)
+    sup_o.projection.load_state_dict({k: v.detach().cpu() for k, v in crit.supcon.projection.state_dict().items()})
+    xc = x.detach().cpu().requires_grad_(True)
+    ls_o = sup_o(xc, class_labels=d["weather"].cpu())
+    (ls_o / wl.B).backward()
+    assert abs(l_sup.item() - ls_o.item()) <= LOSS_RTOL * abs(ls_o.item())
+    want = xc.grad.cuda()                                      # dense part
+    # pixel term: fp64 closed form on the gathered rows
+    rows_f = x.detach().reshape(2 * wl.B, 128, hw)[b, :, p]
+    lp_o, dF_o, _ = O.pixel_contrast_closed_form(rows_f.cpu(), torch.from_numpy(lay.y[: lay.n]).long())
+    assert abs(l_pix.item() - lp_o) <= LOSS_RTOL * abs(lp_o)
+    got_rows = x.grad.reshape(2 * wl.B, 128, hw)[b, :, p] - want.reshape(2 * wl.B, 128, hw)[b, :, p]
+    assert _relmax(got_rows.cpu(), dF_o / wl.B) <= GRAD_RTOL
+    # everywhere else the gradient is the image-level broadcast alone
+    sparse = torch.zeros_like(want).reshape(2 * wl.B, 128, hw)
+    sparse[b, :, p] = got_rows
+    resid = (x.grad - want - sparse.reshape_as(want)).abs().max()
+    assert float(resid) <= GRAD_RTOL * float(want.abs().max())
 
 
 # ------------------------------------------------------------------ multi-GPU (needs >= 2 GPUs)

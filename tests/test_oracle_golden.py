@@ -108,6 +108,36 @@ def test_contrast_closed_form_vs_reference(case):
     assert np.abs(dF_p.numpy() - dF.numpy()[perm]).max() <= 1e-12 * np.abs(dF.numpy()).max() + 1e-18
 
 
+def _large_contrast_case(case):
+    """Rows (reference order, row = v*A + a), labels and golden outputs of a contrastL_* fixture; the inputs are
+    regenerated from the stored seed and checked against the stored digest."""
+    import hashlib
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = _load(case)
+    A, V, K = int(g["A"]), int(g["V"]), int(g["K"])
+    X, y = mg.contrast_inputs(int(g["seed"]), A, V, K)
+    digest = np.frombuffer(hashlib.sha256(X.numpy().tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, g["x_sha256"]), "regenerated inputs differ from the ones the reference saw"
+    assert np.array_equal(y.numpy().astype(np.int64), g["y"])
+    F = torch.cat([X[:, v] for v in range(V)], dim=0)
+    yy = torch.from_numpy(np.tile(g["y"], V))
+    return F, yy, float(g["loss"]), g["dX"], (A, V)
+
+
+@pytest.mark.parametrize("case", ["contrastL_n2048.npz", "contrastL_n8192.npz"])
+def test_contrast_closed_form_vs_reference_large(case):
+    """The reference's own `_contrastive` at N = 2048 / 8192 (fp32 autograd) pins the fp64 closed form at the sizes
+    where the CUDA path switches to its degree-1 polynomial and positive-pair series."""
+    F, yy, loss_ref, dX_ref, (A, V) = _large_contrast_case(case)
+    loss, dF, _ = O.pixel_contrast_closed_form(F, yy, chunk=1024)
+    assert abs(loss - loss_ref) <= 2e-6 * abs(loss_ref)
+    dX = dF.numpy().reshape(V, A, 128).transpose(1, 0, 2)
+    assert np.abs(dX - dX_ref).max() <= 2e-4 * np.abs(dX_ref).max()
+
+
 # ------------------------------------------------------------------ image-level term
 @pytest.mark.parametrize("case", sorted(os.path.basename(p) for p in
                                         glob.glob(os.path.join(GOLDEN, "supcon_*.npz"))))

@@ -234,3 +234,128 @@ def test_c_plan_equals_numpy_plan_on_random_tables():
             assert np.array_equal(getattr(got.layout, name), getattr(ref.layout, name)), (trial, name)
         done += 1
     assert done >= 15
+
+
+# ------------------------------------------------------------------ device-mode plan (k_plan emulated in numpy)
+def _temper(y):
+    y = y.astype(np.uint32)
+    y ^= y >> np.uint32(11)
+    y ^= (y << np.uint32(7)) & np.uint32(0x9D2C5680)
+    y ^= (y << np.uint32(15)) & np.uint32(0xEFC60000)
+    y ^= y >> np.uint32(18)
+    return y
+
+
+def _emulate_k_plan(anchors, n_local, ring, ring_blocks, ycls, ycnt, yoff, world, rank, n_view, n_pad):
+    """What csrc/dcl_plan.cu computes, restated with numpy from the same descriptors: the kept prefix of every local
+    permutation out of the mirrored generator stream -> row requests; labels of every rank block."""
+    req = np.full((n_pad, 4), -9, dtype=np.int32)
+    y_all = np.full(world * n_pad, -9, dtype=np.int32)
+    for i in range(n_local):
+        a = anchors[i]
+        for easy in (0, 1):
+            n = int(a["num_easy"] if easy else a["num_hard"])
+            k = int(a["keep_easy"] if easy else a["keep_hard"])
+            g = int(a["g_easy"] if easy else a["g_hard"])
+            row = int(a["row0"]) + (int(a["keep_hard"]) if easy else 0)
+            moved = {}
+            for s in range(k):
+                j = s
+                if s < n - 1:
+                    gi = g + s
+                    blk, word = divmod(gi, 624)
+                    x = int(_temper(ring[(blk % ring_blocks) * 624 + word: (blk % ring_blocks) * 624 + word + 1])[0])
+                    j = s + x % (n - s)
+                vi, vj = moved.get(s, s), moved.get(j, j)
+                moved[j] = vi
+                req[row + s] = (int(a["image"]), int(a["cls"]), easy, vj)
+    for r in range(world):
+        for i in range(n_pad):
+            o = i // n_view
+            valid = o < ycnt[r]
+            y_all[r * n_pad + i] = ycls[yoff[r] + o] if valid else -1
+            if not valid and r == rank:
+                req[i] = (-1, -1, -1, -1)
+    return req, y_all
+
+
+_PLAN_ANCHOR = np.dtype([("g_hard", np.uint64), ("g_easy", np.uint64), ("num_hard", np.int32), ("num_easy", np.int32),
+                         ("keep_hard", np.int32), ("keep_easy", np.int32), ("row0", np.int32), ("image", np.int32),
+                         ("cls", np.int32), ("reserved", np.int32)])
+
+
+def _device_plan_check(world):
+    """Consecutive plans requested the way dcl_step_fwd requests them: once the look-ahead stream runs, the host only
+    places the permutations in the stream (device mode); replaying them from the ring the way k_plan does must give
+    the numpy / torch.randperm plan bit for bit, and the generator must end where the reference leaves it."""
+    from doubly_contrastive_semseg_b200 import _lib
+    from doubly_contrastive_semseg_b200.loss import shard_plan
+    assert _PLAN_ANCHOR.itemsize == 48
+    B, h, w, K, mv, ms = 8, 96, 128, 9, 40, 4096
+    lab, pred = _inputs(B, h, w, K, seed=33)
+    counts_all = np.ascontiguousarray(_counts(lab, pred).reshape(B, 256, 2))
+    bl = B // world
+    lib = _lib.load()
+    steps = 5
+    for rank in sorted({0, world - 1}):
+        torch.manual_seed(4242 + rank)
+        refs = [shard_plan(counts_all, rank, world, bl, 255, ms, mv) for _ in range(steps)]
+        end_ref = torch.get_rng_state().clone()
+        torch.manual_seed(4242 + rank)
+        taken = 0
+        for ref in refs:
+            cap = max(128, (ms + 127) // 128 * 128) + 128
+            info = np.zeros(8, dtype=np.int32)
+            an = np.empty((5, B * 256), dtype=np.int64)
+            ranks = np.zeros(cap, dtype=np.int64)
+            req = np.full(cap * 4, -5, dtype=np.int32)
+            y_all = np.full(world * cap, -5, dtype=np.int32)
+            anchors = np.zeros(bl * 256, dtype=_PLAN_ANCHOR)
+            ycls = np.zeros(B * 256, dtype=np.int32)
+            yanchor = np.zeros(B * 256, dtype=np.int32)
+            ycnt = np.zeros(world, dtype=np.int32)
+            yoff = np.zeros(world, dtype=np.int32)
+            meta = (ctypes.c_longlong * 8)()
+            ring_ptr = ctypes.c_void_p()
+            st = torch.get_rng_state()
+            sbuf = st.numpy()
+            rc = lib.dcl_debug_plan_device(
+                counts_all.ctypes.data, bl, world, rank, 255, ms, mv, sbuf.ctypes.data, sbuf.nbytes, info.ctypes.data,
+                an[0].ctypes.data, an[1].ctypes.data, an[2].ctypes.data, an[3].ctypes.data, an[4].ctypes.data,
+                ranks.ctypes.data, req.ctypes.data, y_all.ctypes.data, anchors.ctypes.data, ycls.ctypes.data,
+                yanchor.ctypes.data, ycnt.ctypes.data, yoff.ctypes.data, ctypes.cast(meta, ctypes.c_void_p),
+                ctypes.cast(ctypes.byref(ring_ptr), ctypes.c_void_p))
+            assert rc == 0
+            torch.set_rng_state(st)
+            A, n_view, n, n_pad, n_global = (int(v) for v in info[:5])
+            assert (A, n_view, n_pad, n_global) == (ref.plan.A, ref.plan.n_view, ref.n_pad, ref.n_global)
+            if meta[0]:
+                taken += 1
+                ring_blocks = int(meta[5])
+                ring = np.ctypeslib.as_array(ctypes.cast(ring_ptr, ctypes.POINTER(ctypes.c_uint32)),
+                                             shape=(ring_blocks * 624,))
+                assert int(meta[3]) <= int(meta[4]) < int(meta[6])
+                got_req, got_y = _emulate_k_plan(anchors, int(meta[1]), ring, ring_blocks, ycls, ycnt, yoff, world, rank,
+                                                 n_view, n_pad)
+            else:
+                got_req = req[: n_pad * 4].reshape(n_pad, 4)
+                got_y = y_all[: world * n_pad]
+            assert np.array_equal(got_req, ref.layout.req)
+            assert np.array_equal(got_y[rank * n_pad:(rank + 1) * n_pad], ref.layout.y)
+            # the sorted order handed to the caller reproduces the reference row of every device row
+            order = yanchor[int(yoff[rank]): int(yoff[rank]) + int(ycnt[rank])]
+            assert np.array_equal(np.repeat(order, n_view), ref.layout.anchor[: ref.layout.n])
+        assert torch.equal(torch.get_rng_state(), end_ref)
+        if os.environ.get("DCL_HOST_LOOKAHEAD", "1") != "0":
+            assert taken >= steps - 2, taken
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_device_mode_plan_equals_numpy_plan(world):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path[:0] = [%r, %r]; from test_sharded_cpu import _device_plan_check as c; c(%d)"
+            % (root, os.path.join(root, "tests"), world))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
