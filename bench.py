@@ -52,7 +52,11 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples taken DURING the timed regions."""
+    """nvidia-smi clock / throttle-reason samples taken while the bench measures (warm-up, the timed steps and the
+    end-to-end steps of every workload it runs).  One sample per 100 ms: a faster poll - nvidia-smi at 20 ms, or an
+    in-process NVML thread at 10 ms - holds driver / interpreter locks long enough to show up as launch-latency spikes
+    in a sub-millisecond step (measured: cfg2 0.35 -> 0.60 ms per step), so the sample count is what a 100 ms period
+    yields over the few seconds of measurement."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,15 +73,14 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-            time.sleep(0.25)            # nvidia-smi needs a moment before its first sample
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
         if self.proc is not None:
-            time.sleep(0.05)
+            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -85,7 +88,8 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+               "window": "warm-up, timed steps and end-to-end steps of every workload in this line; nvidia-smi, 100 ms period"}
         if not self.path or not os.path.exists(self.path):
             return out
         sm, mx, reasons = [], [], set()
@@ -462,20 +466,25 @@ def hbm_kernels(L, _lib, dev, peaks, reps=7):
     timed("classify", f_classify, B * 19 * hw * 4 + B * hw * 8 + B * hw * 2,
           "k_classify + k_chunk_prefix: predict read + one label per output pixel + code write")
     code, chunk, counts = code_chunk["v"]
-    timed("select", lambda: L.select_pixels(code, chunk, B, hw, req_dev, n_pad), n_pad * (16 + 4) + n_pad * 4096,
-          "k_select: one 2048-pixel chunk of codes scanned per row (L2-resident after classify in the real step)")
+    rowof = torch.empty(B * hw, dtype=torch.int32, device=dev)
+    timed("select", lambda: L.select_pixels(code, chunk, B, hw, req_dev, n_pad, rowof), n_pad * (16 + 4 + 4) + n_pad * 4096,
+          "k_select (+ 4 MB clear of the pixel->row map): one 2048-pixel chunk of codes scanned per row")
     tiles_box = {}
 
     def f_gather():
-        tiles_box["v"] = L.gather_tiles(d["feats"], pix, n_pad)
+        tiles_box["v"] = L.gather_tiles(d["feats"], pix, n_pad, rowof)
     timed("gather", f_gather, n_pad * DIM * 4 + n_pad * DIM * 2,
-          "k_gather: N*D f32 read at stride h*w (one DRAM sector per element) + bf16 tile write")
+          "k_gather_px: N*D f32 read at stride h*w, chunk-wise in pixel order, + bf16 tile write")
     dF = torch.randn(n_pad, DIM, device=dev)
     g = torch.ones((), device=dev)
     dfe = torch.zeros_like(d["feats"])
-    timed("scatter", lambda: _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfe), B, hw, 0, _stream()),
-          2 * n_pad * DIM * 4, "k_scatter: N*D f32 read + N*D scattered f32 writes")
-    timed("zero_fill", lambda: dfe.zero_(), dfe.numel() * 4, "dense gradient clear (cudaMemsetAsync / fill)")
+    timed("scatter", lambda: _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfe), B, hw, 0, _p(rowof), _stream()),
+          2 * n_pad * DIM * 4, "k_scatter_px: N*D f32 read + N*D scattered f32 writes, chunk-wise in pixel order")
+    timed("zero_fill", lambda: _lib.call("dcl_zero_fill", _p(dfe), dfe.numel() * 4, 0, _stream()), dfe.numel() * 4,
+          "k_zero_fill: dense gradient clear (runs on a second stream underneath the sweeps in the real step)")
+    gap_g = torch.randn(B * DIM, device=dev)
+    timed("dense_grad", lambda: _lib.call("dcl_dense_grad", _p(dF), _p(rowof), B, _p(g), _p(gap_g), _p(dfe), B, hw, _stream()),
+          dfe.numel() * 4 + n_pad * DIM * 4, "k_dense_grad: pooled-gradient broadcast + anchor gradients, one pass (doubly step)")
     sampler_us = res["classify"]["us"] + res["select"]["us"] + res["gather"]["us"]
     sampler_bytes = B * 19 * hw * 4 + B * hw * 8 + n_pad * DIM * 4 + n_pad * DIM * 2
     res["sampler_total"] = {"us": round(sampler_us, 2), "algorithmic_bytes": int(sampler_bytes),

@@ -3,5 +3,7 @@ loss-module interface.  See DESIGN.md / INTEGRATION.md."""
 from .loss import (MODE_PIXEL, MODE_SUPCON, DoublyContrastiveLoss, PixelContrastLoss, ShardedPixelContrastLoss, SupConLoss,
                    contrast_rows, layout_rows, plan_anchors, shard_plan)
 
-__all__ = ["PixelContrastLoss", "DoublyContrastiveLoss", "ShardedPixelContrastLoss", "SupConLoss", "shard_plan", "contrast_rows", "plan_anchors", "layout_rows",
+from .focal import BoundaryAwareFocalLoss
+
+__all__ = ["BoundaryAwareFocalLoss", "PixelContrastLoss", "DoublyContrastiveLoss", "ShardedPixelContrastLoss", "SupConLoss", "shard_plan", "contrast_rows", "plan_anchors", "layout_rows",
            "MODE_PIXEL", "MODE_SUPCON"]

@@ -23,19 +23,23 @@ SIGNATURES = {
     "dcl_contrast_launches": (_i, [_i, _i]),
     "dcl_debug_partition": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_sample_classify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "dcl_sample_select": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "dcl_host_sample_ranks": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp]),
     "dcl_host_plan_rows": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcl_host_plan_rows_sharded": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcl_debug_plan_device": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz] + [_vp] * 16),
     "dcl_host_lookahead_stats": (_i, [_vp]),
     "dcl_host_plan_timing": (_i, [_vp]),
-    "dcl_gather_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "dcl_gather_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "dcl_pack_rows": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "dcl_contrast_workspace_bytes": (_sz, [_i, _i]),
     "dcl_contrast_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "dcl_contrast_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
-    "dcl_scatter_grad": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "dcl_scatter_grad": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dcl_zero_fill": (_i, [_vp, _sz, _i, _vp]),
+    "dcl_contrast_small_max_rows": (_i, []),
+    "dcl_contrast_small": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dcl_dense_grad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dcl_unpack_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
     "dcl_gap_fwd": (_i, [_vp, _i, _i, _vp, _vp]),
     "dcl_gap_bwd": (_i, [_vp, _i, _i, _vp, _i, _vp]),
@@ -45,7 +49,10 @@ SIGNATURES = {
     "dcl_step_begin": (_i, [_vp, _vp]),
     "dcl_step_fwd": (_i, [_vp, _vp]),
     "dcl_step_timing": (_i, [_vp]),
-    "dcl_step_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "dcl_step_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "dcl_focal_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dcl_focal_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dcl_focal_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "dcl_comm_unique_id": (_i, [_vp]),
     "dcl_comm_init": (_i, [_vp, _i, _i, _vp]),
     "dcl_comm_destroy": (_i, [_vp]),
@@ -64,7 +71,7 @@ class Step(ctypes.Structure):
         ("world", _i), ("rank", _i), ("comm", _vp),
         ("cap", _i),
         ("code", _vp), ("chunk_hist", _vp), ("counts_dev", _vp),
-        ("req_dev", _vp), ("y_dev", _vp), ("pix", _vp), ("plan_dev", _vp),
+        ("req_dev", _vp), ("y_dev", _vp), ("pix", _vp), ("rowof", _vp), ("plan_dev", _vp),
         ("tiles", _vp), ("sqnorm", _vp), ("colA", _vp), ("colB", _vp), ("rowloss", _vp), ("loss_sum", _vp),
         ("loss", _vp),
         ("xchg_send", _vp), ("xchg_recv", _vp), ("dF", _vp),

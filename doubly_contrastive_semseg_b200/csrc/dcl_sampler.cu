@@ -1,6 +1,6 @@
 // HBM-bound front and back ends of the doubly contrastive loss:
 //   classify : argmax over class logits + legacy-nearest label down-sampling + per-chunk
-//              (label, hard/easy) histograms                      (reference loss.py:396-408, :278-312)
+//              (label, hard/easy) histograms + per-image totals    (reference loss.py:396-408, :278-312)
 //   select   : "rank-th pixel of (image, label, hard/easy) in raster order" -> pixel id  (loss.py:308-331)
 //   gather   : NCHW embeddings at the selected pixels -> bf16 F-tiles (+ |f|^2)          (loss.py:333, :409-410)
 //   scatter  : anchor-row gradients back into a dense NCHW gradient                      (autograd of :333)
@@ -21,36 +21,67 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
     return s < in_size - 1 ? s : in_size - 1;
 }
 
-__global__ void __launch_bounds__(512)
+// ---- classify: 256 threads x 8 pixels = one 2048-pixel chunk per CTA.  All label loads and a batch of class planes
+// are in flight before anything is compared (the kernel is HBM-bound: what matters is bytes in flight per SM).
+template <int kBatch>
+__device__ __forceinline__ void argmax_batch(const float* __restrict__ pl, size_t hw, int c0, int cn, float (&best)[8],
+                                             int (&arg)[8]) {
+    float4 v[kBatch][2];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+        if (u < cn) {
+            const float4* p = reinterpret_cast<const float4*>(pl + static_cast<size_t>(c0 + u) * hw);
+            v[u][0] = __ldcs(p);
+            v[u][1] = __ldcs(p + 1);
+        }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+        if (u < cn) {
+            const float x[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // first-index argmax: strict '>' while scanning classes upward; NaN wins once (torch.max)
+                const bool take = (c0 + u == 0) || (x[e] > best[e]) || (x[e] != x[e] && best[e] == best[e]);
+                if (take) { best[e] = x[e]; arg[e] = c0 + u; }
+            }
+        }
+}
+
+__global__ void __launch_bounds__(256)
 k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict, int H, int W, int h,
            int w, int C, float scale_h, float scale_w, uint16_t* __restrict__ code,
-           int32_t* __restrict__ chunk_hist, int n_chunks) {
+           int32_t* __restrict__ chunk_hist, int32_t* __restrict__ counts, int n_chunks) {
     __shared__ int hist[kBins];
     const int b = blockIdx.y, chunk = blockIdx.x, hw = h * w;
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    const int p0 = chunk * kChunk + threadIdx.x * 4;
+    const int p0 = chunk * kChunk + threadIdx.x * 8;
     const float* pl = predict + static_cast<size_t>(b) * C * hw;
     const int64_t* lb = labels + static_cast<size_t>(b) * H * W;
 
-    float best[4];
-    int arg[4];
+    // labels first: eight independent loads (one DRAM sector each at a 4x down-sampling)
+    long long lab[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { best[e] = 0.f; arg[e] = 0; }
-    const bool vec = ((hw & 3) == 0) && (p0 + 3 < hw);
-    if (vec) {
-        // first-index argmax: strict '>' while scanning classes upward; NaN wins once (torch.max)
-        for (int c = 0; c < C; ++c) {
-            const float4 v4 = __ldg(reinterpret_cast<const float4*>(pl + static_cast<size_t>(c) * hw + p0));
-            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool take = (c == 0) || (v[e] > best[e]) || (v[e] != v[e] && best[e] == best[e]);
-                if (take) { best[e] = v[e]; arg[e] = c; }
-            }
+    for (int e = 0; e < 8; ++e) {
+        const int p = p0 + e;
+        lab[e] = -1;
+        if (p < hw) {
+            const int yy = p / w, xx = p - yy * w;
+            lab[e] = __ldcs(lb + static_cast<size_t>(nearest_src(yy, scale_h, H)) * W + nearest_src(xx, scale_w, W));
         }
+    }
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = 0.f; arg[e] = 0; }
+    const bool vec = ((hw & 3) == 0) && (p0 + 7 < hw);
+    if (vec) {
+        const float* q = pl + p0;
+        int c = 0;
+        for (; c + 4 <= C; c += 4) argmax_batch<4>(q, hw, c, 4, best, arg);
+        if (c < C) argmax_batch<4>(q, hw, c, C - c, best, arg);
     } else {
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 8; ++e) {
             if (p0 + e >= hw) break;
             for (int c = 0; c < C; ++c) {
                 const float v = __ldg(pl + static_cast<size_t>(c) * hw + p0 + e);
@@ -59,57 +90,54 @@ k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict
             }
         }
     }
-    uint16_t out[4];
+    // codes + histogram.  Labels are spatially coherent: the pixels of a thread that share its first pixel's label are
+    // counted in two registers (hard / easy) and warp-aggregated with one match; the others (class boundaries) go
+    // one by one.
+    uint16_t out[8];
+    const int lab0 = (lab[0] >= 0 && lab[0] <= 255) ? static_cast<int>(lab[0]) : -1;
+    int n_hard0 = 0, n_easy0 = 0;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int p = p0 + e;
-        int bin = -1;
+    for (int e = 0; e < 8; ++e) {
         out[e] = 0xFFFF;
-        if (p < hw) {
-            const int yy = p / w, xx = p - yy * w;
-            const long long lab = lb[static_cast<size_t>(nearest_src(yy, scale_h, H)) * W +
-                                     nearest_src(xx, scale_w, W)];
-            if (lab >= 0 && lab <= 255) {
-                const int easy = (arg[e] == static_cast<int>(lab)) ? 1 : 0;
-                out[e] = static_cast<uint16_t>(lab | (easy << 8));
-                bin = static_cast<int>(lab) * 2 + easy;
-            }
+        if (lab[e] >= 0 && lab[e] <= 255) {
+            const int l = static_cast<int>(lab[e]);
+            const int easy = (arg[e] == l) ? 1 : 0;
+            out[e] = static_cast<uint16_t>(l | (easy << 8));
+            if (l == lab0) { n_hard0 += 1 - easy; n_easy0 += easy; }
+            else atomicAdd(&hist[l * 2 + easy], 1);
         }
-        // warp-aggregated shared-memory histogram (labels are spatially coherent: heavy collisions)
-        const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
     }
-    if (vec) {
-        *reinterpret_cast<uint2*>(code + static_cast<size_t>(b) * hw + p0) =
-            make_uint2(out[0] | (static_cast<uint32_t>(out[1]) << 16),
-                       out[2] | (static_cast<uint32_t>(out[3]) << 16));
+    {
+        const unsigned peers = __match_any_sync(0xffffffffu, lab0);
+        const int sh = __reduce_add_sync(peers, n_hard0), se = __reduce_add_sync(peers, n_easy0);
+        if (lab0 >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
+            if (sh) atomicAdd(&hist[lab0 * 2], sh);
+            if (se) atomicAdd(&hist[lab0 * 2 + 1], se);
+        }
+    }
+    if (vec && (hw & 7) == 0) {
+        *reinterpret_cast<uint4*>(code + static_cast<size_t>(b) * hw + p0) =
+            make_uint4(out[0] | (static_cast<uint32_t>(out[1]) << 16), out[2] | (static_cast<uint32_t>(out[3]) << 16),
+                       out[4] | (static_cast<uint32_t>(out[5]) << 16), out[6] | (static_cast<uint32_t>(out[7]) << 16));
     } else {
-        for (int e = 0; e < 4; ++e)
+        for (int e = 0; e < 8; ++e)
             if (p0 + e < hw) code[static_cast<size_t>(b) * hw + p0 + e] = out[e];
     }
     __syncthreads();
+    // per-chunk histogram (select scans it) and the per-image totals (the host's count table)
     int32_t* dst = chunk_hist + (static_cast<size_t>(b) * n_chunks + chunk) * kBins;
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) dst[i] = hist[i];
-}
-
-// per (image, bin): exclusive prefix over chunks in place, totals to counts
-__global__ void __launch_bounds__(kBins)
-k_chunk_prefix(int32_t* __restrict__ chunk_hist, int32_t* __restrict__ counts, int n_chunks) {
-    const int b = blockIdx.x, bin = threadIdx.x;
-    int32_t* base = chunk_hist + static_cast<size_t>(b) * n_chunks * kBins + bin;
-    int run = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int v = base[static_cast<size_t>(c) * kBins];
-        base[static_cast<size_t>(c) * kBins] = run;
-        run += v;
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+        const int v = hist[i];
+        dst[i] = v;
+        if (v) atomicAdd(counts + b * kBins + i, v);
     }
-    counts[b * kBins + bin] = run;
 }
 
-// one warp per request
+// one warp per request: chunk from a warp scan over the bin's per-chunk counts, then the whole 2048-pixel chunk of
+// codes in one round trip (8 x 16 bytes per lane, lane l owns pixels [64 l, 64 l + 64) of the chunk: raster order)
 __global__ void __launch_bounds__(256)
-k_select(const uint16_t* __restrict__ code, const int32_t* __restrict__ chunk_prefix, int hw, int n_chunks,
-         const int4* __restrict__ req, int N, int32_t* __restrict__ pix) {
+k_select(const uint16_t* __restrict__ code, const int32_t* __restrict__ chunk_hist, int hw, int n_chunks,
+         const int4* __restrict__ req, int N, int32_t* __restrict__ pix, int32_t* __restrict__ rowof) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -118,63 +146,79 @@ k_select(const uint16_t* __restrict__ code, const int32_t* __restrict__ chunk_pr
         if (lane == 0) pix[n] = -1;
         return;
     }
-    const int b = rq.x, bin = rq.y * 2 + rq.z, rank = rq.w;
+    const int b = rq.x, bin = rq.y * 2 + rq.z;
+    int rem = rq.w;
     const uint16_t want = static_cast<uint16_t>(rq.y | (rq.z << 8));
-    // chunk = last one whose exclusive prefix is <= rank
-    const int32_t* pre = chunk_prefix + static_cast<size_t>(b) * n_chunks * kBins + bin;
-    int chunk = 0;
-    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+    const int32_t* hst = chunk_hist + static_cast<size_t>(b) * n_chunks * kBins + bin;
+    int chunk = -1;
+    for (int c0 = 0; c0 < n_chunks && chunk < 0; c0 += 32) {
         const int c = c0 + lane;
-        const bool le = (c < n_chunks) && (pre[static_cast<size_t>(c) * kBins] <= rank);
-        const unsigned m = __ballot_sync(0xffffffffu, le);
-        if (m) chunk = c0 + 31 - __clz(m);
-        if (m != 0xffffffffu) break;
-    }
-    int rem = rank - pre[static_cast<size_t>(chunk) * kBins];
-    // scan the chunk, 8 codes per lane per step
-    const uint16_t* cc = code + static_cast<size_t>(b) * hw;
-    const int pbeg = chunk * kChunk;
-    const int pend = min(pbeg + kChunk, hw);
-    int found = -1;
-    for (int p0 = pbeg; p0 < pend && found < 0; p0 += 256) {
-        const int mine = p0 + lane * 8;
-        unsigned mask = 0;
-        if (((hw & 7) == 0) && mine + 7 < pend) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(cc + mine));
-            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+        const int cnt = (c < n_chunks) ? __ldg(hst + static_cast<size_t>(c) * kBins) : 0;
+        int incl = cnt;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint16_t cv = static_cast<uint16_t>(wds[e >> 1] >> ((e & 1) * 16));
-                mask |= (cv == want ? 1u : 0u) << e;
-            }
-        } else {
-            for (int e = 0; e < 8; ++e)
-                if (mine + e < pend && cc[mine + e] == want) mask |= 1u << e;
-        }
-        const int cnt = __popc(mask);
-        int incl = cnt;                                   // inclusive warp scan
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (rem < total) {
-            const int excl = incl - cnt;
-            const bool here = (rem >= excl) && (rem < incl);
-            int pos = -1;
-            if (here) {
-                int k = rem - excl;                        // k-th set bit of mask
-                unsigned m = mask;
-                for (int i = 0; i < k; ++i) m &= m - 1;
-                pos = mine + __ffs(m) - 1;
-            }
-            const unsigned who = __ballot_sync(0xffffffffu, here);
-            found = __shfl_sync(0xffffffffu, pos, __ffs(who) - 1);
+            const unsigned m = __ballot_sync(0xffffffffu, rem < incl);     // first lane whose inclusive count exceeds rem
+            const int src = __ffs(m) - 1;
+            chunk = c0 + src;
+            rem -= __shfl_sync(0xffffffffu, incl - cnt, src);
         } else {
             rem -= total;
         }
     }
-    if (lane == 0) pix[n] = found >= 0 ? b * hw + found : -1;
+    if (chunk < 0) {                      // rank beyond the bin's population: cannot happen for a valid plan
+        if (lane == 0) pix[n] = -1;
+        return;
+    }
+    const uint16_t* cc = code + static_cast<size_t>(b) * hw;
+    const int pbeg = chunk * kChunk, pend = min(pbeg + kChunk, hw);
+    const int mine = pbeg + lane * 64;
+    unsigned long long mask = 0ull;
+    if (((hw & 7) == 0) && mine + 63 < pend) {
+        uint4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(reinterpret_cast<const uint4*>(cc + mine) + q);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t wds[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint16_t cv = static_cast<uint16_t>(wds[e >> 1] >> ((e & 1) * 16));
+                mask |= static_cast<unsigned long long>(cv == want ? 1u : 0u) << (q * 8 + e);
+            }
+        }
+    } else {
+        for (int e = 0; e < 64; ++e)
+            if (mine + e < pend && cc[mine + e] == want) mask |= 1ull << e;
+    }
+    const int cnt = __popcll(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, rem < incl);
+    int found = -1;
+    if (m) {
+        const int src = __ffs(m) - 1;
+        int pos = -1;
+        if (lane == src) {
+            int k = rem - (incl - cnt);                // k-th set bit of this lane's mask
+            unsigned long long mm = mask;
+            for (int i = 0; i < k; ++i) mm &= mm - 1;
+            pos = mine + __ffsll(static_cast<long long>(mm)) - 1;
+        }
+        found = __shfl_sync(0xffffffffu, pos, src);
+    }
+    if (lane == 0) {
+        pix[n] = found >= 0 ? b * hw + found : -1;
+        if (rowof && found >= 0) rowof[static_cast<size_t>(b) * hw + found] = n;     // inverse map for the chunk-wise kernels
+    }
 }
 
 // one warp per anchor row; lane l owns channels 4l..4l+3
@@ -246,6 +290,209 @@ k_unpack(const float* __restrict__ dF, int n, const float* __restrict__ grad_out
     float4 v = __ldg(reinterpret_cast<const float4*>(dF) + i);
     v.x *= g; v.y *= g; v.z *= g; v.w *= g;
     reinterpret_cast<float4*>(dZ)[i] = v;
+}
+
+// ------------------------------------------------------------------------------- pixel-ordered gather / scatter
+// The sampled pixels of an image are a sparse subset of its h*w positions, and the embedding tensor is NCHW: one
+// anchor row touches 128 channel planes at the same pixel offset.  Walking the anchors row by row (one warp per row)
+// costs a DRAM line per (row, channel) in an order without any locality (26 us for 8192 rows, 8x that at 65536).
+// k_select therefore also records `rowof[image*h*w + pixel] = row`, and the kernels below work per 2048-pixel chunk:
+// a CTA reads its chunk of the map (8 KB, coalesced), compacts the sampled pixels in ascending order in shared
+// memory, and then moves 32 of them at a time, channel plane by channel plane - the 32 lanes of a warp touch
+// ascending addresses inside one 8 KB window of one plane, so lines are shared between neighbouring anchors when the
+// sampling is dense and DRAM pages stay open when it is not.
+constexpr int kGsThreads = 256;
+
+// compact the sampled pixels of chunk (b, chunk): list[i] = (pixel offset inside the image, row); returns the count
+__device__ __forceinline__ int chunk_samples(const int32_t* __restrict__ rowof, int b, int chunk, int hw, int2* list,
+                                             int* warp_tot) {
+    const int p0 = chunk * kChunk + threadIdx.x * 8;
+    int r[8];
+    const int32_t* src = rowof + static_cast<size_t>(b) * hw + p0;
+    if (((hw & 3) == 0) && p0 + 7 < hw) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(src)), c = __ldg(reinterpret_cast<const int4*>(src) + 1);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = c.x; r[5] = c.y; r[6] = c.z; r[7] = c.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = (p0 + e < hw) ? __ldg(src + e) : -1;
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cnt += r[e] >= 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kGsThreads / 32; ++w) {
+        const int t = warp_tot[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    int o = base + incl - cnt;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (r[e] >= 0) list[o++] = make_int2(p0 + e, r[e]);
+    __syncthreads();
+    return total;
+}
+
+// gather: feats [B,128,hw] f32 at the sampled pixels -> bf16 F-tiles + |f|^2 (rows that no pixel maps to, i.e. the
+// padding rows, are cleared by k_gather_pad)
+__global__ void __launch_bounds__(kGsThreads)
+k_gather_px(const float* __restrict__ feats, int hw, const int32_t* __restrict__ rowof, uint8_t* __restrict__ tiles,
+            float* __restrict__ sqnorm) {
+    __shared__ int2 list[kChunk];
+    __shared__ int warp_tot[kGsThreads / 32];
+    __shared__ float tile[32][kDim + 1];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int n = chunk_samples(rowof, b, chunk, hw, list, warp_tot);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* plane0 = feats + static_cast<size_t>(b) * kDim * hw;
+    for (int g0 = 0; g0 < n; g0 += 32) {
+        const int m = min(32, n - g0);
+        const int2 mine = list[g0 + min(lane, m - 1)];
+        // warp w: channels 16 w .. 16 w + 15, sixteen independent loads in flight per lane
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(plane0 + static_cast<size_t>(warp * 16 + u) * hw + mine.x);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tile[lane][warp * 16 + u] = v[u];
+        __syncthreads();
+        // warp w writes rows w, w + 8, ..: lane l owns channels 4 l .. 4 l + 3 (256 contiguous bytes per row)
+        for (int i = warp; i < m; i += kGsThreads / 32) {
+            const int row = list[g0 + i].y;
+            const float a0 = tile[i][lane * 4], a1 = tile[i][lane * 4 + 1], a2 = tile[i][lane * 4 + 2], a3 = tile[i][lane * 4 + 3];
+            __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(a2, a3);
+            const float r0 = __low2float(lo), r1 = __high2float(lo), r2 = __low2float(hi), r3 = __high2float(hi);
+            float sq = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            uint8_t* t = tiles + static_cast<size_t>(row >> 7) * kTileBytes + ftile_offset(row & 127, lane * 4);
+            *reinterpret_cast<uint2*>(t) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            if (lane == 0) sqnorm[row] = sq;
+        }
+        __syncthreads();
+    }
+}
+
+// padding rows (pix < 0): zero features, zero norm.  One warp per row; rows with a pixel are left alone.
+__global__ void __launch_bounds__(256)
+k_gather_pad(const int32_t* __restrict__ pix, int n_pad, uint8_t* __restrict__ tiles, float* __restrict__ sqnorm) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= n_pad || pix[n] >= 0) return;
+    uint8_t* t = tiles + static_cast<size_t>(n >> 7) * kTileBytes + ftile_offset(n & 127, lane * 4);
+    *reinterpret_cast<uint2*>(t) = make_uint2(0u, 0u);
+    if (lane == 0) sqnorm[n] = 0.f;
+}
+
+// scatter: dfeats [B,128,hw] at the sampled pixels = (kAdd ? old : 0) + dF[row] * g, chunk by chunk, plane by plane
+template <bool kAdd>
+__global__ void __launch_bounds__(kGsThreads)
+k_scatter_px(const float* __restrict__ dF, const int32_t* __restrict__ rowof, const float* __restrict__ grad_out,
+             float* __restrict__ dfeats, int hw) {
+    __shared__ int2 list[kChunk];
+    __shared__ int warp_tot[kGsThreads / 32];
+    __shared__ float tile[32][kDim + 1];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int n = chunk_samples(rowof, b, chunk, hw, list, warp_tot);
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float g = __ldg(grad_out);
+    float* plane0 = dfeats + static_cast<size_t>(b) * kDim * hw;
+    for (int g0 = 0; g0 < n; g0 += 32) {
+        const int m = min(32, n - g0);
+        for (int i = warp; i < m; i += kGsThreads / 32) {
+            const int row = list[g0 + i].y;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dF + static_cast<size_t>(row) * kDim) + lane);
+            tile[i][lane * 4] = v.x; tile[i][lane * 4 + 1] = v.y;
+            tile[i][lane * 4 + 2] = v.z; tile[i][lane * 4 + 3] = v.w;
+        }
+        __syncthreads();
+        if (lane < m) {
+            const int p = list[g0 + lane].x;
+            float* o = plane0 + static_cast<size_t>(warp * 16) * hw + p;
+            if (kAdd) {
+                float old[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) old[u] = o[static_cast<size_t>(u) * hw];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) o[static_cast<size_t>(u) * hw] = fmaf(tile[lane][warp * 16 + u], g, old[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) o[static_cast<size_t>(u) * hw] = tile[lane][warp * 16 + u] * g;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Dense gradient of the doubly step in ONE pass: every (image, channel) plane is written once with
+// the pooled gradient gap_g[image*128 + channel] / hw (AdaptiveAvgPool2d backward, loss.py:115), and the sampled
+// pixels of the first B images get their anchor gradient added on the way.  grid (n_chunks, images): a CTA owns one
+// 2048-pixel chunk of all 128 planes of an image (1 MB of output).
+__global__ void __launch_bounds__(kGsThreads)
+k_dense_grad(const float* __restrict__ dF, const int32_t* __restrict__ rowof, int B_pix, const float* __restrict__ grad_out,
+             const float* __restrict__ gap_g, float* __restrict__ dfeats, int hw) {
+    __shared__ int2 list[kChunk];
+    __shared__ int warp_tot[kGsThreads / 32];
+    __shared__ float sg[kDim];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    int n = 0;
+    if (b < B_pix) n = chunk_samples(rowof, b, chunk, hw, list, warp_tot);
+    if (threadIdx.x < kDim) sg[threadIdx.x] = __ldg(gap_g + b * kDim + threadIdx.x) / static_cast<float>(hw);
+    __syncthreads();
+    const int pbeg = chunk * kChunk, pend = min(pbeg + kChunk, hw);
+    float* plane0 = dfeats + static_cast<size_t>(b) * kDim * hw;
+    // broadcast: 128 planes x (pend - pbeg) pixels, 16 bytes per thread and store
+    if (((hw & 3) == 0) && (pend - pbeg) == kChunk) {
+        for (int c = 0; c < kDim; ++c) {
+            const float v = sg[c];
+            float4* o = reinterpret_cast<float4*>(plane0 + static_cast<size_t>(c) * hw + pbeg);
+            const float4 v4 = make_float4(v, v, v, v);
+            __stcs(o + threadIdx.x, v4);
+            __stcs(o + threadIdx.x + kGsThreads, v4);
+        }
+    } else {
+        for (int c = 0; c < kDim; ++c)
+            for (int p = pbeg + threadIdx.x; p < pend; p += kGsThreads) plane0[static_cast<size_t>(c) * hw + p] = sg[c];
+    }
+    if (n == 0) return;
+    __syncthreads();                      // the CTA's own broadcast stores are visible to its threads after the barrier
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float g = __ldg(grad_out);
+    for (int g0 = 0; g0 < n; g0 += 32) {
+        const int m = min(32, n - g0);
+        if (lane < m) {
+            const int2 e = list[g0 + lane];
+            const float* src = dF + static_cast<size_t>(e.y) * kDim + warp * 16;
+            float* o = plane0 + static_cast<size_t>(warp * 16) * hw + e.x;
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + u));
+                o[static_cast<size_t>(u) * hw] = fmaf(v.x, g, sg[warp * 16 + u]);
+                o[static_cast<size_t>(u + 1) * hw] = fmaf(v.y, g, sg[warp * 16 + u + 1]);
+                o[static_cast<size_t>(u + 2) * hw] = fmaf(v.z, g, sg[warp * 16 + u + 2]);
+                o[static_cast<size_t>(u + 3) * hw] = fmaf(v.w, g, sg[warp * 16 + u + 3]);
+            }
+        }
+    }
+}
+
+// zero-fill that can share the SMs with the persistent tensor-core kernels (32 registers, no shared memory): issued
+// on a second stream it clears the dense gradient buffer underneath the N x N sweeps, which leave HBM idle
+__global__ void __launch_bounds__(128)
+k_zero_fill(float4* __restrict__ dst, size_t n16) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) __stcs(dst + i, z);
 }
 
 // ------------------------------------------------------------------------------- global avg pool
@@ -323,33 +570,43 @@ extern "C" int dcl_sample_classify(const int64_t* labels, const float* predict, 
     // float32 scale exactly as ATen computes it: (float)in / out
     const float sh = static_cast<float>(H) / static_cast<float>(h);
     const float sw = static_cast<float>(W) / static_cast<float>(w);
-    k_classify<<<dim3(n_chunks, B), 512, 0, as_stream(stream)>>>(labels, predict, H, W, h, w, C_cls, sh, sw,
-                                                                 code, chunk_hist, n_chunks);
+    // the per-image totals are accumulated with atomics: clear them first (2 KB per image)
+    DCL_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * kBins * B, as_stream(stream)));
+    k_classify<<<dim3(n_chunks, B), 256, 0, as_stream(stream)>>>(labels, predict, H, W, h, w, C_cls, sh, sw, code,
+                                                                 chunk_hist, counts, n_chunks);
     DCL_LAUNCH_CHECK("k_classify");
-    k_chunk_prefix<<<B, kBins, 0, as_stream(stream)>>>(chunk_hist, counts, n_chunks);
-    DCL_LAUNCH_CHECK("k_chunk_prefix");
     return 0;
 }
 
 extern "C" int dcl_sample_select(const uint16_t* code, const int32_t* chunk_hist, int B, int hw,
-                                 const int32_t* req, int N, int32_t* pix, void* stream) {
+                                 const int32_t* req, int N, int32_t* pix, int32_t* rowof, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!code || !chunk_hist || !req || !pix) return fail(DCL_ERR_ARG, "null pointer argument");
     if (B <= 0 || hw <= 0 || N < 0) return fail(DCL_ERR_ARG, "bad shape");
     if (reinterpret_cast<uintptr_t>(req) % 16) return fail(DCL_ERR_ARG, "req must be 16-byte aligned");
+    if (rowof) DCL_CUDA(cudaMemsetAsync(rowof, 0xFF, sizeof(int32_t) * static_cast<size_t>(B) * hw, as_stream(stream)));
     if (N == 0) return 0;
     const int n_chunks = (hw + kChunk - 1) / kChunk;
     k_select<<<(N + 7) / 8, 256, 0, as_stream(stream)>>>(code, chunk_hist, hw, n_chunks,
-                                                         reinterpret_cast<const int4*>(req), N, pix);
+                                                         reinterpret_cast<const int4*>(req), N, pix, rowof);
     DCL_LAUNCH_CHECK("k_select");
     return 0;
 }
 
 extern "C" int dcl_gather_tiles(const float* feats, int B, int hw, const int32_t* pix, int n_pad, void* tiles,
-                                float* sqnorm, void* stream) {
+                                float* sqnorm, const int32_t* rowof, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!feats || !pix || !tiles || !sqnorm) return fail(DCL_ERR_ARG, "null pointer argument");
     if (B <= 0 || hw <= 0 || n_pad <= 0 || n_pad % 128) return fail(DCL_ERR_ARG, "n_pad must be a positive multiple of 128");
+    if (rowof) {
+        if (B > 65535) return fail(DCL_ERR_ARG, "B > 65535");
+        const int n_chunks = (hw + kChunk - 1) / kChunk;
+        k_gather_pad<<<(n_pad + 7) / 8, 256, 0, as_stream(stream)>>>(pix, n_pad, static_cast<uint8_t*>(tiles), sqnorm);
+        DCL_LAUNCH_CHECK("k_gather_pad");
+        k_gather_px<<<dim3(n_chunks, B), kGsThreads, 0, as_stream(stream)>>>(feats, hw, rowof, static_cast<uint8_t*>(tiles), sqnorm);
+        DCL_LAUNCH_CHECK("k_gather_px");
+        return 0;
+    }
     k_gather<true><<<(n_pad + 7) / 8, 256, 0, as_stream(stream)>>>(feats, hw, pix, n_pad, n_pad,
                                                                    static_cast<uint8_t*>(tiles), sqnorm);
     DCL_LAUNCH_CHECK("k_gather<pixels>");
@@ -367,14 +624,54 @@ extern "C" int dcl_pack_rows(const float* Z, int n, int n_pad, void* tiles, floa
     return 0;
 }
 
+extern "C" int dcl_zero_fill(void* dst, size_t bytes, int persistent, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!dst || bytes % 16 || reinterpret_cast<uintptr_t>(dst) % 16) return fail(DCL_ERR_ARG, "dst and bytes must be 16-byte aligned");
+    if (bytes == 0) return 0;
+    const size_t n16 = bytes / 16;
+    size_t blocks;
+    if (persistent) {
+        // two 128-thread blocks per SM that walk the whole buffer: they never have blocks waiting for a slot, so a
+        // kernel issued on another stream meanwhile starts at once next to them
+        blocks = static_cast<size_t>(sm_count()) * 2;
+        if (blocks * 128 > n16) blocks = (n16 + 127) / 128;
+    } else {
+        blocks = (n16 + 4095) / 4096;                     // 64 KB per block
+        if (blocks > 1u << 20) blocks = 1u << 20;
+    }
+    k_zero_fill<<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(static_cast<float4*>(dst), n16);
+    DCL_LAUNCH_CHECK("k_zero_fill");
+    return 0;
+}
+
+extern "C" int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, const float* grad_out, const float* gap_g,
+                              float* dfeats, int B_all, int hw, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!dF || !rowof || !grad_out || !gap_g || !dfeats) return fail(DCL_ERR_ARG, "null pointer argument");
+    if (B_pix < 0 || B_all < B_pix || B_all <= 0 || B_all > 65535 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
+    if ((hw & 3) == 0 && reinterpret_cast<uintptr_t>(dfeats) % 16) return fail(DCL_ERR_ARG, "dfeats must be 16-byte aligned");
+    const int n_chunks = (hw + kChunk - 1) / kChunk;
+    k_dense_grad<<<dim3(n_chunks, B_all), kGsThreads, 0, as_stream(stream)>>>(dF, rowof, B_pix, grad_out, gap_g, dfeats, hw);
+    DCL_LAUNCH_CHECK("k_dense_grad");
+    return 0;
+}
+
 extern "C" int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const float* grad_out,
-                                float* dfeats, int B, int hw, int zero_fill, void* stream) {
+                                float* dfeats, int B, int hw, int zero_fill, const int32_t* rowof, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!dF || !pix || !grad_out || !dfeats) return fail(DCL_ERR_ARG, "null pointer argument");
     if (n_rows < 0 || B <= 0 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
     if (zero_fill == 1)
         DCL_CUDA(cudaMemsetAsync(dfeats, 0, static_cast<size_t>(B) * kDim * hw * sizeof(float), as_stream(stream)));
     if (n_rows == 0) return 0;
+    if (rowof) {
+        if (B > 65535) return fail(DCL_ERR_ARG, "B > 65535");
+        const int n_chunks = (hw + kChunk - 1) / kChunk;
+        if (zero_fill == 2) k_scatter_px<true><<<dim3(n_chunks, B), kGsThreads, 0, as_stream(stream)>>>(dF, rowof, grad_out, dfeats, hw);
+        else k_scatter_px<false><<<dim3(n_chunks, B), kGsThreads, 0, as_stream(stream)>>>(dF, rowof, grad_out, dfeats, hw);
+        DCL_LAUNCH_CHECK("k_scatter_px");
+        return 0;
+    }
     if (zero_fill == 2) k_scatter<true><<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(dF, pix, n_rows, grad_out, dfeats, hw);
     else k_scatter<false><<<(n_rows + 7) / 8, 256, 0, as_stream(stream)>>>(dF, pix, n_rows, grad_out, dfeats, hw);
     DCL_LAUNCH_CHECK("k_scatter");

@@ -37,7 +37,7 @@ struct PerDevice {
     uint32_t* d_ring = nullptr;
     uint64_t ring_blocks = 0, epoch = ~0ull, up_hi = 0;
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev_up = nullptr, ev_used = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_need = nullptr, ev_used = nullptr;
     bool used_recorded = false;
     uint64_t last_window = 0;
 };
@@ -59,9 +59,39 @@ int device_slot(PerDevice*& pd) {
         DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_fork, cudaEventDisableTiming));
         DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_zero, cudaEventDisableTiming));
         DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_up, cudaEventDisableTiming));
+        DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_need, cudaEventDisableTiming));
         DCL_CUDA(cudaEventCreateWithFlags(&pd->ev_used, cudaEventDisableTiming));
         DCL_CUDA(cudaStreamCreateWithFlags(&pd->copy, cudaStreamNonBlocking));
     }
+    return 0;
+}
+
+// copy stream blocks [up_hi, target) of the host look-ahead ring into the device mirror (copy stream)
+int upload_blocks(PerDevice& pd, const DevicePlan& dp, uint64_t target) {
+    if (target <= pd.up_hi) return 0;
+    if (pd.used_recorded) DCL_CUDA(cudaStreamWaitEvent(pd.copy, pd.ev_used, 0));
+    uint64_t b = pd.up_hi;
+    while (b < target) {
+        const uint64_t slot = b % pd.ring_blocks;
+        uint64_t n = target - b;
+        if (n > pd.ring_blocks - slot) n = pd.ring_blocks - slot;
+        DCL_CUDA(cudaMemcpyAsync(pd.d_ring + slot * kMtWords, dp.host_ring + slot * kMtWords,
+                                 sizeof(uint32_t) * kMtWords * n, cudaMemcpyHostToDevice, pd.copy));
+        b += n;
+    }
+    pd.up_hi = target;
+    return 0;
+}
+
+// A guess at the NEXT step's window, pushed behind what is already mirrored.  Called once everything of the current
+// step has been issued: the copy then shares neither the copy engine with the step's own small copies nor anything
+// else with its critical path, and nothing waits for it until the next step's k_plan.
+int mirror_prefetch(PerDevice& pd, const DevicePlan& dp) {
+    uint64_t target = dp.last_block + 1 + pd.last_window + pd.last_window / 4 + 16;
+    if (target > dp.produced) target = dp.produced;
+    if (target > dp.first_block + pd.ring_blocks - 8) target = dp.first_block + pd.ring_blocks - 8;
+    if (int e = upload_blocks(pd, dp, target)) return e;
+    DCL_CUDA(cudaEventRecord(pd.ev_up, pd.copy));
     return 0;
 }
 
@@ -81,27 +111,13 @@ int mirror_window(PerDevice& pd, const DevicePlan& dp, cudaStream_t st) {
         pd.up_hi = dp.first_block;
     }
     const uint64_t window = dp.last_block - dp.first_block + 1;
-    uint64_t target = dp.last_block + 1 + window + window / 4 + 16;          // this window and a guess at the next
-    if (target > dp.produced) target = dp.produced;
-    if (target < dp.last_block + 1) target = dp.last_block + 1;
-    if (target > dp.first_block + pd.ring_blocks - 8) target = dp.first_block + pd.ring_blocks - 8;
-    if (target < dp.last_block + 1) return fail(DCL_ERR_ARG, "plan window of %llu blocks exceeds the generator ring",
-                                                static_cast<unsigned long long>(window));
-    if (target > pd.up_hi) {
-        if (pd.used_recorded) DCL_CUDA(cudaStreamWaitEvent(pd.copy, pd.ev_used, 0));
-        uint64_t b = pd.up_hi;
-        while (b < target) {
-            const uint64_t slot = b % pd.ring_blocks;
-            uint64_t n = target - b;
-            if (n > pd.ring_blocks - slot) n = pd.ring_blocks - slot;
-            DCL_CUDA(cudaMemcpyAsync(pd.d_ring + slot * kMtWords, dp.host_ring + slot * kMtWords,
-                                     sizeof(uint32_t) * kMtWords * n, cudaMemcpyHostToDevice, pd.copy));
-            b += n;
-        }
-        DCL_CUDA(cudaEventRecord(pd.ev_up, pd.copy));
-        pd.up_hi = target;
-    }
-    DCL_CUDA(cudaStreamWaitEvent(st, pd.ev_up, 0));
+    if (window > pd.ring_blocks - 16) return fail(DCL_ERR_ARG, "plan window of %llu blocks exceeds the generator ring",
+                                                  static_cast<unsigned long long>(window));
+    // (1) what this step reads: normally already there (pushed by the previous step), so the event below only marks
+    //     the completion of that earlier copy; `st` waits for it
+    if (int e = upload_blocks(pd, dp, dp.last_block + 1)) return e;
+    DCL_CUDA(cudaEventRecord(pd.ev_need, pd.copy));
+    DCL_CUDA(cudaStreamWaitEvent(st, pd.ev_need, 0));
     pd.last_window = window;
     return 0;
 }
@@ -133,20 +149,20 @@ extern "C" int dcl_step_begin(const dcl_step_t* s, void* stream) {
     cudaStream_t st = as_stream(stream);
     const size_t table = static_cast<size_t>(512) * s->B;                       // ints per rank
     int32_t* mine = s->counts_dev + table * s->rank;
-    if (s->zero_fill && s->zero_fill_bytes) {
-        // the dense gradient buffer is cleared off the critical path: on the side stream when there is one (the
-        // buffer was allocated on `st`, so the side stream first waits for st's current position)
-        if (s->side_stream) {
-            cudaStream_t side = as_stream(s->side_stream);
-            DCL_CUDA(cudaEventRecord(pd->ev_fork, st));
-            DCL_CUDA(cudaStreamWaitEvent(side, pd->ev_fork, 0));
-            DCL_CUDA(cudaMemsetAsync(s->zero_fill, 0, s->zero_fill_bytes, side));
-            DCL_CUDA(cudaEventRecord(pd->ev_zero, side));
-        }
-    }
     if (int e = dcl_sample_classify(s->labels, s->predict, s->B, s->H, s->W, s->h, s->w, s->C_cls, s->code, s->chunk_hist,
                                     mine, stream))
         return e;
+    if (s->zero_fill && s->zero_fill_bytes && s->side_stream) {
+        // The dense gradient buffer is cleared on the second stream from here on: while the count table travels to
+        // the host, the host plans and the plan travels back, the GPU has nothing else to do.  The fill runs as a
+        // few persistent blocks per SM (dcl_zero_fill_persistent), so kernels issued on `st` in the meantime always
+        // find room next to it.  The buffer was allocated on `st`: the side stream first waits for st's position.
+        cudaStream_t side = as_stream(s->side_stream);
+        DCL_CUDA(cudaEventRecord(pd->ev_fork, st));
+        DCL_CUDA(cudaStreamWaitEvent(side, pd->ev_fork, 0));
+        if (int e = dcl_zero_fill(s->zero_fill, s->zero_fill_bytes, 1, s->side_stream)) return e;
+        DCL_CUDA(cudaEventRecord(pd->ev_zero, side));
+    }
     if (s->world > 1)
         if (int e = comm_all_gather(s->comm, mine, s->counts_dev, table * sizeof(int32_t), st)) return e;
     DCL_CUDA(cudaMemcpyAsync(s->counts_host, s->counts_dev, sizeof(int32_t) * table * s->world, cudaMemcpyDeviceToHost, st));
@@ -159,7 +175,7 @@ extern "C" int dcl_step_begin(const dcl_step_t* s, void* stream) {
 extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (!s) return fail(DCL_ERR_ARG, "null step descriptor");
-    if (!s->feats || !s->req_dev || !s->y_dev || !s->pix || !s->plan_dev || !s->plan_host || !s->stage_host || !s->tiles ||
+    if (!s->feats || !s->req_dev || !s->y_dev || !s->pix || !s->rowof || !s->plan_dev || !s->plan_host || !s->stage_host || !s->tiles ||
         !s->sqnorm || !s->colA || !s->colB || !s->rowloss || !s->loss_sum || !s->loss || !s->workspace || !s->info ||
         !s->image || !s->cls || !s->num_hard || !s->num_easy || !s->keep_hard || !s->ranks || !s->torch_rng_state)
         return fail(DCL_ERR_ARG, "null pointer in step descriptor");
@@ -221,12 +237,14 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     if (dp.taken) {
         if (int e = mirror_window(*pd, dp, st)) return e;
         g_step_ns[3] = now_ns() - t0;                        // + generator blocks queued for upload
-        DCL_CUDA(cudaMemcpyAsync(pdv, ph, sizeof(int32_t) * (2 * static_cast<size_t>(world) + A), cudaMemcpyHostToDevice, st));
-        if (dp.n_local_anchors)
-            DCL_CUDA(cudaMemcpyAsync(pdv + o_anchor, ph + o_anchor, sizeof(PlanAnchor) * dp.n_local_anchors,
-                                     cudaMemcpyHostToDevice, st));
+        // one copy: [ycnt | yoff | ycls[A]] and, moved right behind it, the local anchors
+        size_t o_pack = sizeof(int32_t) * (2 * static_cast<size_t>(world) + A);
+        o_pack = (o_pack + 15) / 16 * 16;
+        if (dp.n_local_anchors && o_pack != o_anchor)
+            std::memmove(ph + o_pack, ph + o_anchor, sizeof(PlanAnchor) * dp.n_local_anchors);
+        DCL_CUDA(cudaMemcpyAsync(pdv, ph, o_pack + sizeof(PlanAnchor) * dp.n_local_anchors, cudaMemcpyHostToDevice, st));
         const int32_t* d_ycnt = reinterpret_cast<const int32_t*>(pdv);
-        if (int e = launch_plan(pd->d_ring, pd->ring_blocks, reinterpret_cast<const PlanAnchor*>(pdv + o_anchor),
+        if (int e = launch_plan(pd->d_ring, pd->ring_blocks, reinterpret_cast<const PlanAnchor*>(pdv + o_pack),
                                 dp.n_local_anchors, d_ycnt + 2 * world, d_ycnt, d_ycnt + world, world, rank, n_view,
                                 n_pad, s->req_dev, s->y_dev, stream))
             return e;
@@ -237,10 +255,11 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
         DCL_CUDA(cudaMemcpyAsync(s->y_dev, y_h, sizeof(int32_t) * static_cast<size_t>(world) * n_pad, cudaMemcpyHostToDevice, st));
     }
     g_step_ns[4] = now_ns() - t0;                            // + plan kernel / row copies issued
-    if (int e = dcl_sample_select(s->code, s->chunk_hist, s->B, hw, s->req_dev, n_pad, s->pix, stream)) return e;
+    if (int e = dcl_sample_select(s->code, s->chunk_hist, s->B, hw, s->req_dev, n_pad, s->pix, s->rowof, stream)) return e;
     const size_t tile_bytes = static_cast<size_t>(n_pad) * DCL_DIM * 2;
     uint8_t* tl = static_cast<uint8_t*>(s->tiles) + tile_bytes * rank;
-    if (int e = dcl_gather_tiles(s->feats, s->B, hw, s->pix, n_pad, tl, s->sqnorm + static_cast<size_t>(rank) * n_pad, stream))
+    if (int e = dcl_gather_tiles(s->feats, s->B, hw, s->pix, n_pad, tl, s->sqnorm + static_cast<size_t>(rank) * n_pad,
+                                 s->rowof, stream))
         return e;
     if (world > 1)
         if (int e = comm_all_gather(s->comm, tl, s->tiles, tile_bytes, st)) return e;
@@ -270,7 +289,9 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     }
     if (s->zero_fill && s->zero_fill_bytes && s->side_stream)
         DCL_CUDA(cudaStreamWaitEvent(st, pd->ev_zero, 0));   // the cleared buffer is ordered before anything later on st
-    g_step_ns[6] = now_ns() - t0;                            // + exchange, backward issued
+    if (dp.taken)
+        if (int e = mirror_prefetch(*pd, dp)) return e;
+    g_step_ns[6] = now_ns() - t0;                            // + exchange, backward, generator prefetch issued
     return 0;
 }
 
@@ -286,13 +307,14 @@ extern "C" int dcl_step_timing(long long* out) {
 // Autograd backward of the step: d feats = upstream * scatter(dF) [+ the image-level term's pooled gradient
 // broadcast over the pixels, written in the same pass: `gap_g` [gap_rows] = d loss / d pooled, one value per
 // (image, channel) row of d feats; the dense tensor is then written once and needs no zero-fill].
-extern "C" int dcl_step_bwd(const float* dF, const int32_t* pix, int n_pad, const float* grad_out, float* dfeats, int B,
-                            int hw, int zero_fill, const float* gap_g, int gap_rows, void* stream) {
+extern "C" int dcl_step_bwd(const float* dF, const int32_t* pix, const int32_t* rowof, int n_pad, const float* grad_out,
+                            float* dfeats, int B, int hw, int zero_fill, const float* gap_g, int gap_rows, void* stream) {
     if (n_pad <= 0 || n_pad % DCL_TILE_ROWS) return fail(DCL_ERR_ARG, "n_pad must be a positive multiple of %d", DCL_TILE_ROWS);
     if (gap_g) {
-        if (gap_rows < B * DCL_DIM) return fail(DCL_ERR_ARG, "pooled gradient covers %d rows, the pixel term %d", gap_rows, B * DCL_DIM);
+        if (gap_rows < B * DCL_DIM || gap_rows % DCL_DIM) return fail(DCL_ERR_ARG, "pooled gradient covers %d rows, the pixel term %d", gap_rows, B * DCL_DIM);
+        if (rowof) return dcl_dense_grad(dF, rowof, B, grad_out, gap_g, dfeats, gap_rows / DCL_DIM, hw, stream);
         if (int e = dcl_gap_bwd(gap_g, gap_rows, hw, dfeats, 0, stream)) return e;
-        return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, 2, stream);
+        return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, 2, nullptr, stream);
     }
-    return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, zero_fill, stream);
+    return dcl_scatter_grad(dF, pix, n_pad, grad_out, dfeats, B, hw, zero_fill, rowof, stream);
 }

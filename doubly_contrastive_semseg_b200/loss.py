@@ -246,7 +246,7 @@ def layout_rows(plan: AnchorPlan, anchors: np.ndarray, image_offset: int, n_pad:
 # thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------
 def classify(labels: torch.Tensor, predict: torch.Tensor, h: int, w: int):
-    """-> code [B,hw] u16 (as int16 storage), chunk_prefix [B,n_chunks,512] i32, counts [B,512] i32"""
+    """-> code [B,hw] u16 (as int16 storage), chunk_hist [B,n_chunks,512] i32, counts [B,512] i32"""
     B, H, W = labels.shape
     C = predict.shape[1]
     hw = h * w
@@ -257,23 +257,24 @@ def classify(labels: torch.Tensor, predict: torch.Tensor, h: int, w: int):
     counts = torch.empty((B, _BINS), dtype=torch.int32, device=dev)
     _lib.call("dcl_sample_classify", _p(labels), _p(predict), B, H, W, h, w, C, _p(code), _p(chunk),
               _p(counts), _stream())
-    _count(2)
+    _count(1)
     return code, chunk, counts
 
 
-def select_pixels(code, chunk, B, hw, req_dev, n_rows):
+def select_pixels(code, chunk, B, hw, req_dev, n_rows, rowof=None):
+    """rank -> pixel; `rowof` [B*hw] i32 (optional) receives the inverse map pixel -> row (-1 elsewhere)"""
     pix = torch.empty(n_rows, dtype=torch.int32, device=code.device)
-    _lib.call("dcl_sample_select", _p(code), _p(chunk), B, hw, _p(req_dev), n_rows, _p(pix), _stream())
+    _lib.call("dcl_sample_select", _p(code), _p(chunk), B, hw, _p(req_dev), n_rows, _p(pix), _p(rowof), _stream())
     _count(1)
     return pix
 
 
-def gather_tiles(feats, pix, n_pad):
+def gather_tiles(feats, pix, n_pad, rowof=None):
     B, C, h, w = feats.shape
     tiles = torch.empty(n_pad * _DIM * 2, dtype=torch.uint8, device=feats.device)
     sqnorm = torch.empty(n_pad, dtype=torch.float32, device=feats.device)
-    _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tiles), _p(sqnorm), _stream())
-    _count(1)
+    _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, _p(tiles), _p(sqnorm), _p(rowof), _stream())
+    _count(1 if rowof is None else 2)
     return tiles, sqnorm
 
 
@@ -406,7 +407,7 @@ def _shard_comm(group):
 
 class _StepResult:
     """What one dcl_step_fwd left behind: the loss, and for the backward the sampled pixels and the eager dF."""
-    __slots__ = ("loss", "keep", "p_pix", "p_dF", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info")
+    __slots__ = ("loss", "keep", "p_pix", "p_dF", "p_rowof", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info")
 
 
 def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
@@ -423,7 +424,7 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     res.dzero = torch.empty_like(feats) if (want_grad and zero_fill) else None
     # what outlives the call: sampled pixels, eager gradient of the rows, the loss
     loss = torch.empty(1, dtype=torch.float32, device=dev)
-    res.keep, (p_pix, p_dF) = _carve(dev, (cap * 4, cap * _DIM * 4 if want_grad else 0))
+    res.keep, (p_pix, p_rowof, p_dF) = _carve(dev, (cap * 4, B * hw * 4, cap * _DIM * 4 if want_grad else 0))
     st = torch.get_rng_state()
     sbuf = st.numpy()
     step = sb["step"]
@@ -433,7 +434,7 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     step.temperature, step.base_temperature = float(crit.temperature), float(crit.base_temperature)
     step.torch_rng_state, step.state_bytes = sbuf.ctypes.data, sbuf.nbytes
     step.rank, step.comm = rank, comm
-    step.pix, step.dF, step.loss = p_pix, (p_dF if want_grad else None), loss.data_ptr()
+    step.pix, step.rowof, step.dF, step.loss = p_pix, p_rowof, (p_dF if want_grad else None), loss.data_ptr()
     ws = _workspace(dev, sb["ws_bytes"])
     step.workspace, step.workspace_bytes = ws.data_ptr(), sb["ws_bytes"]
     if res.dzero is not None:
@@ -480,14 +481,14 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
             _PROFILE_HOOK("contrast_bwd", ev[2], ev[3])
     A, n_view, n, n_pad, n_global, on_device = res.info[:6]
     res.n, res.n_pad, res.n_global = n, n_pad, n_global
-    res.p_pix, res.p_dF = p_pix, p_dF
+    res.p_pix, res.p_dF, res.p_rowof = p_pix, p_dF, p_rowof
     res.loss = loss.reshape(())
     # last_plan / last_layout / last_pix are built on first access (device buffers of this step: valid until the
     # next forward of this module)
     crit.__dict__["_last_step"] = (res.info, sb, res.keep, rank, world)
     crit.__dict__["last_n_global"] = n_global
-    # classify + prefix, plan or 2 copies, select, gather, forward (+ backward) [+ pack / unpack when sharded]
-    _count(2 + 1 + 1 + 1 + _launches(MODE_PIXEL, 0) + (_launches(MODE_PIXEL, 1) if want_grad else 0) + (2 if world > 1 else 0))
+    # classify, plan, select, gather (2), forward (+ backward) [+ pack / unpack when sharded]; the zero-fill is ours too
+    _count(1 + 1 + 1 + 2 + (1 if res.dzero is not None else 0) + _launches(MODE_PIXEL, 0) + (_launches(MODE_PIXEL, 1) if want_grad else 0) + (2 if world > 1 else 0))
     return res
 
 
@@ -510,7 +511,7 @@ class _PixelContrastFn(torch.autograd.Function):
         loss2 = torch.empty(2, dtype=torch.float32, device=dev)
         nbytes = _ws_bytes(nJ, nJ)
         ws = _workspace(dev, nbytes)
-        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, p_tiles, p_sq, st)
+        _lib.call("dcl_gather_tiles", _p(feats), B, h * w, _p(pix), n_pad, p_tiles, p_sq, None, st)
         with _Timed("contrast_fwd"):
             _lib.call("dcl_contrast_fwd", p_tiles, _p(y_dev), p_sq, nJ, 0, nJ, n_valid, MODE_PIXEL, float(T), float(Tb),
                       _p(ws), nbytes, p_cA, p_cB, p_rl, _p(loss2), st)
@@ -538,7 +539,7 @@ class _PixelContrastFn(torch.autograd.Function):
         if dfeats is None:
             dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
             zero_fill = 1
-        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfeats), B, h * w, zero_fill, st)
+        _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n_pad, _p(g), _p(dfeats), B, h * w, zero_fill, None, st)
         _count(_launches(MODE_PIXEL, 1) + 1 + zero_fill)
         return dfeats, None, None, None, None, None, None
 
@@ -573,8 +574,8 @@ class _StepFn(torch.autograd.Function):
         if dfeats is None:                                 # a second backward through the same graph
             dfeats = torch.empty((B, C, h, w), dtype=torch.float32, device=dev)
             zero_fill = 1
-        _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.n_pad, _p(_grad_scalar(grad_out)), _p(dfeats), B, h * w,
-                  zero_fill, None, 0, _stream())
+        _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.p_rowof, res.n_pad, _p(_grad_scalar(grad_out)), _p(dfeats), B,
+                  h * w, zero_fill, None, 0, _stream())
         _count(1 + zero_fill)
         return dfeats, None, None, None, None
 
@@ -609,20 +610,35 @@ class _DoublyFn(torch.autograd.Function):
             _lib.call("dcl_gap_bwd", _p(gp), B2 * C, h * w, _p(dx), 0, _stream())
             _count(1)
         else:
-            _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.n_pad, _p(_grad_scalar(g_pixel)), _p(dx), B, h * w, 0,
-                      _p(gp), B2 * C, _stream())
-            _count(2)
+            _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.p_rowof, res.n_pad, _p(_grad_scalar(g_pixel)), _p(dx), B,
+                      h * w, 0, _p(gp), B2 * C, _stream())
+            _count(1)
         return dx, None, None, None
 
 
+_SMALL_ROWS = 128          # dcl_contrast_small_max_rows()
+
+
 class _ContrastRowsFn(torch.autograd.Function):
-    """Row-normalised contrast of a dense [n,128] matrix (image-level term)."""
+    """Row-normalised contrast of a dense [n,128] matrix (image-level term).  The image-level term at its real size
+    (2B rows <= 128) runs in exact fp32 in one launch, forward and gradient together (csrc/dcl_contrast_small.cu);
+    larger row counts and the pixel form go through the tensor-core tiles."""
 
     @staticmethod
     def forward(ctx, Z, y, mode, T, Tb):
         n = Z.shape[0]
-        n_pad = (n + _TILE - 1) // _TILE * _TILE
         Zc = Z.contiguous().to(torch.float32)
+        if mode == MODE_SUPCON and n <= _SMALL_ROWS:
+            y32 = y.to(torch.int32).contiguous()
+            loss = torch.empty(1, dtype=torch.float32, device=Z.device)
+            dZ = torch.empty((n, _DIM), dtype=torch.float32, device=Z.device) if ctx.needs_input_grad[0] else None
+            _lib.call("dcl_contrast_small", _p(Zc), _p(y32), n, mode, float(T), float(Tb), _p(loss), _p(dZ), _stream())
+            _count(1)
+            ctx.small = True
+            ctx.save_for_backward(dZ) if dZ is not None else ctx.save_for_backward()
+            return loss.reshape(())
+        ctx.small = False
+        n_pad = (n + _TILE - 1) // _TILE * _TILE
         tiles, sqnorm = pack_rows(Zc, n_pad)
         y_pad = torch.full((n_pad,), -1, dtype=torch.int32, device=Z.device)
         y_pad[:n] = y.to(torch.int32)
@@ -634,6 +650,9 @@ class _ContrastRowsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.small:
+            (dZ,) = ctx.saved_tensors
+            return dZ * grad_out.to(torch.float32), None, None, None, None
         tiles, y_pad, colA, colB = ctx.saved_tensors
         n, nJ, mode = ctx.meta
         dF = contrast_backward(tiles, y_pad, colA, colB, nJ, 0, nJ, mode)

@@ -75,8 +75,7 @@ int dcl_contrast_launches(int mode, int backward);
  *   labels   [B,H,W] int64      predict [B,C_cls,h,w] f32
  *   code     [B,h*w] u16 out :  low byte = down-sampled label (0..255), bit 8 = easy
  *                               (label == argmax), 0xFFFF = label outside 0..255
- *   chunk_hist [B,n_chunks,512] i32 out : on return holds, per (image, bin = label*2+easy),
- *                               the EXCLUSIVE prefix over chunks of that bin's pixel count
+ *   chunk_hist [B,n_chunks,512] i32 out : per (image, chunk, bin = label*2+easy) pixel counts
  *   counts   [B,512] i32 out  : per-image totals per bin  (hard = bin label*2, easy = +1)
  *   n_chunks = ceil(h*w / DCL_CHUNK_PIXELS)
  */
@@ -89,17 +88,20 @@ int dcl_sample_classify(const int64_t* labels, const float* predict, int B, int 
  *                   that image whose code matches"; rank comes from the host's randperm draw.
  *                   image < 0 marks a padding row.
  *   pix [N] i32 out : flat pixel id image*h*w + p, or -1 for padding rows.
+ *   rowof [B*hw] i32 out, optional (NULL to skip): the inverse map, rowof[pix[n]] = n and -1 everywhere else; with
+ *                   it dcl_gather_tiles / dcl_scatter_grad work chunk-wise in pixel order instead of row by row.
  */
 int dcl_sample_select(const uint16_t* code, const int32_t* chunk_hist, int B, int hw,
-                      const int32_t* req, int N, int32_t* pix, void* stream);
+                      const int32_t* req, int N, int32_t* pix, int32_t* rowof, void* stream);
 
 /* Gather anchor rows into F-tiles: replaces the NCHW->NHWC copy + per-class advanced-index gather
  * of loss.py:409-410, :333.
  *   feats [B,128,h*w] f32 (NCHW), pix [n_pad] (from dcl_sample_select; -1 => zero row)
  *   tiles [n_pad/128] F-tiles out, sqnorm [n_pad] f32 out (|bf16(f)|^2, the row shift)
+ *   rowof: optional inverse map from dcl_sample_select (NULL: one warp per row)
  */
 int dcl_gather_tiles(const float* feats, int B, int hw, const int32_t* pix, int n_pad,
-                     void* tiles, float* sqnorm, void* stream);
+                     void* tiles, float* sqnorm, const int32_t* rowof, void* stream);
 
 /* Same, from a dense row-major matrix Z [n,128] f32 (image-level term, loss.py:161). Rows >= n
  * are zero padding. */
@@ -195,13 +197,32 @@ int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, con
                      int nJ, int rb0, int nI, int mode, void* workspace, size_t workspace_bytes,
                      float* dF, void* stream);
 
+/* The same contrast for a handful of rows (n <= dcl_contrast_small_max_rows() = 128) in exact fp32, forward and
+ * gradient in one launch: what the image-level term uses (2B rows; its rows are projections of pooled features,
+ * nearly identical across images, and bf16 operands would drown their differences).  Z [n,128] f32 row-major,
+ * y [n] i32 -> loss [1]; dZ [n,128] out (d loss / d Z, optional). */
+int dcl_contrast_small_max_rows(void);
+int dcl_contrast_small(const float* Z, const int32_t* y, int n, int mode, float temperature, float base_temperature,
+                       float* loss, float* dZ, void* stream);
+
 /* ---------------------------------------------------------------- gradient back to NCHW
  * Replaces autograd of the gather (index_put into a zero tensor per class):
  * row n's gradient * (*grad_out) is written at pixel pix[n] of dfeats [B,128,h*w] f32 (pix < 0 skipped).
  * zero_fill: 0 = dfeats is already clear, 1 = clear it first, 2 = ADD to what dfeats holds (sampled pixels are
- * distinct, so no atomics are needed).  grad_out: device scalar (upstream dL/dloss). */
+ * distinct, so no atomics are needed).  grad_out: device scalar (upstream dL/dloss).  rowof: optional inverse map
+ * from dcl_sample_select (NULL: one warp per row). */
 int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const float* grad_out,
-                     float* dfeats, int B, int hw, int zero_fill, void* stream);
+                     float* dfeats, int B, int hw, int zero_fill, const int32_t* rowof, void* stream);
+/* Clears `bytes` (multiple of 16) at dst.  persistent != 0: two 128-thread blocks per SM walk the whole buffer, so
+ * that on a second stream the fill never keeps kernels of the main stream waiting for a slot (the step clears the
+ * dense gradient buffer this way while the count table is with the host); 0: one short block per 64 KB. */
+int dcl_zero_fill(void* dst, size_t bytes, int persistent, void* stream);
+/* The dense gradient of the doubly contrastive step in ONE pass (both losses hit the same `fine_feat`,
+ * trainer.py:144-152): dfeats [B_all,128,hw] = gap_g[image*128 + channel] / hw everywhere (AdaptiveAvgPool2d
+ * backward, loss.py:115) + (*grad_out) * dF[row] at the sampled pixels of the first B_pix images (rowof from
+ * dcl_sample_select).  No zero-fill, no read-modify-write. */
+int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, const float* grad_out, const float* gap_g,
+                   float* dfeats, int B_all, int hw, void* stream);
 /* dZ [n,128] = dF[:n] * (*grad_out)  (image-level term). */
 int dcl_unpack_rows(const float* dF, int n, const float* grad_out, float* dZ, void* stream);
 
@@ -236,7 +257,8 @@ int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumulate, void* 
  *   B                images of THIS rank; every rank passes the same B
  *   cap              rows per rank block the buffers hold: multiple of 128, >= max_samples rounded up to 128
  *   device scratch   code [B*h*w] u16, chunk_hist [B*n_chunks*512] i32, counts_dev [world*B*512] i32,
- *                    req_dev [4*cap] i32, y_dev [world*cap] i32, pix [cap] i32, plan_dev [plan_bytes]
+ *                    req_dev [4*cap] i32, y_dev [world*cap] i32, pix [cap] i32, rowof [B*h*w] i32 (pixel -> row
+ *                    map; kept for dcl_step_bwd), plan_dev [plan_bytes]
  *   device state     tiles [world*cap*256 B], sqnorm [world*cap], colA/colB [world*cap*4] f32, rowloss [world*cap],
  *                    loss_sum [2], loss [1] (the step's result), dF [cap*128] f32 or NULL,
  *                    xchg_send [(2*cap+1)*4] f32 and xchg_recv [world*(2*cap+1)*4] f32 (world > 1 only)
@@ -262,7 +284,7 @@ typedef struct dcl_step {
     int world, rank; void* comm;
     int cap;
     uint16_t* code; int32_t* chunk_hist; int32_t* counts_dev;
-    int32_t* req_dev; int32_t* y_dev; int32_t* pix; void* plan_dev;
+    int32_t* req_dev; int32_t* y_dev; int32_t* pix; int32_t* rowof; void* plan_dev;
     void* tiles; float* sqnorm; float* colA; float* colB; float* rowloss; float* loss_sum; float* loss;
     float* xchg_send; float* xchg_recv; float* dF;
     void* workspace; size_t workspace_bytes;
@@ -282,10 +304,11 @@ int dcl_step_fwd(const dcl_step_t* step, void* stream);
 /* Autograd backward of the step: dfeats [B(+),128,hw] = (*grad_out) * scatter(dF at pix).  zero_fill != 0 clears
  * dfeats first (0: the caller already did, e.g. through dcl_step_t.zero_fill).  gap_g != NULL fuses the image-level
  * term's gradient into the same pass (both losses hit the same `fine_feat`, trainer.py:144-152):
- * dfeats has gap_rows/128 >= B images, every (image, channel) row r is first written with gap_g[r] / hw (the
- * AdaptiveAvgPool2d backward, loss.py:115), then the anchor gradients are added - the dense tensor is written once. */
-int dcl_step_bwd(const float* dF, const int32_t* pix, int n_pad, const float* grad_out, float* dfeats, int B, int hw,
-                 int zero_fill, const float* gap_g, int gap_rows, void* stream);
+ * dfeats has gap_rows/128 >= B images, every (image, channel) row r is written with gap_g[r] / hw (the
+ * AdaptiveAvgPool2d backward, loss.py:115) and the anchor gradients are added on the way (dcl_dense_grad): the dense
+ * tensor is written once and never read. */
+int dcl_step_bwd(const float* dF, const int32_t* pix, const int32_t* rowof, int n_pad, const float* grad_out,
+                 float* dfeats, int B, int hw, int zero_fill, const float* gap_g, int gap_rows, void* stream);
 
 /* Diagnostics: cumulative host nanoseconds of the last dcl_step_fwd at the end of each of its sections: out[8] =
  * classify / count-table copy / zero-fill issued, + wait for the count table, + host plan, + generator blocks queued
@@ -301,6 +324,22 @@ int dcl_comm_unique_id(void* out128);
 int dcl_comm_init(const void* id128, int world, int rank, void** comm);
 int dcl_comm_destroy(void* comm);
 int dcl_comm_all_gather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+
+/* ---------------------------------------------------------------- segmentation-loss neighbour
+ * BoundaryAwareFocalLoss (loss.py:27-80), forward and gradient in one pass, the up-sampled logits never formed:
+ *   logits [B,C,h,w] f32 (C <= 32) pre-upsample (h == H, w == W allowed: full-resolution logits); target [B,H,W] i64,
+ *   REWRITTEN in place like the reference does (ignore_id -> 0, loss.py:43); alpha [B,H,W] f32 = the batch's
+ *   `label_distance_weight`; weight [C] class weights (modes 0 and 3).
+ *   mode: 0 weight*alpha (default), 1 `plain_focal`, 2 `no_class_weights`, 3 `no_EDT` (loss.py:63-70)
+ *   dlogits_unscaled [B,C,h,w] out: N * d loss / d logits;  loss_n [2] out: the loss (0 when N == 0) and
+ *   N = #(alpha > 0);  workspace >= dcl_focal_workspace_bytes(B, h, w).
+ * dcl_focal_bwd: dlogits [n] = dlogits_unscaled * (*grad_out) / N (zeros when N == 0). */
+size_t dcl_focal_workspace_bytes(int B, int h, int w);
+int dcl_focal_fwd(const float* logits, int64_t* target, const float* alpha, const float* weight, int B, int C, int h,
+                  int w, int H, int W, int ignore_id, float gamma, int mode, float* dlogits_unscaled, float* loss_n,
+                  void* workspace, size_t workspace_bytes, void* stream);
+int dcl_focal_bwd(const float* dlogits_unscaled, const float* loss_n, const float* grad_out, float* dlogits, size_t n,
+                  void* stream);
 
 #ifdef __cplusplus
 }

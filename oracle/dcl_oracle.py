@@ -424,3 +424,105 @@ class SupConPort(torch.nn.Module):
         lp = l - torch.log((torch.exp(l) * not_self).sum(dim=1, keepdim=True))
         per_row = -(T / Tb) * (pos * lp).sum(dim=1) / pos.sum(dim=1)
         return per_row.view(V, bsz).mean()
+
+
+# --------------------------------------------------------------------------------------
+# Segmentation-loss neighbour of the hot path: BoundaryAwareFocalLoss, loss.py:27-80
+# --------------------------------------------------------------------------------------
+
+
+def bilinear_source(out_size: int, in_size: int):
+    """F.interpolate(mode='bilinear', align_corners=False) source taps of every output index (loss.py:5):
+    src = max((dst + 0.5) * (in/out) - 0.5, 0) in float32; i0 = floor(src), i1 = min(i0 + 1, in - 1), lambda = src - i0."""
+    scale = np.float32(in_size) / np.float32(out_size)
+    src = np.maximum((np.arange(out_size, dtype=np.float32) + np.float32(0.5)) * scale - np.float32(0.5), np.float32(0))
+    i0 = np.minimum(src.astype(np.int64), in_size - 1)
+    i1 = np.minimum(i0 + 1, in_size - 1)
+    lam = (src - i0.astype(np.float32)).astype(np.float32)
+    return i0, i1, lam
+
+
+class BoundaryFocalPort(torch.nn.Module):
+    """CPU restatement of BoundaryAwareFocalLoss (loss.py:27-80): bilinear up-sampling of the logits to the label
+    size when the sizes differ, log-softmax, gather at the target, class weight x EDT weight x detached focal factor
+    exp(gamma (1 - p_t)), sum / #(EDT weight > 0).  Like the reference it rewrites `target` in place (ignore -> 0)."""
+
+    def __init__(self, gamma=0, num_classes=19, ignore_id=19, print_each=20, weight=None, device=None, opts=None):
+        super().__init__()
+        self.num_classes, self.ignore_id, self.print_each = num_classes, ignore_id, print_each
+        self.step_counter = 0
+        self.gamma, self.weight, self.device, self.opts = gamma, weight, device, opts
+
+    def forward(self, input, target, batch, **kwargs):
+        if input.shape[-2:] != target.shape[-2:]:
+            input = torch.nn.functional.interpolate(input, target.shape[-2:], mode="bilinear", align_corners=False)
+        target[target == self.ignore_id] = 0                                         # :43
+        alpha = batch["label_distance_weight"]
+        N = (alpha.data > 0.).sum()                                                   # :45
+        if N.le(0):
+            return torch.zeros(size=(0,), requires_grad=True).sum()
+        x = input.view(input.size(0), input.size(1), -1).transpose(1, 2).contiguous().view(-1, input.size(1))
+        t = target.view(-1, 1)
+        alphas = alpha.view(-1)
+        w = self.weight[t].view(-1)                                                   # :54 (TypeError when weight is None)
+        logpt = torch.nn.functional.log_softmax(x.to(torch.float32), dim=-1).gather(1, t).view(-1)
+        pt = logpt.detach().exp()
+        focal = torch.exp(self.gamma * (1 - pt))
+        crit = getattr(self.opts, "criterion", None)
+        if crit == "plain_focal":
+            loss = -1 * focal * logpt
+        elif getattr(self.opts, "no_class_weights", False):
+            loss = -1 * alphas * focal * logpt
+        elif getattr(self.opts, "no_EDT", False):
+            loss = -1 * w * focal * logpt
+        else:
+            loss = -1 * w * alphas * focal * logpt
+        self.step_counter += 1
+        return loss.sum() / N
+
+
+def focal_closed_form(logits, target, alpha, weight, gamma, mode="full", ignore_id=255):
+    """fp64 forward + analytic backward of BoundaryAwareFocalLoss (loss.py:27-80) on pre-upsample logits [B,C,h,w]
+    (h == H, w == W allowed): what the fused CUDA kernel computes.  With the up-sampled logits z = U x (U = the
+    separable bilinear operator of `bilinear_source`), p = softmax(z), k = coefficient of the mode
+    (class weight x EDT weight x exp(gamma (1 - p_t)), the focal factor detached):
+        loss = - sum_i k_i log p_{i,t_i} / N,     N = #(alpha > 0)
+        d loss / d z_{i,c} = - k_i (delta_{c,t_i} - p_{i,c}) / N,     d loss / d x = U^T (d loss / d z).
+    Returns (loss, dlogits [B,C,h,w], target with ignore -> 0)."""
+    x = np.asarray(logits, dtype=np.float64)
+    t = np.asarray(target).astype(np.int64).copy()
+    a = np.asarray(alpha, dtype=np.float64)
+    B, C, h, w = x.shape
+    H, W = t.shape[1:]
+    t[t == ignore_id] = 0
+    N = int((a > 0).sum())
+    if N <= 0:
+        return 0.0, np.zeros_like(x), t
+    y0, y1, ly = bilinear_source(H, h)
+    x0, x1, lx = bilinear_source(W, w)
+    ly = ly.astype(np.float64)[None, None, :, None]
+    lx = lx.astype(np.float64)[None, None, None, :]
+    rows = (1 - ly) * x[:, :, y0, :] + ly * x[:, :, y1, :]                     # [B,C,H,w]
+    z = (1 - lx) * rows[:, :, :, x0] + lx * rows[:, :, :, x1]                   # [B,C,H,W]
+    m = z.max(axis=1, keepdims=True)
+    lse = m + np.log(np.exp(z - m).sum(axis=1, keepdims=True))
+    logp = z - lse
+    p = np.exp(logp)
+    bi, yi, xi = np.meshgrid(np.arange(B), np.arange(H), np.arange(W), indexing="ij")
+    logpt = logp[bi, t, yi, xi]
+    pt = np.exp(logpt)
+    wt = np.asarray(weight, dtype=np.float64)[t]
+    focal = np.exp(gamma * (1 - pt))
+    k = {"plain_focal": focal, "no_class_weights": a * focal, "no_EDT": wt * focal}.get(mode, wt * a * focal)
+    loss = float(-(k * logpt).sum() / N)
+    onehot = np.zeros_like(z)
+    onehot[bi, t, yi, xi] = 1.0
+    dz = -(k[:, None] * (onehot - p)) / N
+    # U^T: scatter columns, then rows
+    drows = np.zeros((B, C, H, w))
+    np.add.at(drows, (slice(None), slice(None), slice(None), x0), dz * (1 - lx))
+    np.add.at(drows, (slice(None), slice(None), slice(None), x1), dz * lx)
+    dx = np.zeros_like(x)
+    np.add.at(dx, (slice(None), slice(None), y0, slice(None)), drows * (1 - ly))
+    np.add.at(dx, (slice(None), slice(None), y1, slice(None)), drows * ly)
+    return loss, dx, t

@@ -132,6 +132,36 @@ def run_supcon(ref, name, seed, B, h, w, use_labels):
     print(f"supcon_{name}: rows={2 * B} loss={loss.item():.6f}")
 
 
+def focal_inputs(seed, B, C, h, w, H, W, ignore_frac=0.08):
+    g = torch.Generator().manual_seed(seed)
+    logits = 2.0 * torch.randn(B, C, h, w, generator=g)
+    target = torch.randint(0, C, (B, H, W), generator=g)
+    target[torch.rand(B, H, W, generator=g) < ignore_frac] = 255
+    # EDT-style weight: positive near "boundaries", exactly zero on a part of the image and on ignore pixels
+    alpha = torch.rand(B, H, W, generator=g) * 3.0
+    alpha[torch.rand(B, H, W, generator=g) < 0.3] = 0.0
+    alpha[target == 255] = 0.0
+    weight = 0.5 + torch.rand(C, generator=g) * 4.0
+    return logits, target.long(), alpha, weight
+
+
+def run_focal(ref, name, seed, B, C, h, w, H, W, gamma, mode):
+    """BoundaryAwareFocalLoss (loss.py:27-80) on pre-upsample logits [B,C,h,w] (the loss up-samples them itself when the
+    label size differs, loss.py:41-42) or on full-resolution logits (h == H)."""
+    logits, target, alpha, weight = focal_inputs(seed, B, C, h, w, H, W)
+    opts = types.SimpleNamespace(with_depth_level_loss=False, criterion="plain_focal" if mode == "plain_focal" else "x",
+                                 no_class_weights=mode == "no_class_weights", no_EDT=mode == "no_EDT")
+    crit = ref.BoundaryAwareFocalLoss(gamma=gamma, num_classes=C, ignore_id=255, weight=weight, device="cpu", opts=opts)
+    x = logits.clone().requires_grad_(True)
+    t = target.clone()
+    loss = crit(x, t, {"label_distance_weight": alpha})
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, f"focal_{name}.npz"), logits=logits.numpy(), target=target.numpy().astype(np.int16),
+                        alpha=alpha.numpy(), weight=weight.numpy(), gamma=gamma, mode=mode, loss=loss.item(),
+                        dlogits=x.grad.numpy(), target_after=t.numpy().astype(np.int16))
+    print(f"focal_{name}: loss={loss.item():.6f}")
+
+
 def main():
     ref = load_reference()
     # name, seed, B, H, W, h, w, K, block, correct_frac, max_samples, max_views, call_seed
@@ -146,6 +176,12 @@ def main():
     run_contrast(ref, "n40_twoclass", 23, 20, 2, 2, 0.0)
     run_contrast_large(ref, "n2048", 41, 64, 32, 16)
     run_contrast_large(ref, "n8192", 42, 128, 64, 16)
+    run_focal(ref, "x4", 51, 2, 19, 6, 10, 24, 40, 0.5, "full")
+    run_focal(ref, "ragged", 52, 2, 19, 5, 7, 18, 30, 0.5, "full")
+    run_focal(ref, "fullres", 53, 1, 19, 12, 20, 12, 20, 0.5, "full")
+    run_focal(ref, "no_edt", 54, 2, 7, 6, 10, 24, 40, 2.0, "no_EDT")
+    run_focal(ref, "no_cw", 55, 2, 7, 6, 10, 24, 40, 0.0, "no_class_weights")
+    run_focal(ref, "plain", 56, 1, 19, 8, 8, 32, 32, 0.5, "plain_focal")
     run_supcon(ref, "labels_b4", 31, 4, 4, 6, True)
     run_supcon(ref, "simclr_b3", 32, 3, 4, 6, False)
     run_supcon(ref, "labels_b16", 33, 16, 2, 3, True)

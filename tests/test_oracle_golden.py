@@ -182,3 +182,42 @@ def test_supcon_port_errors_match_reference_contract():
         crit(x, class_labels=torch.zeros(2, 1, dtype=torch.long), mask=torch.eye(2))
     with pytest.raises(ValueError):
         crit(x, class_labels=torch.zeros(3, 1, dtype=torch.long))
+
+
+# ------------------------------------------------------------------ segmentation-loss neighbour
+FOCAL_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "focal_*.npz")))
+
+
+def _focal_opts(mode):
+    return types.SimpleNamespace(with_depth_level_loss=False, criterion="plain_focal" if mode == "plain_focal" else "x",
+                                 no_class_weights=mode == "no_class_weights", no_EDT=mode == "no_EDT")
+
+
+@pytest.mark.parametrize("case", FOCAL_CASES)
+def test_boundary_focal_port_and_closed_form_vs_reference(case):
+    """BoundaryAwareFocalLoss (loss.py:27-80): the torch port and the fp64 closed form (the math of the fused CUDA
+    kernel, including the bilinear taps and their transpose) against outputs of the real reference."""
+    g = _load(case)
+    mode, gamma = str(g["mode"]), float(g["gamma"])
+    C = g["logits"].shape[1]
+    crit = O.BoundaryFocalPort(gamma=gamma, num_classes=C, ignore_id=255, weight=torch.from_numpy(g["weight"]),
+                               device="cpu", opts=_focal_opts(mode))
+    x = torch.from_numpy(g["logits"]).requires_grad_(True)
+    t = torch.from_numpy(g["target"].astype(np.int64))
+    loss = crit(x, t, {"label_distance_weight": torch.from_numpy(g["alpha"])})
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert np.abs(x.grad.numpy() - g["dlogits"]).max() <= 1e-5 * np.abs(g["dlogits"]).max()
+    assert np.array_equal(t.numpy(), g["target_after"].astype(np.int64))          # the in-place ignore -> 0 rewrite
+    loss_cf, dx, t_cf = O.focal_closed_form(g["logits"], g["target"], g["alpha"], g["weight"], gamma, mode)
+    assert abs(loss_cf - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    assert np.abs(dx - g["dlogits"]).max() <= 2e-5 * np.abs(g["dlogits"]).max()
+    assert np.array_equal(t_cf, g["target_after"].astype(np.int64))
+
+
+def test_boundary_focal_port_zero_weight_returns_zero():
+    crit = O.BoundaryFocalPort(gamma=0.5, weight=torch.ones(19), opts=_focal_opts("full"), ignore_id=255)
+    x = torch.randn(1, 19, 4, 4, requires_grad=True)
+    loss = crit(x, torch.zeros(1, 8, 8, dtype=torch.long), {"label_distance_weight": torch.zeros(1, 8, 8)})
+    assert loss.item() == 0.0
+    loss.backward()

@@ -13,7 +13,7 @@ from doubly_contrastive_semseg_b200.loss import _p, _stream   # noqa: E402
 
 rt = ctypes.CDLL("libcudart.so.12")
 B, hw, n = 8, 256 * 512, 8192
-feats = torch.randn(B, 128, hw, device="cuda")
+feats = torch.randn(B, 128, 256, 512, device="cuda")
 g = torch.Generator(device="cuda").manual_seed(1)
 pix = torch.randperm(B * hw, generator=g, device="cuda")[:n].int().contiguous()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -27,7 +27,7 @@ for gran in (0, 32, 64, 128):
         rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
         print("set granularity", gran, "rc", rc, "now", val.value)
     for name, fn in (("gather", lambda: L.gather_tiles(feats, pix, n)),
-                     ("scatter", lambda: _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n, _p(one), _p(dfe), B, hw, 0, _stream()))):
+                     ("scatter", lambda: _lib.call("dcl_scatter_grad", _p(dF), _p(pix), n, _p(one), _p(dfe), B, hw, 0, None, _stream()))):
         ts = []
         for _ in range(7):
             flush.fill_(1)
