@@ -52,63 +52,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples taken while the bench measures (warm-up, the timed steps and the
-    end-to-end steps of every workload it runs).  One sample per 100 ms: a faster poll - nvidia-smi at 20 ms, or an
-    in-process NVML thread at 10 ms - holds driver / interpreter locks long enough to show up as launch-latency spikes
-    in a sub-millisecond step (measured: cfg2 0.35 -> 0.60 ms per step), so the sample count is what a 100 ms period
-    yields over the few seconds of measurement."""
+    """SM clock / throttle-reason samples taken DURING the timed regions by a native NVML thread inside the library
+    (dcl_clock_sampler_start / _stop, csrc/dcl_clocks.cpp; 2 ms period, started and stopped around every timed
+    region).  `nvidia-smi -lms` is not used: while it polls, even at 100 ms, every step of the 0.4 ms workload takes
+    0.25 ms longer (measured, profiles/r02j_*), and its start-up can stall a step for 100+ ms."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    PERIOD_US = 2000
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.path = None
+    def __init__(self, lib):
+        self.lib = lib
+        self.regions = []
+        self.active = False
+        # first use loads and initialises NVML (tens of milliseconds of driver activity): do it now, not inside the
+        # first timed region
+        self.start()
+        time.sleep(0.02)
+        self.stop()
+        self.regions = []
 
-    def __enter__(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-        return self
+    def start(self):
+        if os.environ.get("DCL_BENCH_NO_SAMPLER"):          # experiments only
+            return
+        self.active = self.lib.dcl_clock_sampler_start(self.PERIOD_US) == 0
 
-    def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+    def stop(self):
+        if not self.active:
+            return
+        import ctypes
+        out = (ctypes.c_double * 5)()
+        self.lib.dcl_clock_sampler_stop(ctypes.cast(out, ctypes.c_void_p))
+        self.active = False
+        if out[0] > 0:
+            self.regions.append([float(v) for v in out])
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
-               "window": "warm-up, timed steps and end-to-end steps of every workload in this line; nvidia-smi, 100 ms period"}
-        if not self.path or not os.path.exists(self.path):
+               "window": "inside the timed regions only (device-resident and end-to-end steps of every workload in this "
+                         "line); native NVML thread, %d ms period" % (self.PERIOD_US // 1000)}
+        if not self.regions:
             return out
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+        mask = 0
+        for r in self.regions:
+            mask |= int(r[3])
+        out.update(sm_mhz=float(np.median([r[1] for r in self.regions])), sm_mhz_min_region=float(min(r[1] for r in self.regions)),
+                   sm_max_mhz=float(max(r[2] for r in self.regions)), samples=int(sum(r[0] for r in self.regions)),
+                   power_w_max=float(max(r[4] for r in self.regions)))
+        out["reasons"] = sorted(k for k, bit in self.BITS.items() if mask & bit)
         return out
 
 
@@ -251,16 +241,33 @@ def run_reference(args):
 class Timer:
     """K steps bracketed by events on the current stream + a per-step event after every step."""
 
+    clocks = None            # ClockSampler shared by every timed region of the process
+
     def __init__(self, barrier):
         self.barrier = barrier
 
     def run(self, step, steps, first_seed=100):
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         self.barrier()
+        if Timer.clocks is not None:
+            Timer.clocks.start()
+        try:
+            return self._run(step, steps, first_seed, marks)
+        finally:
+            if Timer.clocks is not None:
+                Timer.clocks.stop()
+
+    def _run(self, step, steps, first_seed, marks):
         marks[0].record()
+        nomarks = bool(os.environ.get("DCL_BENCH_NO_MARKS"))          # experiments only
         for s in range(steps):
             step(first_seed + s)
-            marks[s + 1].record()
+            if not nomarks or s == steps - 1:
+                marks[s + 1].record()
+        if nomarks:
+            self.barrier()
+            total = marks[0].elapsed_time(marks[-1])
+            return total, [total / steps] * steps
         self.barrier()
         total = marks[0].elapsed_time(marks[-1])
         per = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
@@ -309,7 +316,8 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
         torch.cuda.empty_cache()
 
     sim_events = []
-    L.set_profile_hook(lambda name, a, b: sim_events.append((name, a, b)))
+    if not os.environ.get("DCL_BENCH_NO_HOOK"):            # experiments only: the similarity events are the roofline's clock
+        L.set_profile_hook(lambda name, a, b: sim_events.append((name, a, b)))
     # Identical CPU generator state on every rank, set ONCE: every rank consumes the same stream (each replays the
     # global plan), so the states stay identical, and an untouched generator lets the library keep its look-ahead
     # of the mt19937 stream (host thread + device mirror) running off the step's critical path.
@@ -335,6 +343,8 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total, med = float(t[0]), float(t[1])
+    if os.environ.get("DCL_BENCH_DUMP_STEPS") and rank == 0:              # experiments only
+        print("per-step ms (%s):" % wl.name, " ".join("%.3f" % v for v in per), file=sys.stderr, flush=True)
     out.update(value=n_global * args.steps / (total * 1e-3), ms_per_step=total / args.steps, ms_per_step_median=med,
                anchors=n_global, anchors_per_gpu=n_local, gpu_launches=launches, sim_ms_per_step=sim_ms / args.steps,
                timed_calls=len(sim_events), embed_mb=feats.numel() * 4 / 1e6)
@@ -556,7 +566,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     peaks = load_peaks()
-    with ClockSampler(local) as clk:
+    clk = Timer.clocks = ClockSampler(_lib.load())
+    if True:
         if wl.two_crop:
             m = measure_doubly(pkg, L, wl, dev, args, barrier)
         else:
@@ -638,6 +649,9 @@ def workload_named(name):
 
 
 def main():
+    if os.environ.get("DCL_BENCH_NO_GC"):                   # experiments only
+        import gc
+        gc.disable()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -53,6 +53,8 @@ SIGNATURES = {
     "dcl_focal_workspace_bytes": (_sz, [_i, _i, _i]),
     "dcl_focal_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "dcl_focal_bwd": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "dcl_clock_sampler_start": (_i, [_i]),
+    "dcl_clock_sampler_stop": (_i, [_vp]),
     "dcl_comm_unique_id": (_i, [_vp]),
     "dcl_comm_init": (_i, [_vp, _i, _i, _vp]),
     "dcl_comm_destroy": (_i, [_vp]),

@@ -21,6 +21,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <immintrin.h>
 #include <unistd.h>
 #include "dcl_common.cuh"
 #include "dcl_plan.h"
@@ -55,6 +56,23 @@ inline void twist_words(uint32_t* s) {
     else twist_generic(s);
 }
 
+// Publishing a block to the look-ahead ring.  The ring (41 MB) is far larger than the worker's cache share, and a
+// plain store to it first reads the line from DRAM: regenerating straight into the ring ran at 0.46 us per block, the
+// same arithmetic on a cache-resident block at 0.12 us.  So the worker keeps ONE block in its L1 (in-place twist) and
+// streams a copy into the ring slot with non-temporal stores (no read-for-ownership, no cache pollution; the slots
+// are 64-byte aligned and 2496 = 39 x 64 bytes long).  The consumers - the GPU's copy engine and, for a host-side
+// plan, the main thread - read the ring from memory anyway.
+__attribute__((target("avx2"))) void stream_block_avx2(uint32_t* dst, const uint32_t* src) {
+    for (int i = 0; i < kN; i += 8)
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)));
+    _mm_sfence();
+}
+inline void stream_block(uint32_t* dst, const uint32_t* src) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) stream_block_avx2(dst, src);
+    else std::memcpy(dst, src, sizeof(uint32_t) * kN);
+}
+
 // Look-ahead of the generator's state sequence.  The sequence of regenerated state blocks depends only on the
 // generator state, not on the data, so a worker thread produces it ahead of time into a ring; the sampler then
 // consumes blocks instead of regenerating them on the step's critical path (0.2 ms per step at cfg2).  The stream is
@@ -74,7 +92,7 @@ public:
                 seen = produced_.load(std::memory_order_acquire);
             }
         }
-        return ring_.data() + (idx % kRing) * kN;
+        return ring_ + (idx % kRing) * kN;
     }
     // does the serialized torch state equal where the last plan left the generator?  (same process only)
     bool active() const { return active_ && pid_ == getpid(); }
@@ -89,19 +107,21 @@ public:
     uint64_t position() const { return pos_block_; }
     uint64_t epoch() const { return epoch_; }
     uint64_t produced() const { return produced_.load(std::memory_order_acquire); }
-    const uint32_t* ring() const { return ring_.data(); }
+    uint32_t* ring() const { return ring_; }
     // restart from the state words `s` as block 0
     void restart(const uint32_t* s) {
         stop();
         ++epoch_;
-        if (ring_.empty()) {
-            ring_.resize(kRing * kN);
+        if (!ring_) {
+            void* mem = nullptr;
+            if (posix_memalign(&mem, 4096, sizeof(uint32_t) * kRing * kN) != 0) mem = nullptr;
+            ring_ = static_cast<uint32_t*>(mem);
             // page-locked so the device mirror of the stream (dcl_step.cu) can be filled by asynchronous copies;
             // without a CUDA device (CPU tests) the registration simply fails and nothing depends on it
-            if (cudaHostRegister(ring_.data(), sizeof(uint32_t) * kRing * kN, cudaHostRegisterPortable) != cudaSuccess)
+            if (ring_ && cudaHostRegister(ring_, sizeof(uint32_t) * kRing * kN, cudaHostRegisterPortable) != cudaSuccess)
                 cudaGetLastError();
         }
-        std::memcpy(ring_.data(), s, sizeof(uint32_t) * kN);
+        std::memcpy(ring_, s, sizeof(uint32_t) * kN);
         std::memcpy(last_, s, sizeof(uint32_t) * kN);
         produced_.store(1, std::memory_order_release);
         floor_.store(0, std::memory_order_release);
@@ -117,7 +137,12 @@ public:
     void commit(uint64_t idx, const uint8_t* raw, uint64_t keep_from) {
         pos_block_ = idx;
         expect(raw);
-        floor_.store(keep_from < idx ? keep_from : idx, std::memory_order_release);
+        {
+            // under the worker's mutex: a store + notify that slipped between the worker's predicate check and its
+            // wait would be lost and the worker would sleep through its time-out while the ring runs dry
+            std::lock_guard<std::mutex> g(mu_);
+            floor_.store(keep_from < idx ? keep_from : idx, std::memory_order_release);
+        }
         cv_.notify_one();
     }
     void stop() {
@@ -137,7 +162,7 @@ private:
         for (;;) {
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait_for(lk, std::chrono::milliseconds(50), [this] {
+                cv_.wait_for(lk, std::chrono::milliseconds(2), [this] {
                     return quit_ || produced_.load(std::memory_order_relaxed) - floor_.load(std::memory_order_acquire) < kRing - 1;
                 });
                 if (quit_) return;
@@ -145,14 +170,14 @@ private:
             while (produced_.load(std::memory_order_relaxed) - floor_.load(std::memory_order_acquire) < kRing - 1) {
                 twist_words(last_);
                 const uint64_t idx = produced_.load(std::memory_order_relaxed);
-                std::memcpy(ring_.data() + (idx % kRing) * kN, last_, sizeof(uint32_t) * kN);
+                stream_block(ring() + (idx % kRing) * kN, last_);
                 produced_.store(idx + 1, std::memory_order_release);
                 if (quit_) return;
             }
         }
     }
-    std::vector<uint32_t> ring_;
-    uint32_t last_[kN];
+    uint32_t* ring_ = nullptr;                 // kRing blocks, page-aligned, page-locked when a device is present
+    alignas(64) uint32_t last_[kN];
     std::atomic<uint64_t> produced_{0}, floor_{0};
     std::mutex mu_;
     std::condition_variable cv_;
@@ -515,7 +540,7 @@ int dcl::plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignor
         // without drawing it (randperm(n) consumes n - 1 draws whatever its outcome), so the host only records
         // where each local permutation starts and advances the generator; k_plan (dcl_plan.cu) replays the kept
         // prefixes on the GPU from its mirror of the same stream blocks.
-        device_mode = dp && m.la && n_view <= dcl::kMaxDeviceViews;
+        device_mode = dp && dp->allow_device && m.la && n_view <= dcl::kMaxDeviceViews;
         const int threads = (m.la && !device_mode) ? std::min(n_local, host_threads(static_cast<int64_t>(n_local) * n_view)) : 1;
         // draw index of the generator's next output, counted from word 0 of stream block 0
         auto gabs = [](const Mt& g) -> uint64_t {
@@ -524,6 +549,7 @@ int dcl::plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignor
         if (device_mode) {
             int li = 0;
             uint64_t g_first = ~0ull, g_last = 0;
+            dp->plan_first_block = gabs(m) / kN;
             for (int a = 0; a < A; ++a) {
                 const bool local = image[a] >= lo && image[a] < hi;
                 const uint64_t gh = gabs(m);
@@ -549,6 +575,7 @@ int dcl::plan_rows(const int32_t* counts, int Bl, int world, int rank, int ignor
                     if (endh > g_last) g_last = endh;
                 }
             }
+            dp->plan_end_block = gabs(m) / kN;
             dp->n_local_anchors = li;
             dp->first_block = li ? g_first / kN : la.position();
             dp->last_block = li ? g_last / kN : la.position();
@@ -728,6 +755,7 @@ extern "C" int dcl_debug_plan_device(const int32_t* counts, int Bl, int world, i
                                      int32_t* yoff, long long* meta, const void** ring_out) {
     if (!anchors || !ycls || !yanchor || !ycnt || !yoff || !meta || !ring_out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
     dcl::DevicePlan dp{};
+    dp.allow_device = 1;
     dp.anchors = static_cast<dcl::PlanAnchor*>(anchors);
     dp.ycls = ycls; dp.yanchor = yanchor; dp.ycnt = ycnt; dp.yoff = yoff;
     const int rc = dcl::plan_rows(counts, Bl, world, rank, ignore_label, max_samples, max_views, torch_rng_state,

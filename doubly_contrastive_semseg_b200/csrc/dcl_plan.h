@@ -27,6 +27,7 @@ struct PlanAnchor {
 // not running yet, plan longer than the ring, n_view too large) and req / y hold the finished rows.
 struct DevicePlan {
     // in
+    int allow_device;                         // 0: fill the class-sorted order only, draw on the host
     PlanAnchor* anchors;                      // [>= Bl*256] host (pinned)
     int32_t* ycls;                            // [>= world*Bl*256] class of the o-th class-sorted anchor of rank r at ycls[yoff[r] + o]
     int32_t* yanchor;                         // same indexing: its anchor id a (reference order)
@@ -37,6 +38,7 @@ struct DevicePlan {
     int n_local_anchors;
     uint64_t epoch;                           // restart count of the stream (the device mirror resets when it changes)
     uint64_t first_block, last_block;         // stream blocks the permutations read
+    uint64_t plan_first_block, plan_end_block;   // blocks where the whole plan (every rank's draws) starts and ends
     const uint32_t* host_ring;                // look-ahead ring: block b lives at host_ring + (b % ring_blocks) * 624
     uint64_t ring_blocks;
     uint64_t produced;                        // blocks [.., produced) exist on the host right now (prefetch hint)

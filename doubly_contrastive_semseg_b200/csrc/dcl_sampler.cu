@@ -436,53 +436,51 @@ k_scatter_px(const float* __restrict__ dF, const int32_t* __restrict__ rowof, co
 
 // Dense gradient of the doubly step in ONE pass: every (image, channel) plane is written once with
 // the pooled gradient gap_g[image*128 + channel] / hw (AdaptiveAvgPool2d backward, loss.py:115), and the sampled
-// pixels of the first B images get their anchor gradient added on the way.  grid (n_chunks, images): a CTA owns one
-// 2048-pixel chunk of all 128 planes of an image (1 MB of output).
+// pixels of the first B_pix images get their anchor gradient added on the way.  A CTA owns kDgChunks consecutive
+// 2048-pixel chunks (64 KB per plane: long enough runs for the DRAM pages) of kDgPlanes channel planes of one image:
+// it streams the broadcast value over them, then walks the sampled pixels of its chunks and rewrites those elements
+// with broadcast + anchor gradient (same CTA, after a barrier: no read-modify-write, no second kernel).
+constexpr int kDgChunks = 8, kDgPlanes = 16;
 __global__ void __launch_bounds__(kGsThreads)
 k_dense_grad(const float* __restrict__ dF, const int32_t* __restrict__ rowof, int B_pix, const float* __restrict__ grad_out,
-             const float* __restrict__ gap_g, float* __restrict__ dfeats, int hw) {
+             const float* __restrict__ gap_g, float* __restrict__ dfeats, int hw, int n_chunks) {
     __shared__ int2 list[kChunk];
     __shared__ int warp_tot[kGsThreads / 32];
-    __shared__ float sg[kDim];
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    int n = 0;
-    if (b < B_pix) n = chunk_samples(rowof, b, chunk, hw, list, warp_tot);
-    if (threadIdx.x < kDim) sg[threadIdx.x] = __ldg(gap_g + b * kDim + threadIdx.x) / static_cast<float>(hw);
+    __shared__ float sg[kDgPlanes];
+    const int b = blockIdx.z, c0 = blockIdx.y * kDgPlanes, chunk0 = blockIdx.x * kDgChunks;
+    if (threadIdx.x < kDgPlanes) sg[threadIdx.x] = __ldg(gap_g + b * kDim + c0 + threadIdx.x) / static_cast<float>(hw);
     __syncthreads();
-    const int pbeg = chunk * kChunk, pend = min(pbeg + kChunk, hw);
-    float* plane0 = dfeats + static_cast<size_t>(b) * kDim * hw;
-    // broadcast: 128 planes x (pend - pbeg) pixels, 16 bytes per thread and store
-    if (((hw & 3) == 0) && (pend - pbeg) == kChunk) {
-        for (int c = 0; c < kDim; ++c) {
+    const int pbeg = chunk0 * kChunk, pend = min(pbeg + kDgChunks * kChunk, hw);
+    float* plane0 = dfeats + (static_cast<size_t>(b) * kDim + c0) * hw;
+    if (((hw & 3) == 0)) {
+        const int n4 = (pend - pbeg) >> 2;
+        for (int c = 0; c < kDgPlanes; ++c) {
             const float v = sg[c];
-            float4* o = reinterpret_cast<float4*>(plane0 + static_cast<size_t>(c) * hw + pbeg);
             const float4 v4 = make_float4(v, v, v, v);
-            __stcs(o + threadIdx.x, v4);
-            __stcs(o + threadIdx.x + kGsThreads, v4);
+            float4* o = reinterpret_cast<float4*>(plane0 + static_cast<size_t>(c) * hw + pbeg);
+            for (int i = threadIdx.x; i < n4; i += kGsThreads) __stcs(o + i, v4);
         }
     } else {
-        for (int c = 0; c < kDim; ++c)
+        for (int c = 0; c < kDgPlanes; ++c)
             for (int p = pbeg + threadIdx.x; p < pend; p += kGsThreads) plane0[static_cast<size_t>(c) * hw + p] = sg[c];
     }
-    if (n == 0) return;
-    __syncthreads();                      // the CTA's own broadcast stores are visible to its threads after the barrier
+    if (b >= B_pix) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float g = __ldg(grad_out);
-    for (int g0 = 0; g0 < n; g0 += 32) {
-        const int m = min(32, n - g0);
-        if (lane < m) {
-            const int2 e = list[g0 + lane];
-            const float* src = dF + static_cast<size_t>(e.y) * kDim + warp * 16;
-            float* o = plane0 + static_cast<size_t>(warp * 16) * hw + e.x;
-#pragma unroll
-            for (int u = 0; u < 16; u += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + u));
-                o[static_cast<size_t>(u) * hw] = fmaf(v.x, g, sg[warp * 16 + u]);
-                o[static_cast<size_t>(u + 1) * hw] = fmaf(v.y, g, sg[warp * 16 + u + 1]);
-                o[static_cast<size_t>(u + 2) * hw] = fmaf(v.z, g, sg[warp * 16 + u + 2]);
-                o[static_cast<size_t>(u + 3) * hw] = fmaf(v.w, g, sg[warp * 16 + u + 3]);
+    for (int j = 0; j < kDgChunks && chunk0 + j < n_chunks; ++j) {
+        // (the barriers inside chunk_samples also order this CTA's broadcast stores before the rewrites below)
+        const int n = chunk_samples(rowof, b, chunk0 + j, hw, list, warp_tot);
+        for (int g0 = 0; g0 < n; g0 += 32) {
+            if (g0 + lane < n) {
+                const int2 e = list[g0 + lane];
+                // warp w: planes 2 w, 2 w + 1 of the group
+                const float2 v = __ldg(reinterpret_cast<const float2*>(dF + static_cast<size_t>(e.y) * kDim + c0 + warp * 2));
+                float* o = plane0 + static_cast<size_t>(warp * 2) * hw + e.x;
+                o[0] = fmaf(v.x, g, sg[warp * 2]);
+                o[static_cast<size_t>(hw)] = fmaf(v.y, g, sg[warp * 2 + 1]);
             }
         }
+        __syncthreads();                   // `list` is reused by the next chunk
     }
 }
 
@@ -651,7 +649,8 @@ extern "C" int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, 
     if (B_pix < 0 || B_all < B_pix || B_all <= 0 || B_all > 65535 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
     if ((hw & 3) == 0 && reinterpret_cast<uintptr_t>(dfeats) % 16) return fail(DCL_ERR_ARG, "dfeats must be 16-byte aligned");
     const int n_chunks = (hw + kChunk - 1) / kChunk;
-    k_dense_grad<<<dim3(n_chunks, B_all), kGsThreads, 0, as_stream(stream)>>>(dF, rowof, B_pix, grad_out, gap_g, dfeats, hw);
+    const dim3 grid((n_chunks + kDgChunks - 1) / kDgChunks, kDim / kDgPlanes, B_all);
+    k_dense_grad<<<grid, kGsThreads, 0, as_stream(stream)>>>(dF, rowof, B_pix, grad_out, gap_g, dfeats, hw, n_chunks);
     DCL_LAUNCH_CHECK("k_dense_grad");
     return 0;
 }

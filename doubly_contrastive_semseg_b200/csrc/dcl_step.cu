@@ -83,11 +83,14 @@ int upload_blocks(PerDevice& pd, const DevicePlan& dp, uint64_t target) {
     return 0;
 }
 
-// A guess at the NEXT step's window, pushed behind what is already mirrored.  Called once everything of the current
-// step has been issued: the copy then shares neither the copy engine with the step's own small copies nor anything
-// else with its critical path, and nothing waits for it until the next step's k_plan.
+// A guess at the NEXT step's window, pushed behind what is already mirrored: the next plan starts where this one
+// ended (every rank consumes the whole stream), and this rank's permutations will sit at about the same offset into
+// it.  Called once everything of the current step has been issued: the copy then shares neither the copy engine with
+// the step's own small copies nor anything else with its critical path, and nothing waits for it until the next
+// step's k_plan.  (The blocks of other ranks' permutations in between are copied too: 4 MB per step at most.)
 int mirror_prefetch(PerDevice& pd, const DevicePlan& dp) {
-    uint64_t target = dp.last_block + 1 + pd.last_window + pd.last_window / 4 + 16;
+    const uint64_t span = dp.last_block - dp.plan_first_block + 1;         // plan start .. end of this rank's window
+    uint64_t target = dp.plan_end_block + span + span / 4 + 16;
     if (target > dp.produced) target = dp.produced;
     if (target > dp.first_block + pd.ring_blocks - 8) target = dp.first_block + pd.ring_blocks - 8;
     if (int e = upload_blocks(pd, dp, target)) return e;
@@ -216,6 +219,7 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     size_t o_yanchor = o_anchor + sizeof(PlanAnchor) * static_cast<size_t>(s->B) * 256;
     o_yanchor = (o_yanchor + 63) / 64 * 64;
     DevicePlan dp{};
+    dp.allow_device = s->device_plan ? 1 : 0;
     dp.ycnt = reinterpret_cast<int32_t*>(ph);
     dp.yoff = dp.ycnt + world;
     dp.ycls = dp.yoff + world;
@@ -226,7 +230,7 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     int32_t inf[6] = {0, 0, 0, 0, 0, 0};
     const int rc = plan_rows(s->counts_host, s->B, world, rank, s->ignore_label, s->max_samples, s->max_views,
                              s->torch_rng_state, s->state_bytes, inf, s->image, s->cls, s->num_hard, s->num_easy,
-                             s->keep_hard, s->ranks, req_h, y_h, nullptr, nullptr, s->device_plan ? &dp : nullptr);
+                             s->keep_hard, s->ranks, req_h, y_h, nullptr, nullptr, &dp);
     for (int i = 0; i < 5; ++i) s->info[i] = inf[i];
     s->info[5] = dp.taken;
     g_step_ns[2] = now_ns() - t0;                            // + host plan

@@ -315,6 +315,13 @@ int dcl_step_bwd(const float* dF, const int32_t* pix, const int32_t* rowof, int 
  * for upload, + plan kernel (or row copies) issued, + select / gather / forward issued, + exchange / backward issued, -. */
 int dcl_step_timing(long long* out);
 
+/* Measurement aid (bench.py): a native thread samples the CURRENT device's SM clock, throttle reasons and power through
+ * NVML every period_us microseconds while a timed region runs (`nvidia-smi -lms` itself slows a sub-millisecond step).
+ * dcl_clock_sampler_stop: out[5] = samples, median SM MHz, max SM MHz, OR of NVML throttle-reason masks (0x4 sw power
+ * cap, 0x8 hw slowdown, 0x20 sw thermal slowdown, 0x40 hw thermal slowdown), highest power draw in W. */
+int dcl_clock_sampler_start(int period_us);
+int dcl_clock_sampler_stop(double* out);
+
 /* ---------------------------------------------------------------- NCCL plumbing of the sharded step
  * libnccl.so.2 is taken from the process (torch has it mapped) or dlopen'ed; nothing is linked.  Rank 0 creates the
  * 128-byte id, every rank receives it out of band (e.g. one torch.distributed broadcast) and calls dcl_comm_init on
