@@ -248,9 +248,12 @@ class Timer:
 
     def run(self, step, steps, first_seed=100):
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        self.barrier()
+        # the sampler thread starts BEFORE the barrier: its first NVML queries (the slow ones, and with several ranks
+        # they queue on NVML's lock) then land in the barrier, not in the first timed step
         if Timer.clocks is not None:
             Timer.clocks.start()
+        time.sleep(0.005)
+        self.barrier()
         try:
             return self._run(step, steps, first_seed, marks)
         finally:
@@ -323,15 +326,30 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
     # of the mt19937 stream (host thread + device mirror) running off the step's critical path.
     torch.manual_seed(1234)
 
+    host_log = []                     # experiments only (DCL_BENCH_DUMP_STEPS): host wall time and sections per step
+    dump = bool(os.environ.get("DCL_BENCH_DUMP_STEPS"))
+
     def step(seed, f=feats, lab=labels, pred=predict):
         f.grad = None
+        t0 = time.perf_counter()
         loss = crit(f, labels=lab, predict=pred)
+        t1 = time.perf_counter()
         loss.backward()
+        if dump:
+            import ctypes
+            t2 = time.perf_counter()
+            sec = (ctypes.c_longlong * 8)()
+            _lib_handle.dcl_step_timing(sec)
+            py = L._DEBUG_PY_TIMES[-1] if L._DEBUG_PY_TIMES else []
+            host_log.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, [v / 1e6 for v in sec[:7]] + [-1.0] + list(py)))
         return loss
 
+    from doubly_contrastive_semseg_b200 import _lib as _lib_mod
+    _lib_handle = _lib_mod.load()
     for s in range(args.warmup):
         step(s)
     barrier()
+    host_log.clear()
     sim_events.clear()
     L.reset_launch_count()
     total, per = Timer(barrier).run(step, args.steps)
@@ -343,8 +361,17 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total, med = float(t[0]), float(t[1])
-    if os.environ.get("DCL_BENCH_DUMP_STEPS") and rank == 0:              # experiments only
+    if dump and rank == 0:
+        import ctypes
         print("per-step ms (%s):" % wl.name, " ".join("%.3f" % v for v in per), file=sys.stderr, flush=True)
+        medp = float(np.median(per))
+        for i, v in enumerate(per):
+            if v > 1.5 * medp and i < len(host_log):
+                print("  slow step %d: %.3f ms gpu; host forward %.3f ms backward %.3f ms; sections(ms) %s"
+                      % (i, v, host_log[i][0], host_log[i][1], " ".join("%.3f" % x for x in host_log[i][2])), file=sys.stderr)
+        w = (ctypes.c_longlong * 2)()
+        _lib_handle.dcl_host_lookahead_wait(w)
+        print("  look-ahead waits: total %.3f ms, longest %.3f ms" % (w[0] / 1e6, w[1] / 1e6), file=sys.stderr, flush=True)
     out.update(value=n_global * args.steps / (total * 1e-3), ms_per_step=total / args.steps, ms_per_step_median=med,
                anchors=n_global, anchors_per_gpu=n_local, gpu_launches=launches, sim_ms_per_step=sim_ms / args.steps,
                timed_calls=len(sim_events), embed_mb=feats.numel() * 4 / 1e6)

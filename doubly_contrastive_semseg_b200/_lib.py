@@ -29,6 +29,7 @@ SIGNATURES = {
     "dcl_host_plan_rows_sharded": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dcl_debug_plan_device": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz] + [_vp] * 16),
     "dcl_host_lookahead_stats": (_i, [_vp]),
+    "dcl_host_lookahead_wait": (_i, [_vp]),
     "dcl_host_plan_timing": (_i, [_vp]),
     "dcl_gather_tiles": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "dcl_pack_rows": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

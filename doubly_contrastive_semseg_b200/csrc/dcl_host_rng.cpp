@@ -87,9 +87,16 @@ public:
     const uint32_t* block(uint64_t idx, uint64_t& seen) {
         if (idx >= seen) {
             seen = produced_.load(std::memory_order_acquire);
-            while (seen <= idx) {
-                std::this_thread::yield();
-                seen = produced_.load(std::memory_order_acquire);
+            if (seen <= idx) {
+                // the consumer has caught up with the worker: diagnostics keep the time lost here
+                const auto t0 = std::chrono::steady_clock::now();
+                while (seen <= idx) {
+                    std::this_thread::yield();
+                    seen = produced_.load(std::memory_order_acquire);
+                }
+                const long long ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+                wait_ns_ += ns;
+                if (ns > wait_max_ns_) wait_max_ns_ = ns;
             }
         }
         return ring_ + (idx % kRing) * kN;
@@ -105,6 +112,8 @@ public:
         epid_ = getpid();
     }
     uint64_t position() const { return pos_block_; }
+    long long wait_ns() const { return wait_ns_; }
+    long long wait_max_ns() const { return wait_max_ns_; }
     uint64_t epoch() const { return epoch_; }
     uint64_t produced() const { return produced_.load(std::memory_order_acquire); }
     uint32_t* ring() const { return ring_; }
@@ -185,6 +194,7 @@ private:
     bool quit_ = false, active_ = false, have_expected_ = false;
     pid_t pid_ = 0, epid_ = 0;
     uint64_t pos_block_ = 0, epoch_ = 0;
+    long long wait_ns_ = 0, wait_max_ns_ = 0;
     uint8_t expected_[24 + 8 * kN] = {0};
 };
 
@@ -451,7 +461,14 @@ static inline long long now_ns() {
 
 static long long g_la_stats[4] = {0, 0, 0, 0};
 static Lookahead g_la;
-static std::mutex g_la_mu;   // plans served by the look-ahead stream, inline plans, stream starts, drops
+static std::mutex g_la_mu;
+// Diagnostics: out[2] = nanoseconds the plans have spent waiting for the look-ahead worker (total, longest wait)
+extern "C" int dcl_host_lookahead_wait(long long* out) {
+    if (!out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
+    out[0] = g_la.wait_ns();
+    out[1] = g_la.wait_max_ns();
+    return 0;
+}   // plans served by the look-ahead stream, inline plans, stream starts, drops
 // Diagnostics: counters of the generator look-ahead (see Lookahead): out[4] = stream plans, inline plans, starts, drops.
 extern "C" int dcl_host_plan_timing(long long* out) {
     if (!out) return dcl::fail(DCL_ERR_ARG, "null pointer argument");
@@ -459,6 +476,7 @@ extern "C" int dcl_host_plan_timing(long long* out) {
     return 0;
 }
 
+extern "C" int dcl_host_lookahead_wait(long long* out);
 extern "C" int dcl_host_lookahead_stats(long long* out) {
     for (int i = 0; i < 4; ++i) out[i] = g_la_stats[i];
     return 0;

@@ -63,23 +63,38 @@ k_plan(const uint32_t* __restrict__ ring, unsigned long long ring_blocks, const 
         for (int t = lane; t < tab_slots; t += 32) tab[t] = make_int2(-1, 0);
         __syncwarp();
         if (lane == 0) {
+            // The chain is latency-bound (shared-memory round trips), so the operands of step i + 1 - its target j, the
+            // value at position i + 1 and the table slot j hashes to - are fetched while step i completes, and patched
+            // in the rare case that step i has just written one of them.
             const uint32_t mask = static_cast<uint32_t>(tab_slots - 1);
+            auto slot_of = [&](int j) { return (static_cast<uint32_t>(j) * 0x9E3779B1u >> 12) & mask; };
+            int j_n = jbuf[0], v_n = front[0];
+            uint32_t h_n = j_n >= k ? slot_of(j_n) : 0u;
+            int2 t_n = j_n >= k ? tab[h_n] : make_int2(-1, 0);
             for (int i = 0; i < k; ++i) {
-                const int j = jbuf[i];
-                const int vi = front[i];
+                const int j = j_n, vi = v_n;
+                uint32_t h = h_n;
+                int2 t = t_n;
+                const bool more = i + 1 < k;
+                if (more) {
+                    j_n = jbuf[i + 1];
+                    v_n = front[i + 1];
+                    h_n = j_n >= k ? slot_of(j_n) : 0u;
+                    t_n = j_n >= k ? tab[h_n] : make_int2(-1, 0);
+                }
                 int o;
                 if (j < k) {
-                    o = front[j];
+                    o = (j == i) ? vi : front[j];
                     front[j] = vi;
+                    if (more && j == i + 1) v_n = vi;                 // the value just moved to the next position
                 } else {
-                    uint32_t h = (static_cast<uint32_t>(j) * 0x9E3779B1u >> 12) & mask;
-                    int2 t = tab[h];
                     while (t.x != -1 && t.x != j) {
                         h = (h + 1) & mask;
                         t = tab[h];
                     }
                     o = (t.x == j) ? t.y : j;
                     tab[h] = make_int2(j, vi);
+                    if (more && j_n >= k && h_n == h) t_n = tab[h_n];   // the next probe starts on the slot just written
                 }
                 out[i] = o;
             }

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
@@ -319,6 +320,7 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 # ----------------------------------------------------------------------------------------------
 # the one-call step (dcl_step_fwd / dcl_step_bwd): cached sizes, persistent scratch, raw pointers
 # ----------------------------------------------------------------------------------------------
+_DEBUG_PY_TIMES = [] if os.environ.get("DCL_DEBUG_PY_TIMES") else None      # diagnostics: host milliseconds of _run_step's parts
 _FUSED_STEP = os.environ.get("DCL_FUSED_STEP", "1") != "0"     # 0: the stage-by-stage Python path (same results)
 _DEVICE_PLAN = os.environ.get("DCL_DEVICE_PLAN", "1") != "0"   # 0: always replay the generator on the host (same results)
 _SIDE_STREAM_FILL = os.environ.get("DCL_SIDE_STREAM_FILL", "1") != "0"
@@ -417,14 +419,19 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     dev = feats.device
     hw = h * w
     world, rank, comm = shard if shard is not None else (1, 0, None)
+    _t = [time.perf_counter()] if _DEBUG_PY_TIMES is not None else None
     sb = crit._step_buffers(B, h, w, dev, world)
     cap = sb["cap"]
     res = _StepResult()
     res.shape = (B, C, h, w)
     res.dzero = torch.empty_like(feats) if (want_grad and zero_fill) else None
+    if _t is not None:
+        _t.append(time.perf_counter())
     # what outlives the call: sampled pixels, eager gradient of the rows, the loss
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     res.keep, (p_pix, p_rowof, p_dF) = _carve(dev, (cap * 4, B * hw * 4, cap * _DIM * 4 if want_grad else 0))
+    if _t is not None:
+        _t.append(time.perf_counter())
     st = torch.get_rng_state()
     sbuf = st.numpy()
     step = sb["step"]
@@ -453,7 +460,12 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     else:
         step.ev_fwd_begin = step.ev_fwd_end = step.ev_bwd_begin = step.ev_bwd_end = None
     lib = _lib.load()
+    if _t is not None:
+        _t.append(time.perf_counter())
     rc = lib.dcl_step_fwd(ctypes.byref(step), _stream())
+    if _t is not None:
+        _t.append(time.perf_counter())
+        _DEBUG_PY_TIMES.append([(b - a) * 1e3 for a, b in zip(_t[:-1], _t[1:])])      # buffers+dzero, carve, rng+struct, C call
     info = sb["info"]
     if rc == 2:
         print("this shoud be never touched! {} {} {}".format(int(info[0]), int(info[1]), int(info[2])))
@@ -558,7 +570,11 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, feats, labels, predict, crit, shard):
         res = _run_step(crit, feats, labels, predict, shard, ctx.needs_input_grad[0], True)
         ctx.res = res
-        return res.loss
+        # the output must not stay reachable from ctx: output -> grad_fn -> ctx -> res -> output would be a reference
+        # cycle, and everything the step holds (the 537 MB gradient buffer included) would live until the cyclic
+        # garbage collector runs - the allocator then has to cudaMalloc fresh blocks in the meantime (15-45 ms stalls)
+        out, res.loss = res.loss, None
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -596,7 +612,8 @@ class _DoublyFn(torch.autograd.Function):
         res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False)
         ctx.res = res
         ctx.shape2 = (B2, C, h, w)
-        return pooled, res.loss
+        out, res.loss = res.loss, None           # no reference cycle through the output (see _StepFn.forward)
+        return pooled, out
 
     @staticmethod
     def backward(ctx, g_pooled, g_pixel):

@@ -153,6 +153,8 @@ int dcl_host_plan_rows_sharded(const int32_t* counts, int Bl, int world, int ran
  * previous plan left it): out[4] = plans served by the stream, inline plans, stream starts, drops.
  * DCL_HOST_LOOKAHEAD=0 in the environment disables the stream. */
 int dcl_host_lookahead_stats(long long* out);
+/* Diagnostics: out[2] = nanoseconds the plans have spent waiting for the look-ahead worker (total, longest wait). */
+int dcl_host_lookahead_wait(long long* out);
 /* Diagnostics: cumulative nanoseconds of the last plan at the end of each of its sections: out[8] = anchor list,
  * + generator state / look-ahead attach, + permutations, + state write-back / commit, + row requests, -, -, -. */
 int dcl_host_plan_timing(long long* out);

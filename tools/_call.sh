@@ -1,6 +1,5 @@
 set -x
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551"
-DCL_BENCH_DUMP_STEPS=1 timeout 600 $TR bench.py --gpus 2 --steps 60 --warmup 5 > gpurun_out/r02p_a.json 2> gpurun_out/r02p_a.err
-NCCL_PROTO=Simple DCL_BENCH_DUMP_STEPS=1 timeout 600 $TR bench.py --gpus 2 --steps 60 --warmup 5 > gpurun_out/r02p_b.json 2> gpurun_out/r02p_b.err
-NCCL_PROTO=Simple timeout 300 $TR tools/sharded_profile.py cfg4 > gpurun_out/r02p_sharded_timeline_2gpu_simple.log 2>&1
-grep "per-step" gpurun_out/r02p_*.err
+B="python bench.py --warmup 5 --no-cpu-baseline --no-hbm"
+for i in 1 2; do DCL_DEBUG_PY_TIMES=1 DCL_BENCH_DUMP_STEPS=1 $B --steps 100 --workload cfg4 > gpurun_out/r02u_$i.json 2> gpurun_out/r02u_$i.err; done
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02u_bench.json 2> gpurun_out/r02u_bench.err
+grep -E "slow step|look-ahead" gpurun_out/r02u_*.err
