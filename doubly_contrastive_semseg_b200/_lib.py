@@ -60,6 +60,9 @@ SIGNATURES = {
     "dcl_comm_init": (_i, [_vp, _i, _i, _vp]),
     "dcl_comm_destroy": (_i, [_vp]),
     "dcl_comm_all_gather": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dcl_p2p_create": (_i, [_i, _i, _i, _i, _vp, _vp]),
+    "dcl_p2p_open": (_i, [_vp, _vp]),
+    "dcl_p2p_destroy": (_i, [_vp]),
 }
 
 
@@ -71,7 +74,7 @@ class Step(ctypes.Structure):
         ("max_samples", _i), ("max_views", _i),
         ("temperature", _f), ("base_temperature", _f),
         ("torch_rng_state", _vp), ("state_bytes", _sz),
-        ("world", _i), ("rank", _i), ("comm", _vp),
+        ("world", _i), ("rank", _i), ("comm", _vp), ("p2p", _vp),
         ("cap", _i),
         ("code", _vp), ("chunk_hist", _vp), ("counts_dev", _vp),
         ("req_dev", _vp), ("y_dev", _vp), ("pix", _vp), ("rowof", _vp), ("plan_dev", _vp),

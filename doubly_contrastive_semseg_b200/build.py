@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcl_b200.so")
-SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_contrast_small.cu", "dcl_sampler.cu", "dcl_plan.cu", "dcl_focal.cu", "dcl_step.cu", "dcl_host_rng.cpp", "dcl_comm.cpp", "dcl_clocks.cpp"]
+SOURCES = ["dcl_api.cu", "dcl_contrast.cu", "dcl_contrast_small.cu", "dcl_sampler.cu", "dcl_plan.cu", "dcl_focal.cu", "dcl_p2p.cu", "dcl_step.cu", "dcl_host_rng.cpp", "dcl_comm.cpp", "dcl_clocks.cpp"]
 HEADERS = ["dcl_ptx.cuh", "dcl_common.cuh", "dcl_plan.h", os.path.join("..", "..", "include", "dcl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3", "--use_fast_math", "-Xptxas", "-v"]

@@ -13,6 +13,7 @@
 // more than the kernels themselves.
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <cuda_runtime.h>
@@ -23,6 +24,9 @@ using namespace dcl;
 
 namespace dcl {
 int comm_all_gather(void* comm, const void* send, void* recv, size_t bytes, cudaStream_t st);
+struct P2p;
+uint8_t* p2p_begin(P2p* p, int kind);
+int p2p_exchange(P2p* p, int kind, size_t bytes_per_rank, bool use_copy_engine, cudaStream_t st);
 }
 
 namespace {
@@ -47,6 +51,16 @@ std::mutex g_mu;
 long long g_step_ns[12] = {0};
 inline long long now_ns() {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Where the dense gradient buffer is cleared on the second stream: 0 = right after classify, while the count table
+// is with the host (the GPU is idle then, but the fill also runs into k_plan / select and slows them); 1 = after the
+// gather, underneath the N x N sweeps (they lose ~10 us to it, which only pays when they are long).  Measured
+// (profiles/r02y_*): 8192 anchors 0.396 ms early vs 0.406 late; 65536 anchors 2.956 ms early vs 2.885 late.
+int fill_placement(int max_samples) {
+    static const int v = [] { const char* e = std::getenv("DCL_FILL_PLACEMENT"); return e ? std::atoi(e) : -1; }();
+    if (v >= 0) return v;
+    return max_samples >= 16384 ? 1 : 0;
 }
 
 int device_slot(PerDevice*& pd) {
@@ -144,18 +158,20 @@ extern "C" int dcl_step_begin(const dcl_step_t* s, void* stream) {
     if (!s) return fail(DCL_ERR_ARG, "null step descriptor");
     if (!s->labels || !s->predict || !s->code || !s->chunk_hist || !s->counts_dev || !s->counts_host)
         return fail(DCL_ERR_ARG, "null pointer in step descriptor");
-    if (s->world <= 0 || s->rank < 0 || s->rank >= s->world || (s->world > 1 && !s->comm))
+    if (s->world <= 0 || s->rank < 0 || s->rank >= s->world || (s->world > 1 && !s->comm && !s->p2p))
         return fail(DCL_ERR_ARG, "bad sharding (world=%d rank=%d)", s->world, s->rank);
     std::lock_guard<std::mutex> lock(g_mu);
     PerDevice* pd = nullptr;
     if (int e = device_slot(pd)) return e;
     cudaStream_t st = as_stream(stream);
     const size_t table = static_cast<size_t>(512) * s->B;                       // ints per rank
-    int32_t* mine = s->counts_dev + table * s->rank;
+    P2p* p2p = s->world > 1 ? static_cast<P2p*>(s->p2p) : nullptr;
+    int32_t* counts_all = p2p ? reinterpret_cast<int32_t*>(p2p_begin(p2p, 0)) : s->counts_dev;
+    int32_t* mine = counts_all + table * s->rank;
     if (int e = dcl_sample_classify(s->labels, s->predict, s->B, s->H, s->W, s->h, s->w, s->C_cls, s->code, s->chunk_hist,
                                     mine, stream))
         return e;
-    if (s->zero_fill && s->zero_fill_bytes && s->side_stream) {
+    if (s->zero_fill && s->zero_fill_bytes && s->side_stream && fill_placement(s->max_samples) == 0) {
         // The dense gradient buffer is cleared on the second stream from here on: while the count table travels to
         // the host, the host plans and the plan travels back, the GPU has nothing else to do.  The fill runs as a
         // few persistent blocks per SM (dcl_zero_fill_persistent), so kernels issued on `st` in the meantime always
@@ -166,9 +182,12 @@ extern "C" int dcl_step_begin(const dcl_step_t* s, void* stream) {
         if (int e = dcl_zero_fill(s->zero_fill, s->zero_fill_bytes, 1, s->side_stream)) return e;
         DCL_CUDA(cudaEventRecord(pd->ev_zero, side));
     }
-    if (s->world > 1)
+    if (p2p) {
+        if (int e = p2p_exchange(p2p, 0, table * sizeof(int32_t), false, st)) return e;
+    } else if (s->world > 1) {
         if (int e = comm_all_gather(s->comm, mine, s->counts_dev, table * sizeof(int32_t), st)) return e;
-    DCL_CUDA(cudaMemcpyAsync(s->counts_host, s->counts_dev, sizeof(int32_t) * table * s->world, cudaMemcpyDeviceToHost, st));
+    }
+    DCL_CUDA(cudaMemcpyAsync(s->counts_host, counts_all, sizeof(int32_t) * table * s->world, cudaMemcpyDeviceToHost, st));
     DCL_CUDA(cudaEventRecord(pd->ev_counts, st));
     if (s->zero_fill && s->zero_fill_bytes && !s->side_stream)
         DCL_CUDA(cudaMemsetAsync(s->zero_fill, 0, s->zero_fill_bytes, st));    // still overlaps the host's plan
@@ -182,7 +201,7 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
         !s->sqnorm || !s->colA || !s->colB || !s->rowloss || !s->loss_sum || !s->loss || !s->workspace || !s->info ||
         !s->image || !s->cls || !s->num_hard || !s->num_easy || !s->keep_hard || !s->ranks || !s->torch_rng_state)
         return fail(DCL_ERR_ARG, "null pointer in step descriptor");
-    if (s->world > 1 && (!s->xchg_send || !s->xchg_recv)) return fail(DCL_ERR_ARG, "sharded step without exchange buffers");
+    if (s->world > 1 && !s->p2p && (!s->xchg_send || !s->xchg_recv)) return fail(DCL_ERR_ARG, "sharded step without exchange buffers");
     const int cap_min = (s->max_samples + DCL_TILE_ROWS - 1) / DCL_TILE_ROWS * DCL_TILE_ROWS;
     if (s->B <= 0 || s->h <= 0 || s->w <= 0 || s->cap < cap_min || s->cap < DCL_TILE_ROWS || s->cap % DCL_TILE_ROWS)
         return fail(DCL_ERR_ARG, "bad step shape (B=%d h=%d w=%d cap=%d max_samples=%d)", s->B, s->h, s->w, s->cap, s->max_samples);
@@ -261,15 +280,33 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     g_step_ns[4] = now_ns() - t0;                            // + plan kernel / row copies issued
     if (int e = dcl_sample_select(s->code, s->chunk_hist, s->B, hw, s->req_dev, n_pad, s->pix, s->rowof, stream)) return e;
     const size_t tile_bytes = static_cast<size_t>(n_pad) * DCL_DIM * 2;
-    uint8_t* tl = static_cast<uint8_t*>(s->tiles) + tile_bytes * rank;
+    P2p* p2p = world > 1 ? static_cast<P2p*>(s->p2p) : nullptr;
+    // The contrast set (megabytes) goes through NCCL's all-gather when a communicator is at hand: on eight GPUs its
+    // ring moves 16.8 MB in 66 us, where pushing every block to seven peers took 90 us plus the peers' skew
+    // (profiles/r02w_*).  tile_exchange (diagnostics): 0 = NCCL, 1 = push kernel, 2 = peer copies by the copy engines.
+    static const int tile_exchange = [] { const char* e = std::getenv("DCL_TILE_EXCHANGE"); return e ? std::atoi(e) : 0; }();
+    const bool tiles_p2p = p2p && (!s->comm || tile_exchange != 0);
+    uint8_t* tiles_all = tiles_p2p ? p2p_begin(p2p, 1) : static_cast<uint8_t*>(s->tiles);
+    uint8_t* tl = tiles_all + tile_bytes * rank;
     if (int e = dcl_gather_tiles(s->feats, s->B, hw, s->pix, n_pad, tl, s->sqnorm + static_cast<size_t>(rank) * n_pad,
                                  s->rowof, stream))
         return e;
-    if (world > 1)
+    if (s->zero_fill && s->zero_fill_bytes && s->side_stream && fill_placement(s->max_samples) == 1) {
+        // large problems: clear the gradient buffer underneath the N x N sweeps instead (see fill_placement)
+        cudaStream_t side = as_stream(s->side_stream);
+        DCL_CUDA(cudaEventRecord(pd->ev_fork, st));
+        DCL_CUDA(cudaStreamWaitEvent(side, pd->ev_fork, 0));
+        if (int e = dcl_zero_fill(s->zero_fill, s->zero_fill_bytes, 1, s->side_stream)) return e;
+        DCL_CUDA(cudaEventRecord(pd->ev_zero, side));
+    }
+    if (tiles_p2p) {
+        if (int e = p2p_exchange(p2p, 1, tile_bytes, tile_exchange == 2, st)) return e;
+    } else if (world > 1) {
         if (int e = comm_all_gather(s->comm, tl, s->tiles, tile_bytes, st)) return e;
+    }
     const int nI = n_pad / DCL_TILE_ROWS, nJ = nI * world, rb0 = nI * rank;
     if (s->ev_fwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_begin), st));
-    if (int e = dcl_contrast_fwd(s->tiles, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
+    if (int e = dcl_contrast_fwd(tiles_all, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
                                  s->base_temperature, s->workspace, s->workspace_bytes, s->colA, s->colB, s->rowloss,
                                  s->loss_sum, stream))
         return e;
@@ -277,16 +314,24 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     g_step_ns[5] = now_ns() - t0;                            // + select, gather, forward issued
     if (world > 1) {
         // every rank's row constants (32 B per row: the dS_ki terms of the backward) and loss partial, one message
-        if (int e = dcl_shard_pack(s->colA, s->colB, s->loss_sum, rank, n_pad, s->xchg_send, stream)) return e;
         const size_t msg = sizeof(float) * 4 * (2 * static_cast<size_t>(n_pad) + 1);
-        if (int e = comm_all_gather(s->comm, s->xchg_send, s->xchg_recv, msg, st)) return e;
-        if (int e = dcl_shard_unpack(s->xchg_recv, world, n_pad, s->colA, s->colB, n_global, s->loss, stream)) return e;
+        if (p2p) {
+            float* recv = reinterpret_cast<float*>(p2p_begin(p2p, 2));
+            float* send = recv + (msg / sizeof(float)) * rank;          // the rank's message is packed in place
+            if (int e = dcl_shard_pack(s->colA, s->colB, s->loss_sum, rank, n_pad, send, stream)) return e;
+            if (int e = p2p_exchange(p2p, 2, msg, false, st)) return e;
+            if (int e = dcl_shard_unpack(recv, world, n_pad, s->colA, s->colB, n_global, s->loss, stream)) return e;
+        } else {
+            if (int e = dcl_shard_pack(s->colA, s->colB, s->loss_sum, rank, n_pad, s->xchg_send, stream)) return e;
+            if (int e = comm_all_gather(s->comm, s->xchg_send, s->xchg_recv, msg, st)) return e;
+            if (int e = dcl_shard_unpack(s->xchg_recv, world, n_pad, s->colA, s->colB, n_global, s->loss, stream)) return e;
+        }
     } else {
         DCL_CUDA(cudaMemcpyAsync(s->loss, s->loss_sum + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (s->dF) {
         if (s->ev_bwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_begin), st));
-        if (int e = dcl_contrast_bwd(s->tiles, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
+        if (int e = dcl_contrast_bwd(tiles_all, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
                                      s->workspace_bytes, s->dF, stream))
             return e;
         if (s->ev_bwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_end), st));

@@ -403,8 +403,35 @@ def _shard_comm(group):
         dist.broadcast_object_list(box, src=src, group=group)
         comm = ctypes.c_void_p()
         _lib.call("dcl_comm_init", box[0], world, rank, ctypes.byref(comm))
-        ent = _COMMS[key] = (world, rank, comm)
+        ent = _COMMS[key] = (world, rank, comm, group)
     return ent
+
+
+_P2P = os.environ.get("DCL_P2P", "1") != "0"        # 0: the sharded step's exchanges go through NCCL
+
+
+def _peer_arena(group, world, rank, B, cap):
+    """Peer-memory arena of a sharded step (csrc/dcl_p2p.cu): created by every rank, IPC handles all-gathered once
+    through torch.distributed, peers mapped.  Returns the handle, or None when peer mapping is not possible (the
+    step then uses NCCL); the decision is taken collectively so that all ranks agree."""
+    import torch.distributed as dist
+    handle = ctypes.c_void_p()
+    ipc = (ctypes.c_ubyte * 64)()
+    lib = _lib.load()
+    ok = _P2P and world <= 16 and lib.dcl_p2p_create(world, rank, B, cap, ctypes.byref(handle), ipc) == 0
+    box = [None] * world
+    dist.all_gather_object(box, bytes(ipc) if ok else None, group=group)
+    if ok and all(b is not None for b in box):
+        ok = lib.dcl_p2p_open(handle, b"".join(box)) == 0
+    else:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok), group=group)
+    if all(flags):
+        return handle
+    if handle.value:
+        lib.dcl_p2p_destroy(handle)
+    return None
 
 
 class _StepResult:
@@ -418,7 +445,7 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     B, C, h, w = feats.shape
     dev = feats.device
     hw = h * w
-    world, rank, comm = shard if shard is not None else (1, 0, None)
+    world, rank, comm, group = shard if shard is not None else (1, 0, None, None)
     _t = [time.perf_counter()] if _DEBUG_PY_TIMES is not None else None
     sb = crit._step_buffers(B, h, w, dev, world)
     cap = sb["cap"]
@@ -441,6 +468,12 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     step.temperature, step.base_temperature = float(crit.temperature), float(crit.base_temperature)
     step.torch_rng_state, step.state_bytes = sbuf.ctypes.data, sbuf.nbytes
     step.rank, step.comm = rank, comm
+    if world > 1:
+        if "p2p" not in sb:
+            sb["p2p"] = _peer_arena(group, world, rank, B, cap)
+        step.p2p = sb["p2p"]
+    else:
+        step.p2p = None
     step.pix, step.rowof, step.dF, step.loss = p_pix, p_rowof, (p_dF if want_grad else None), loss.data_ptr()
     ws = _workspace(dev, sb["ws_bytes"])
     step.workspace, step.workspace_bytes = ws.data_ptr(), sb["ws_bytes"]

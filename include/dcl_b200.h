@@ -272,6 +272,9 @@ int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumulate, void* 
  *                    image / cls / num_hard / num_easy / keep_hard [>= world*B*256] i64: the anchors in reference
  *                    order; ranks [>= cap] i64: randperm prefixes (host-side plan only)
  *   comm             dcl_comm_init handle (world > 1)
+ *   p2p              optional dcl_p2p_create handle (world > 1): the three exchanges then go through NVLink peer memory
+ *                    (push kernels + flag waits, csrc/dcl_p2p.cu) instead of NCCL, and counts_dev / tiles / xchg_* are
+ *                    not used
  *   zero_fill        optional device buffer cleared off the critical path (side_stream: optional second stream)
  *   device_plan      0: always replay the generator on the host
  *   ev_*             optional cudaEvent_t recorded around the N x N forward / backward (measurement)
@@ -283,7 +286,7 @@ typedef struct dcl_step {
     int B, H, W, h, w, C_cls, ignore_label, max_samples, max_views;
     float temperature, base_temperature;
     void* torch_rng_state; size_t state_bytes;
-    int world, rank; void* comm;
+    int world, rank; void* comm; void* p2p;
     int cap;
     uint16_t* code; int32_t* chunk_hist; int32_t* counts_dev;
     int32_t* req_dev; int32_t* y_dev; int32_t* pix; int32_t* rowof; void* plan_dev;
@@ -333,6 +336,14 @@ int dcl_comm_unique_id(void* out128);
 int dcl_comm_init(const void* id128, int world, int rank, void** comm);
 int dcl_comm_destroy(void* comm);
 int dcl_comm_all_gather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+
+/* ---------------------------------------------------------------- peer-memory exchange of the sharded step
+ * Every rank creates an arena sized for (B images per rank, `cap` rows per rank, `world` ranks <= 16) and publishes its
+ * 64-byte CUDA IPC handle; after an out-of-band all-gather of the handles (world * 64 bytes, rank order) dcl_p2p_open
+ * maps the peers' arenas.  All ranks must live on one node with peer access between their GPUs (NVLink / NVSwitch). */
+int dcl_p2p_create(int world, int rank, int B_local, int cap, void** p2p_out, void* ipc_handle_out);
+int dcl_p2p_open(void* p2p, const void* all_handles);
+int dcl_p2p_destroy(void* p2p);
 
 /* ---------------------------------------------------------------- segmentation-loss neighbour
  * BoundaryAwareFocalLoss (loss.py:27-80), forward and gradient in one pass, the up-sampled logits never formed:

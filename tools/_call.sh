@@ -1,5 +1,5 @@
 set -x
-B="python bench.py --warmup 5 --no-cpu-baseline --no-hbm"
-for i in 1 2; do DCL_DEBUG_PY_TIMES=1 DCL_BENCH_DUMP_STEPS=1 $B --steps 100 --workload cfg4 > gpurun_out/r02u_$i.json 2> gpurun_out/r02u_$i.err; done
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02u_bench.json 2> gpurun_out/r02u_bench.err
-grep -E "slow step|look-ahead" gpurun_out/r02u_*.err
+DCL_FILL_PLACEMENT=1 python tools/torch_profile.py cfg2 > gpurun_out/r02y_timeline_cfg2_late.log 2>&1
+DCL_FILL_PLACEMENT=1 python tools/torch_profile.py cfg4 > gpurun_out/r02y_timeline_cfg4_late.log 2>&1
+DCL_FILL_PLACEMENT=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hbm > gpurun_out/r02y_bench_late.json 2> gpurun_out/r02y_bench_late.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hbm > gpurun_out/r02y_bench_early.json 2> gpurun_out/r02y_bench_early.err
