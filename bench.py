@@ -190,17 +190,16 @@ def run_reference(args):
     headline, wl, note = reference_workload(args, max(world, args.gpus))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # calibrate on a quarter of the images, then keep the largest sample whose steps + warm-up fit the budget
-    # (the reference's cost grows about quadratically with the number of images: one full-size index_put per anchor)
+    # One untimed step at full size decides: if steps + warm-up fit the budget the whole workload is timed; otherwise a
+    # proportional sample is (fewer images, max_samples scaled alike; the reference's cost grows about quadratically
+    # with the number of images - one full-size index_put per anchor).
     total_steps = args.steps + args.warmup
-    probe = shrink(wl, 0.25)
-    data = make_inputs(probe, seed=1, device="cpu")
-    crit, kind = cpu_module(probe)
-    t_probe, _ = cpu_step(crit, data, 999)
-    est_full = t_probe * (wl.B / probe.B) ** 2
+    data = make_inputs(wl, seed=1, device="cpu")
+    crit, kind = cpu_module(wl)
+    t_full, _ = cpu_step(crit, data, 999)
     sample = wl
-    if est_full * total_steps > REF_BUDGET_S:
-        f = (REF_BUDGET_S / (est_full * total_steps)) ** 0.5
+    if t_full * total_steps > REF_BUDGET_S:
+        f = (REF_BUDGET_S / (t_full * total_steps)) ** 0.5
         sample = shrink(wl, max(f, 1.0 / wl.B))
     data = make_inputs(sample, seed=1, device="cpu")
     crit, kind = cpu_module(sample)
@@ -521,7 +520,7 @@ def hbm_kernels(L, _lib, dev, peaks, reps=7):
           "k_zero_fill: dense gradient clear (runs on a second stream underneath the sweeps in the real step)")
     gap_g = torch.randn(B * DIM, device=dev)
     timed("dense_grad", lambda: _lib.call("dcl_dense_grad", _p(dF), _p(rowof), B, _p(g), _p(gap_g), _p(dfe), B, hw, _stream()),
-          dfe.numel() * 4 + n_pad * DIM * 4, "k_dense_grad: pooled-gradient broadcast + anchor gradients, one pass (doubly step)")
+          dfe.numel() * 4 + n_pad * DIM * 4, "dcl_dense_grad: pooled-gradient broadcast (k_gap_bwd) + anchor gradients added by k_scatter_px (doubly step)")
     sampler_us = res["classify"]["us"] + res["select"]["us"] + res["gather"]["us"]
     sampler_bytes = B * 19 * hw * 4 + B * hw * 8 + n_pad * DIM * 4 + n_pad * DIM * 2
     res["sampler_total"] = {"us": round(sampler_us, 2), "algorithmic_bytes": int(sampler_bytes),

@@ -434,56 +434,6 @@ k_scatter_px(const float* __restrict__ dF, const int32_t* __restrict__ rowof, co
     }
 }
 
-// Dense gradient of the doubly step in ONE pass: every (image, channel) plane is written once with
-// the pooled gradient gap_g[image*128 + channel] / hw (AdaptiveAvgPool2d backward, loss.py:115), and the sampled
-// pixels of the first B_pix images get their anchor gradient added on the way.  A CTA owns kDgChunks consecutive
-// 2048-pixel chunks (64 KB per plane: long enough runs for the DRAM pages) of kDgPlanes channel planes of one image:
-// it streams the broadcast value over them, then walks the sampled pixels of its chunks and rewrites those elements
-// with broadcast + anchor gradient (same CTA, after a barrier: no read-modify-write, no second kernel).
-constexpr int kDgChunks = 8, kDgPlanes = 16;
-__global__ void __launch_bounds__(kGsThreads)
-k_dense_grad(const float* __restrict__ dF, const int32_t* __restrict__ rowof, int B_pix, const float* __restrict__ grad_out,
-             const float* __restrict__ gap_g, float* __restrict__ dfeats, int hw, int n_chunks) {
-    __shared__ int2 list[kChunk];
-    __shared__ int warp_tot[kGsThreads / 32];
-    __shared__ float sg[kDgPlanes];
-    const int b = blockIdx.z, c0 = blockIdx.y * kDgPlanes, chunk0 = blockIdx.x * kDgChunks;
-    if (threadIdx.x < kDgPlanes) sg[threadIdx.x] = __ldg(gap_g + b * kDim + c0 + threadIdx.x) / static_cast<float>(hw);
-    __syncthreads();
-    const int pbeg = chunk0 * kChunk, pend = min(pbeg + kDgChunks * kChunk, hw);
-    float* plane0 = dfeats + (static_cast<size_t>(b) * kDim + c0) * hw;
-    if (((hw & 3) == 0)) {
-        const int n4 = (pend - pbeg) >> 2;
-        for (int c = 0; c < kDgPlanes; ++c) {
-            const float v = sg[c];
-            const float4 v4 = make_float4(v, v, v, v);
-            float4* o = reinterpret_cast<float4*>(plane0 + static_cast<size_t>(c) * hw + pbeg);
-            for (int i = threadIdx.x; i < n4; i += kGsThreads) __stcs(o + i, v4);
-        }
-    } else {
-        for (int c = 0; c < kDgPlanes; ++c)
-            for (int p = pbeg + threadIdx.x; p < pend; p += kGsThreads) plane0[static_cast<size_t>(c) * hw + p] = sg[c];
-    }
-    if (b >= B_pix) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float g = __ldg(grad_out);
-    for (int j = 0; j < kDgChunks && chunk0 + j < n_chunks; ++j) {
-        // (the barriers inside chunk_samples also order this CTA's broadcast stores before the rewrites below)
-        const int n = chunk_samples(rowof, b, chunk0 + j, hw, list, warp_tot);
-        for (int g0 = 0; g0 < n; g0 += 32) {
-            if (g0 + lane < n) {
-                const int2 e = list[g0 + lane];
-                // warp w: planes 2 w, 2 w + 1 of the group
-                const float2 v = __ldg(reinterpret_cast<const float2*>(dF + static_cast<size_t>(e.y) * kDim + c0 + warp * 2));
-                float* o = plane0 + static_cast<size_t>(warp * 2) * hw + e.x;
-                o[0] = fmaf(v.x, g, sg[warp * 2]);
-                o[static_cast<size_t>(hw)] = fmaf(v.y, g, sg[warp * 2 + 1]);
-            }
-        }
-        __syncthreads();                   // `list` is reused by the next chunk
-    }
-}
-
 // zero-fill that can share the SMs with the persistent tensor-core kernels (32 registers, no shared memory): issued
 // on a second stream it clears the dense gradient buffer underneath the N x N sweeps, which leave HBM idle
 __global__ void __launch_bounds__(128)
@@ -642,19 +592,6 @@ extern "C" int dcl_zero_fill(void* dst, size_t bytes, int persistent, void* stre
     return 0;
 }
 
-extern "C" int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, const float* grad_out, const float* gap_g,
-                              float* dfeats, int B_all, int hw, void* stream) {
-    if (int e = dcl_check_device()) return e;
-    if (!dF || !rowof || !grad_out || !gap_g || !dfeats) return fail(DCL_ERR_ARG, "null pointer argument");
-    if (B_pix < 0 || B_all < B_pix || B_all <= 0 || B_all > 65535 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
-    if ((hw & 3) == 0 && reinterpret_cast<uintptr_t>(dfeats) % 16) return fail(DCL_ERR_ARG, "dfeats must be 16-byte aligned");
-    const int n_chunks = (hw + kChunk - 1) / kChunk;
-    const dim3 grid((n_chunks + kDgChunks - 1) / kDgChunks, kDim / kDgPlanes, B_all);
-    k_dense_grad<<<grid, kGsThreads, 0, as_stream(stream)>>>(dF, rowof, B_pix, grad_out, gap_g, dfeats, hw, n_chunks);
-    DCL_LAUNCH_CHECK("k_dense_grad");
-    return 0;
-}
-
 extern "C" int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const float* grad_out,
                                 float* dfeats, int B, int hw, int zero_fill, const int32_t* rowof, void* stream) {
     if (int e = dcl_check_device()) return e;
@@ -754,5 +691,24 @@ extern "C" int dcl_gap_bwd(const float* g, int R, int hw, float* dx, int accumul
     if (accumulate) k_gap_bwd<true><<<R, 256, 0, as_stream(stream)>>>(g, hw, dx);
     else k_gap_bwd<false><<<R, 256, 0, as_stream(stream)>>>(g, hw, dx);
     DCL_LAUNCH_CHECK("k_gap_bwd");
+    return 0;
+}
+
+// Dense gradient of the doubly step: dfeats = pooled-gradient broadcast (+ anchor gradients at the
+// sampled pixels of the first B_pix images).  The dense tensor is written ONCE, by the streaming broadcast kernel
+// (k_gap_bwd, at the HBM write roofline); the anchor rows are then added by the pixel-ordered scatter, which touches
+// N x 128 elements only (1.03x the tensor size in DRAM traffic at the cfg3 shapes).  A single kernel that merged the
+// two (per-chunk sample lists inside the broadcast loop) reached 58 % of the roofline where the broadcast alone runs
+// at 100 %: 450 us against 313 + 35 us (profiles/r02_ncu_sampler_ncu_summary.csv), so the two stay separate launches.
+extern "C" int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, const float* grad_out, const float* gap_g,
+                              float* dfeats, int B_all, int hw, void* stream) {
+    if (int e = dcl_check_device()) return e;
+    if (!dF || !rowof || !grad_out || !gap_g || !dfeats) return fail(DCL_ERR_ARG, "null pointer argument");
+    if (B_pix < 0 || B_all < B_pix || B_all <= 0 || B_all > 65535 || hw <= 0) return fail(DCL_ERR_ARG, "bad shape");
+    if (int e = dcl_gap_bwd(gap_g, B_all * kDim, hw, dfeats, 0, stream)) return e;
+    if (B_pix == 0) return 0;
+    const int n_chunks = (hw + kChunk - 1) / kChunk;
+    k_scatter_px<true><<<dim3(n_chunks, B_pix), kGsThreads, 0, as_stream(stream)>>>(dF, rowof, grad_out, dfeats, hw);
+    DCL_LAUNCH_CHECK("k_scatter_px");
     return 0;
 }

@@ -633,7 +633,7 @@ class _DoublyFn(torch.autograd.Function):
     """Both terms' touch points on the shared embedding tensor in one autograd node (the reference
     applies SupConLoss to `fine_feat` [2B,...] and PixelContrastLoss to `fine_feat[:B]`, trainer.py:143-158,
     network/weathernet.py:76-82): forward = global average pool of all 2B images + the pixel step on the first B;
-    backward = ONE pass over the dense gradient: pooled gradient broadcast, anchor gradients added."""
+    backward = the dense gradient written once (pooled gradient broadcast), anchor gradients added at 1M elements."""
 
     @staticmethod
     def forward(ctx, feats2, labels, predict, crit):
@@ -662,7 +662,7 @@ class _DoublyFn(torch.autograd.Function):
         else:
             _lib.call("dcl_step_bwd", res.p_dF, res.p_pix, res.p_rowof, res.n_pad, _p(_grad_scalar(g_pixel)), _p(dx), B,
                       h * w, 0, _p(gp), B2 * C, _stream())
-            _count(1)
+            _count(2)
         return dx, None, None, None
 
 

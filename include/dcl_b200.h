@@ -219,10 +219,10 @@ int dcl_scatter_grad(const float* dF, const int32_t* pix, int n_rows, const floa
  * that on a second stream the fill never keeps kernels of the main stream waiting for a slot (the step clears the
  * dense gradient buffer this way while the count table is with the host); 0: one short block per 64 KB. */
 int dcl_zero_fill(void* dst, size_t bytes, int persistent, void* stream);
-/* The dense gradient of the doubly contrastive step in ONE pass (both losses hit the same `fine_feat`,
+/* The dense gradient of the doubly contrastive step (both losses hit the same `fine_feat`,
  * trainer.py:144-152): dfeats [B_all,128,hw] = gap_g[image*128 + channel] / hw everywhere (AdaptiveAvgPool2d
- * backward, loss.py:115) + (*grad_out) * dF[row] at the sampled pixels of the first B_pix images (rowof from
- * dcl_sample_select).  No zero-fill, no read-modify-write. */
+ * backward, loss.py:115), written once by the streaming broadcast, + (*grad_out) * dF[row] added at the sampled
+ * pixels of the first B_pix images (rowof from dcl_sample_select).  No zero-fill; DRAM traffic 1.03x the tensor. */
 int dcl_dense_grad(const float* dF, const int32_t* rowof, int B_pix, const float* grad_out, const float* gap_g,
                    float* dfeats, int B_all, int hw, void* stream);
 /* dZ [n,128] = dF[:n] * (*grad_out)  (image-level term). */
@@ -310,8 +310,8 @@ int dcl_step_fwd(const dcl_step_t* step, void* stream);
  * dfeats first (0: the caller already did, e.g. through dcl_step_t.zero_fill).  gap_g != NULL fuses the image-level
  * term's gradient into the same pass (both losses hit the same `fine_feat`, trainer.py:144-152):
  * dfeats has gap_rows/128 >= B images, every (image, channel) row r is written with gap_g[r] / hw (the
- * AdaptiveAvgPool2d backward, loss.py:115) and the anchor gradients are added on the way (dcl_dense_grad): the dense
- * tensor is written once and never read. */
+ * AdaptiveAvgPool2d backward, loss.py:115) and the anchor gradients are added at the sampled pixels (dcl_dense_grad):
+ * the dense tensor is written once, no zero-fill. */
 int dcl_step_bwd(const float* dF, const int32_t* pix, const int32_t* rowof, int n_pad, const float* grad_out,
                  float* dfeats, int B, int hw, int zero_fill, const float* gap_g, int gap_rows, void* stream);
 

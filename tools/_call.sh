@@ -1,5 +1,5 @@
 set -x
-DCL_FILL_PLACEMENT=1 python tools/torch_profile.py cfg2 > gpurun_out/r02y_timeline_cfg2_late.log 2>&1
-DCL_FILL_PLACEMENT=1 python tools/torch_profile.py cfg4 > gpurun_out/r02y_timeline_cfg4_late.log 2>&1
-DCL_FILL_PLACEMENT=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hbm > gpurun_out/r02y_bench_late.json 2> gpurun_out/r02y_bench_late.err
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-hbm > gpurun_out/r02y_bench_early.json 2> gpurun_out/r02y_bench_early.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r03a_tests.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r03a_bench.json 2> gpurun_out/r03a_bench.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r03a_bench_ref.json 2> gpurun_out/r03a_bench_ref.err
+python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/r03a_smoke.log 2>&1

@@ -26,10 +26,16 @@ torch.cuda.synchronize()
 print("pixel loss", float(loss))
 del d, x
 torch.cuda.empty_cache()
-big = torch.randn(32, 128, 256, 512, device="cuda", requires_grad=True)
+# the doubly step at the cfg3 shape: global average pool over [32,128,256,512] (2.15 GB), one-pass dense gradient
+import types
+wl3 = WORKLOADS["cfg3"]
+d3 = make_inputs(wl3, seed=1, device="cuda")
+both = pkg.DoublyContrastiveLoss(device="cuda", opts=types.SimpleNamespace(deeplab=False))
+both.pixel.max_samples, both.pixel.max_views = wl3.max_samples, wl3.max_views
+big = d3["feats"].requires_grad_(True)
 for _ in range(reps):
     big.grad = None
-    p = _GapFn.apply(big)
-    p.sum().backward()
+    sup, pix = both(big, labels=d3["labels"], predict=d3["predict"], class_labels=d3["weather"])
+    ((sup + pix) / wl3.B).backward()
 torch.cuda.synchronize()
-print("gap", float(p.sum()))
+print("doubly", float(sup.detach()), float(pix.detach()))
