@@ -529,6 +529,22 @@ def hbm_kernels(L, _lib, dev, peaks, reps=7):
                             "what": "classify + select + gather against SURVEY 8d's sampler bytes (cfg2: 94 MB)"}
     del d, dfe, dF
     torch.cuda.empty_cache()
+    # segmentation-loss neighbour at the cfg2 shapes: logits [8,19,256,512], labels / EDT weights [8,1024,2048]
+    gq = torch.Generator(device=dev).manual_seed(3)
+    logits = 2.0 * torch.randn(wl.B, 19, wl.h, wl.w, generator=gq, device=dev)
+    target = torch.randint(0, 19, (wl.B, wl.H, wl.W), generator=gq, device=dev)
+    alpha = torch.rand(wl.B, wl.H, wl.W, generator=gq, device=dev)
+    cw = torch.ones(19, device=dev)
+    unscaled = torch.empty_like(logits)
+    loss_n = torch.empty(2, device=dev)
+    fws = int(_lib.load().dcl_focal_workspace_bytes(wl.B, wl.h, wl.w))
+    fbuf = torch.empty(fws, dtype=torch.uint8, device=dev)
+    timed("focal", lambda: _lib.call("dcl_focal_fwd", _p(logits), _p(target), _p(alpha), _p(cw), wl.B, 19, wl.h, wl.w,
+                                     wl.H, wl.W, 255, 0.5, 0, _p(unscaled), _p(loss_n), _p(fbuf), fws, _stream()),
+          target.numel() * 12 + 2 * logits.numel() * 4,
+          "k_focal: BoundaryAwareFocalLoss forward + gradient in one pass (labels 8 B + EDT weight 4 B per pixel, "
+          "logits read, gradient written); MUFU-bound")
+    del logits, target, alpha, unscaled
     wl3 = WORKLOADS["cfg3"]
     x = torch.randn(2 * wl3.B, DIM, wl3.h, wl3.w, device=dev)
     pooled = torch.empty(2 * wl3.B * DIM, device=dev)
