@@ -14,6 +14,7 @@ The headline line is the SAME workload at every N, so that the driver's 1/2/4/8 
 At N = 1 the line also carries, under "workloads", the same measurements for
   cfg2 (configs[1]): batch 8 @ 2048x1024, 8192 anchors (pixel term), and
   cfg3 (configs[2]): the doubly contrastive step (pixel term + 32x32 image-level term) on the 2x16-crop batch,
+  cfg5 (configs[4]): one GPU's share (8 images x 2 crops at 1024x512) of the full SwiftNet-RN18 training step,
 and "roofline_hbm": achieved GB/s of the HBM-bound kernels (sampler, gather, scatter, global average pool).
 `value` has inputs resident in HBM; `e2e` times the same step through the module with pinned HOST inputs
 (H2D of feats/labels/predict inside the timed region, D2H of the loss).
@@ -500,7 +501,7 @@ def hbm_kernels(L, _lib, dev, peaks, reps=7):
     def f_classify():
         code_chunk["v"] = L.classify(d["labels"], d["predict"], h, w)
     timed("classify", f_classify, B * 19 * hw * 4 + B * hw * 8 + B * hw * 2,
-          "k_classify + k_chunk_prefix: predict read + one label per output pixel + code write")
+          "k_classify: predict read + one label per output pixel + code write")
     code, chunk, counts = code_chunk["v"]
     rowof = torch.empty(B * hw, dtype=torch.int32, device=dev)
     timed("select", lambda: L.select_pixels(code, chunk, B, hw, req_dev, n_pad, rowof), n_pad * (16 + 4 + 4) + n_pad * 4096,
@@ -657,6 +658,16 @@ def run_ours(args):
                     b["config"]["step"] = "(supcon + pixel) / batch_size through DoublyContrastiveLoss, one backward (trainer.py:143-158)"
                 blocks[k] = b
             line["workloads"] = blocks
+        if world == 1 and args.workload == "auto" and not args.no_train_step:
+            # BASELINE.json configs[4] on ONE of its eight GPUs: the full SwiftNet-RN18 training step (network in
+            # cuDNN under bf16 autocast, the three losses of this repository, fused Adam), 8 images x 2 crops per GPU
+            from tools import train_bench
+            t5 = train_bench.run(train_bench.parse(["--steps", str(min(args.steps, 10)), "--warmup", "3"]), init_dist=False)
+            line.setdefault("workloads", {})["cfg5"] = {
+                "value": t5["value"], "unit": t5["unit"], "ms_per_step": t5["ms_per_step"], "config": t5["config"],
+                "losses": t5["losses"], "peak_mem_gb": t5["peak_mem_gb"],
+                "note": "per-GPU share of configs[4] (batch 64 over 8 GPUs = 8 images per GPU); tools/train_bench.py under "
+                        "torchrun runs it on N GPUs (DDP, pixel term sharded)"}
         if world == 1 and not args.no_hbm:
             hb = hbm_kernels(L, _lib, dev, peaks)
             top = "gap_fwd"
@@ -702,6 +713,7 @@ def main():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the cfg5 block (full training step)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

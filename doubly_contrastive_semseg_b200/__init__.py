@@ -4,6 +4,8 @@ from .loss import (MODE_PIXEL, MODE_SUPCON, DoublyContrastiveLoss, PixelContrast
                    contrast_rows, layout_rows, plan_anchors, shard_plan)
 
 from .focal import BoundaryAwareFocalLoss
+from .swiftnet import WeatherNet
+from .train_step import TrainStep
 
-__all__ = ["BoundaryAwareFocalLoss", "PixelContrastLoss", "DoublyContrastiveLoss", "ShardedPixelContrastLoss", "SupConLoss", "shard_plan", "contrast_rows", "plan_anchors", "layout_rows",
+__all__ = ["BoundaryAwareFocalLoss", "WeatherNet", "TrainStep", "PixelContrastLoss", "DoublyContrastiveLoss", "ShardedPixelContrastLoss", "SupConLoss", "shard_plan", "contrast_rows", "plan_anchors", "layout_rows",
            "MODE_PIXEL", "MODE_SUPCON"]

@@ -26,6 +26,14 @@ int current_device();                         // ordinal of the current device, 
             return ::dcl::fail(static_cast<int>(e_), "launch %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
+// dcl_contrast.cu, for the one-call step (dcl_step.cu): the C-ABI entry points plus `loss_out` (the loss written by the
+// forward's last block, no copy afterwards) and `chained` (the backward directly follows that forward on the stream)
+int contrast_fwd_ex(const void* tiles, const int32_t* y, const float* sqnorm, int nJ, int rb0, int nI, int n_valid,
+                    int mode, float temperature, float base_temperature, void* workspace, size_t workspace_bytes,
+                    float* colA, float* colB, float* rowloss, float* loss_sum, float* loss_out, void* stream);
+int contrast_bwd_ex(const void* tiles, const int32_t* y, const float* colA, const float* colB, int nJ, int rb0,
+                    int nI, int mode, void* workspace, size_t workspace_bytes, float* dF, bool chained, void* stream);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace dcl

@@ -130,6 +130,7 @@ struct Params {
     float* rowloss;          // [nJ*128]
     float* blockloss;        // [nI]
     float* loss_sum;
+    float* loss_out;         // optional: the loss itself (sum / n_valid) once more, where the caller wants it
     unsigned int* ticket;    // last-block counters: [0] k_rows, [1] k_finalize
     long long* trace;        // diagnostics only (dcl_debug_trace)
     long long* cta_times;    // diagnostics only (dcl_debug_cta_times): [kernel slot][256 CTAs][4] globaltimer / clock64 at entry, exit
@@ -1185,6 +1186,7 @@ __device__ __forceinline__ void block_loss_sum(const Params& p, float rl, unsign
         if (r == 0) {
             p.loss_sum[0] = s;
             p.loss_sum[1] = s / static_cast<float>(p.n_valid);      // the loss itself when the rows are not sharded
+            if (p.loss_out) p.loss_out[0] = s / static_cast<float>(p.n_valid);
         }
     }
 }
@@ -2153,8 +2155,10 @@ static int run_fwd_legacy(Params p, const Layout& L, cudaStream_t st) {
     return 0;
 }
 
+// `chained`: the call directly follows this module's forward of the same problem on `st`, so the first kernel may be
+// a programmatic dependent of the forward's last one instead of waiting for the stream to drain
 template <int kMode>
-static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
+static int run_bwd(Params p, const Layout& L, float* dF, bool chained, cudaStream_t st) {
     static Configured cfgd;
     bool& configured = cfgd.here();
     if (!configured) {
@@ -2162,8 +2166,8 @@ static int run_bwd(Params p, const Layout& L, float* dF, cudaStream_t st) {
         configured = true;
     }
     // first kernel of the chain (launched plainly): block info, and for the pixel term the row polynomials with it
-    if (kMode == DCL_MODE_PIXEL) DCL_LAUNCH("k_bwd_prep", k_bwd_prep, p.nJ, 128, 0, st, false, p);
-    else DCL_LAUNCH("k_blockinfo", k_blockinfo, p.nJ, 128, 0, st, false, p);
+    if (kMode == DCL_MODE_PIXEL) DCL_LAUNCH("k_bwd_prep", k_bwd_prep, p.nJ, 128, 0, st, chained, p);
+    else DCL_LAUNCH("k_blockinfo", k_blockinfo, p.nJ, 128, 0, st, chained, p);
     p.dF = dF;
     DCL_LAUNCH("k_backward", k_backward<kMode>, L.partD.G, kThreads, SmemBwd::kBytes, st, true, p);
     return 0;
@@ -2242,11 +2246,9 @@ static int check_args(const void* tiles, const int32_t* y, int nJ, int rb0, int 
     return 0;
 }
 
-extern "C" int dcl_contrast_fwd(const void* tiles, const int32_t* y, const float* sqnorm, int nJ, int rb0,
-                                int nI, int n_valid, int mode, float temperature,
-                                float base_temperature, void* workspace, size_t workspace_bytes,
-                                float* colA, float* colB, float* rowloss, float* loss_sum,
-                                void* stream) {
+int dcl::contrast_fwd_ex(const void* tiles, const int32_t* y, const float* sqnorm, int nJ, int rb0, int nI, int n_valid,
+                         int mode, float temperature, float base_temperature, void* workspace, size_t workspace_bytes,
+                         float* colA, float* colB, float* rowloss, float* loss_sum, float* loss_out, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (nJ <= 0 || nI <= 0) return fail(DCL_ERR_ARG, "empty problem");
     Layout L = make_layout(nI, nJ);
@@ -2261,15 +2263,24 @@ extern "C" int dcl_contrast_fwd(const void* tiles, const int32_t* y, const float
     p.colB = reinterpret_cast<float4*>(colB);
     p.rowloss = rowloss;
     p.loss_sum = loss_sum;
+    p.loss_out = loss_out;
     if (mode == DCL_MODE_PIXEL)
         return (g_debug_flags & 8) ? run_fwd_legacy<DCL_MODE_PIXEL>(p, L, as_stream(stream))
                                    : run_fwd_v3(p, L, as_stream(stream));
     return run_fwd_legacy<DCL_MODE_SUPCON>(p, L, as_stream(stream));
 }
 
-extern "C" int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB,
-                                int nJ, int rb0, int nI, int mode, void* workspace,
-                                size_t workspace_bytes, float* dF, void* stream) {
+extern "C" int dcl_contrast_fwd(const void* tiles, const int32_t* y, const float* sqnorm, int nJ, int rb0,
+                                int nI, int n_valid, int mode, float temperature,
+                                float base_temperature, void* workspace, size_t workspace_bytes,
+                                float* colA, float* colB, float* rowloss, float* loss_sum,
+                                void* stream) {
+    return contrast_fwd_ex(tiles, y, sqnorm, nJ, rb0, nI, n_valid, mode, temperature, base_temperature, workspace,
+                           workspace_bytes, colA, colB, rowloss, loss_sum, nullptr, stream);
+}
+
+int dcl::contrast_bwd_ex(const void* tiles, const int32_t* y, const float* colA, const float* colB, int nJ, int rb0,
+                         int nI, int mode, void* workspace, size_t workspace_bytes, float* dF, bool chained, void* stream) {
     if (int e = dcl_check_device()) return e;
     if (nJ <= 0 || nI <= 0) return fail(DCL_ERR_ARG, "empty problem");
     Layout L = make_layout(nI, nJ);
@@ -2281,6 +2292,12 @@ extern "C" int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float
     Params p = make_params(L, tiles, y, nullptr, nJ, rb0, nI, 1, mode, 1.f, 1.f, workspace);
     p.colA = reinterpret_cast<float4*>(const_cast<float*>(colA));
     p.colB = reinterpret_cast<float4*>(const_cast<float*>(colB));
-    return mode == DCL_MODE_PIXEL ? run_bwd<DCL_MODE_PIXEL>(p, L, dF, as_stream(stream))
-                                  : run_bwd<DCL_MODE_SUPCON>(p, L, dF, as_stream(stream));
+    return mode == DCL_MODE_PIXEL ? run_bwd<DCL_MODE_PIXEL>(p, L, dF, chained, as_stream(stream))
+                                  : run_bwd<DCL_MODE_SUPCON>(p, L, dF, chained, as_stream(stream));
+}
+
+extern "C" int dcl_contrast_bwd(const void* tiles, const int32_t* y, const float* colA, const float* colB,
+                                int nJ, int rb0, int nI, int mode, void* workspace,
+                                size_t workspace_bytes, float* dF, void* stream) {
+    return contrast_bwd_ex(tiles, y, colA, colB, nJ, rb0, nI, mode, workspace, workspace_bytes, dF, false, stream);
 }

@@ -6,6 +6,7 @@
 //   scatter  : anchor-row gradients back into a dense NCHW gradient                      (autograd of :333)
 //   gap      : global average pool forward / backward for the image-level term          (loss.py:104,115)
 // All index work is integer-exact with respect to the reference; only `gather` rounds (to bf16).
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "dcl_common.cuh"
 #include "dcl_ptx.cuh"
@@ -21,48 +22,56 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
     return s < in_size - 1 ? s : in_size - 1;
 }
 
-// ---- classify: 256 threads x 8 pixels = one 2048-pixel chunk per CTA.  All label loads and a batch of class planes
-// are in flight before anything is compared (the kernel is HBM-bound: what matters is bytes in flight per SM).
-template <int kBatch>
-__device__ __forceinline__ void argmax_batch(const float* __restrict__ pl, size_t hw, int c0, int cn, float (&best)[8],
-                                             int (&arg)[8]) {
-    float4 v[kBatch][2];
+// ---- classify: one 2048-pixel chunk per CTA, kPx pixels per thread (4 -> 512 threads, 8 -> 256 threads).  The kernel is
+// HBM-bound: what matters is bytes in flight per SM, so all label loads and a batch of class planes are issued before
+// anything is compared.  Four pixels per thread keep the thread under 64 registers (two 512-thread CTAs = 32 warps
+// per SM instead of 16) and make a warp's plane loads contiguous (512 B per instruction).
+template <int kPx, int kBatch>
+__device__ __forceinline__ void argmax_batch(const float* __restrict__ pl, size_t hw, int c0, int cn, float (&best)[kPx],
+                                             int (&arg)[kPx]) {
+    float4 v[kBatch][kPx / 4];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
         if (u < cn) {
             const float4* p = reinterpret_cast<const float4*>(pl + static_cast<size_t>(c0 + u) * hw);
-            v[u][0] = __ldcs(p);
-            v[u][1] = __ldcs(p + 1);
+#pragma unroll
+            for (int q = 0; q < kPx / 4; ++q) v[u][q] = __ldcs(p + q);
         }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u)
         if (u < cn) {
-            const float x[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                // first-index argmax: strict '>' while scanning classes upward; NaN wins once (torch.max)
-                const bool take = (c0 + u == 0) || (x[e] > best[e]) || (x[e] != x[e] && best[e] == best[e]);
-                if (take) { best[e] = x[e]; arg[e] = c0 + u; }
+            for (int q = 0; q < kPx / 4; ++q) {
+                const float x[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // first-index argmax: strict '>' while scanning classes upward; NaN wins once (torch.max)
+                    float& b = best[q * 4 + e];
+                    const bool take = (c0 + u == 0) || (x[e] > b) || (x[e] != x[e] && b == b);
+                    if (take) { b = x[e]; arg[q * 4 + e] = c0 + u; }
+                }
             }
         }
 }
 
-__global__ void __launch_bounds__(256)
+template <int kPx>
+__global__ void __launch_bounds__(kChunk / kPx, kPx == 4 ? 2 : 1)
 k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict, int H, int W, int h,
            int w, int C, float scale_h, float scale_w, uint16_t* __restrict__ code,
            int32_t* __restrict__ chunk_hist, int32_t* __restrict__ counts, int n_chunks) {
+    constexpr int kBatch = kPx == 4 ? 5 : 4;
     __shared__ int hist[kBins];
     const int b = blockIdx.y, chunk = blockIdx.x, hw = h * w;
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    const int p0 = chunk * kChunk + threadIdx.x * 8;
+    const int p0 = chunk * kChunk + threadIdx.x * kPx;
     const float* pl = predict + static_cast<size_t>(b) * C * hw;
     const int64_t* lb = labels + static_cast<size_t>(b) * H * W;
 
-    // labels first: eight independent loads (one DRAM sector each at a 4x down-sampling)
-    long long lab[8];
+    // labels first: independent loads (one DRAM sector each at a 4x down-sampling)
+    long long lab[kPx];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < kPx; ++e) {
         const int p = p0 + e;
         lab[e] = -1;
         if (p < hw) {
@@ -70,18 +79,18 @@ k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict
             lab[e] = __ldcs(lb + static_cast<size_t>(nearest_src(yy, scale_h, H)) * W + nearest_src(xx, scale_w, W));
         }
     }
-    float best[8];
-    int arg[8];
+    float best[kPx];
+    int arg[kPx];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { best[e] = 0.f; arg[e] = 0; }
-    const bool vec = ((hw & 3) == 0) && (p0 + 7 < hw);
+    for (int e = 0; e < kPx; ++e) { best[e] = 0.f; arg[e] = 0; }
+    const bool vec = ((hw & 3) == 0) && (p0 + kPx - 1 < hw);
     if (vec) {
         const float* q = pl + p0;
         int c = 0;
-        for (; c + 4 <= C; c += 4) argmax_batch<4>(q, hw, c, 4, best, arg);
-        if (c < C) argmax_batch<4>(q, hw, c, C - c, best, arg);
+        for (; c + kBatch <= C; c += kBatch) argmax_batch<kPx, kBatch>(q, hw, c, kBatch, best, arg);
+        if (c < C) argmax_batch<kPx, kBatch>(q, hw, c, C - c, best, arg);
     } else {
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < kPx; ++e) {
             if (p0 + e >= hw) break;
             for (int c = 0; c < C; ++c) {
                 const float v = __ldg(pl + static_cast<size_t>(c) * hw + p0 + e);
@@ -93,11 +102,11 @@ k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict
     // codes + histogram.  Labels are spatially coherent: the pixels of a thread that share its first pixel's label are
     // counted in two registers (hard / easy) and warp-aggregated with one match; the others (class boundaries) go
     // one by one.
-    uint16_t out[8];
+    uint16_t out[kPx];
     const int lab0 = (lab[0] >= 0 && lab[0] <= 255) ? static_cast<int>(lab[0]) : -1;
     int n_hard0 = 0, n_easy0 = 0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < kPx; ++e) {
         out[e] = 0xFFFF;
         if (lab[e] >= 0 && lab[e] <= 255) {
             const int l = static_cast<int>(lab[e]);
@@ -116,19 +125,23 @@ k_classify(const int64_t* __restrict__ labels, const float* __restrict__ predict
         }
     }
     if (vec && (hw & 7) == 0) {
-        *reinterpret_cast<uint4*>(code + static_cast<size_t>(b) * hw + p0) =
-            make_uint4(out[0] | (static_cast<uint32_t>(out[1]) << 16), out[2] | (static_cast<uint32_t>(out[3]) << 16),
-                       out[4] | (static_cast<uint32_t>(out[5]) << 16), out[6] | (static_cast<uint32_t>(out[7]) << 16));
+        uint32_t wds[kPx / 2];
+#pragma unroll
+        for (int e = 0; e < kPx / 2; ++e) wds[e] = out[2 * e] | (static_cast<uint32_t>(out[2 * e + 1]) << 16);
+        uint16_t* dstc = code + static_cast<size_t>(b) * hw + p0;
+        if (kPx == 8) *reinterpret_cast<uint4*>(dstc) = make_uint4(wds[0], wds[1], wds[kPx / 2 - 2], wds[kPx / 2 - 1]);
+        else *reinterpret_cast<uint2*>(dstc) = make_uint2(wds[0], wds[1]);
     } else {
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < kPx; ++e)
             if (p0 + e < hw) code[static_cast<size_t>(b) * hw + p0 + e] = out[e];
     }
     __syncthreads();
-    // per-chunk histogram (select scans it) and the per-image totals (the host's count table)
-    int32_t* dst = chunk_hist + (static_cast<size_t>(b) * n_chunks + chunk) * kBins;
+    // per-chunk histogram, bin-major ([image][bin][chunk]: select reads one bin's chunks as a contiguous run), and the
+    // per-image totals (the host's count table)
+    int32_t* dst = chunk_hist + static_cast<size_t>(b) * kBins * n_chunks + chunk;
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
         const int v = hist[i];
-        dst[i] = v;
+        dst[static_cast<size_t>(i) * n_chunks] = v;
         if (v) atomicAdd(counts + b * kBins + i, v);
     }
 }
@@ -149,11 +162,11 @@ k_select(const uint16_t* __restrict__ code, const int32_t* __restrict__ chunk_hi
     const int b = rq.x, bin = rq.y * 2 + rq.z;
     int rem = rq.w;
     const uint16_t want = static_cast<uint16_t>(rq.y | (rq.z << 8));
-    const int32_t* hst = chunk_hist + static_cast<size_t>(b) * n_chunks * kBins + bin;
+    const int32_t* hst = chunk_hist + (static_cast<size_t>(b) * kBins + bin) * n_chunks;
     int chunk = -1;
     for (int c0 = 0; c0 < n_chunks && chunk < 0; c0 += 32) {
         const int c = c0 + lane;
-        const int cnt = (c < n_chunks) ? __ldg(hst + static_cast<size_t>(c) * kBins) : 0;
+        const int cnt = (c < n_chunks) ? __ldg(hst + c) : 0;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -520,8 +533,14 @@ extern "C" int dcl_sample_classify(const int64_t* labels, const float* predict, 
     const float sw = static_cast<float>(W) / static_cast<float>(w);
     // the per-image totals are accumulated with atomics: clear them first (2 KB per image)
     DCL_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * kBins * B, as_stream(stream)));
-    k_classify<<<dim3(n_chunks, B), 256, 0, as_stream(stream)>>>(labels, predict, H, W, h, w, C_cls, sh, sw, code,
-                                                                 chunk_hist, counts, n_chunks);
+    // pixels per thread: 4 by default (DCL_CLASSIFY_PX=8 selects the 256-thread variant, diagnostics)
+    static const int px = [] { const char* e = std::getenv("DCL_CLASSIFY_PX"); return (e && std::atoi(e) == 8) ? 8 : 4; }();
+    if (px == 8)
+        k_classify<8><<<dim3(n_chunks, B), kChunk / 8, 0, as_stream(stream)>>>(labels, predict, H, W, h, w, C_cls, sh, sw, code,
+                                                                               chunk_hist, counts, n_chunks);
+    else
+        k_classify<4><<<dim3(n_chunks, B), kChunk / 4, 0, as_stream(stream)>>>(labels, predict, H, W, h, w, C_cls, sh, sw, code,
+                                                                               chunk_hist, counts, n_chunks);
     DCL_LAUNCH_CHECK("k_classify");
     return 0;
 }

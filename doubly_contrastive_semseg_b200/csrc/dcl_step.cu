@@ -306,9 +306,11 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
     }
     const int nI = n_pad / DCL_TILE_ROWS, nJ = nI * world, rb0 = nI * rank;
     if (s->ev_fwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_begin), st));
-    if (int e = dcl_contrast_fwd(tiles_all, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
-                                 s->base_temperature, s->workspace, s->workspace_bytes, s->colA, s->colB, s->rowloss,
-                                 s->loss_sum, stream))
+    // one GPU: the forward's last block writes the loss where the caller wants it and the backward is chained onto
+    // the forward (no copy and no stream drain between the two)
+    if (int e = contrast_fwd_ex(tiles_all, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
+                                s->base_temperature, s->workspace, s->workspace_bytes, s->colA, s->colB, s->rowloss,
+                                s->loss_sum, world == 1 ? s->loss : nullptr, stream))
         return e;
     if (s->ev_fwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_end), st));
     g_step_ns[5] = now_ns() - t0;                            // + select, gather, forward issued
@@ -326,13 +328,12 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
             if (int e = comm_all_gather(s->comm, s->xchg_send, s->xchg_recv, msg, st)) return e;
             if (int e = dcl_shard_unpack(s->xchg_recv, world, n_pad, s->colA, s->colB, n_global, s->loss, stream)) return e;
         }
-    } else {
-        DCL_CUDA(cudaMemcpyAsync(s->loss, s->loss_sum + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     if (s->dF) {
         if (s->ev_bwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_begin), st));
-        if (int e = dcl_contrast_bwd(tiles_all, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
-                                     s->workspace_bytes, s->dF, stream))
+        const bool chained = world == 1 && !s->ev_fwd_end && !s->ev_bwd_begin;      // nothing was recorded in between
+        if (int e = contrast_bwd_ex(tiles_all, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
+                                    s->workspace_bytes, s->dF, chained, stream))
             return e;
         if (s->ev_bwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_end), st));
     }

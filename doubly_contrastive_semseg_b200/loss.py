@@ -247,14 +247,14 @@ def layout_rows(plan: AnchorPlan, anchors: np.ndarray, image_offset: int, n_pad:
 # thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------
 def classify(labels: torch.Tensor, predict: torch.Tensor, h: int, w: int):
-    """-> code [B,hw] u16 (as int16 storage), chunk_hist [B,n_chunks,512] i32, counts [B,512] i32"""
+    """-> code [B,hw] u16 (as int16 storage), chunk_hist [B,512,n_chunks] i32, counts [B,512] i32"""
     B, H, W = labels.shape
     C = predict.shape[1]
     hw = h * w
     n_chunks = (hw + _CHUNK - 1) // _CHUNK
     dev = labels.device
     code = torch.empty((B, hw), dtype=torch.int16, device=dev)
-    chunk = torch.empty((B, n_chunks, _BINS), dtype=torch.int32, device=dev)
+    chunk = torch.empty((B, _BINS, n_chunks), dtype=torch.int32, device=dev)
     counts = torch.empty((B, _BINS), dtype=torch.int32, device=dev)
     _lib.call("dcl_sample_classify", _p(labels), _p(predict), B, H, W, h, w, C, _p(code), _p(chunk),
               _p(counts), _stream())

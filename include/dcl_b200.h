@@ -75,7 +75,7 @@ int dcl_contrast_launches(int mode, int backward);
  *   labels   [B,H,W] int64      predict [B,C_cls,h,w] f32
  *   code     [B,h*w] u16 out :  low byte = down-sampled label (0..255), bit 8 = easy
  *                               (label == argmax), 0xFFFF = label outside 0..255
- *   chunk_hist [B,n_chunks,512] i32 out : per (image, chunk, bin = label*2+easy) pixel counts
+ *   chunk_hist [B,512,n_chunks] i32 out : per (image, bin = label*2+easy, chunk) pixel counts
  *   counts   [B,512] i32 out  : per-image totals per bin  (hard = bin label*2, easy = +1)
  *   n_chunks = ceil(h*w / DCL_CHUNK_PIXELS)
  */

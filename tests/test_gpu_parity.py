@@ -710,3 +710,82 @@ def test_boundary_focal_error_contract(dcl):
     from doubly_contrastive_semseg_b200 import _lib
     with pytest.raises(_lib.DclError):
         crit(x.cpu(), t, {"label_distance_weight": torch.ones(1, 8, 8)})
+
+
+# ------------------------------------------------------------------ full training step (BASELINE config 5)
+def _train_sample(B, H, W, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    left = torch.rand(2 * B, 3, H, W, generator=g) * 255.0
+    coarse = torch.randint(0, K, (B, H // 32, W // 32), generator=g)
+    label = coarse.repeat_interleave(32, 1).repeat_interleave(32, 2).clone()
+    label[torch.rand(B, H, W, generator=g) < 0.04] = 255
+    alpha = torch.rand(B, H, W, generator=g) * 2.0
+    alpha[torch.rand(B, H, W, generator=g) < 0.3] = 0.0
+    return {"left": left, "label": label.long(), "weather": torch.arange(B) % 2, "label_distance_weight": alpha}
+
+
+@pytest.mark.gpu
+def test_train_step_vs_ports(dcl):
+    """One optimisation step of `TrainStep` (trainer.py:60-215, criterion supcon_pixelcontrast_focal) in fp32 against
+    the same network driven by the CPU ports of the three losses and a plain torch Adam: the three losses, the
+    parameter gradients and the updated weights."""
+    import copy
+    from doubly_contrastive_semseg_b200.swiftnet import fill_deterministic
+    B, H, W, K = 2, 128, 256, 5
+    opts = types.SimpleNamespace(amp=False, batch_size=B, lr=4e-4, weight_decay=1e-4, deeplab=False)
+    torch.manual_seed(3)
+    step = dcl.TrainStep(opts, device="cuda", class_weights=0.5 + torch.rand(19))
+    fill_deterministic(step.net, 11)
+    step.pixelcontrast_criterion.max_samples, step.pixelcontrast_criterion.max_views = 1024, 8
+    ref_net = copy.deepcopy(step.net)
+    ref_net.upsample_logits = True
+    groups = [{"params": list(ref_net.random_init_params()), "lr": 4e-4, "weight_decay": 1e-4},
+              {"params": list(ref_net.fine_tune_params()), "lr": 1e-4, "weight_decay": 2.5e-5}]
+    ref_opt = torch.optim.Adam(groups, betas=(0.9, 0.99))
+    sample = _train_sample(B, H, W, K, seed=21)
+    # ---- ours
+    torch.manual_seed(9)
+    out = step({k: v.clone() for k, v in sample.items()})
+    # ---- the same step with the ports (losses on the CPU, network on the GPU)
+    sup_o = O.SupConPort(opts=opts)
+    sup_o.projection.load_state_dict({k: v.detach().cpu() for k, v in step.supcon_criterion.projection.state_dict().items()})
+    pix_o = O.PixelContrastPort()
+    pix_o.max_samples, pix_o.max_views = 1024, 8
+    foc_o = O.BoundaryFocalPort(gamma=0.5, num_classes=19, ignore_id=255, weight=step.criterion.weight.detach().cpu(),
+                                device="cpu", opts=step.opts)
+    ref_net.train()
+    seg, before, fine, fine0 = ref_net(sample["left"].cuda(), return_supcon_feature=True)
+    labels = sample["label"].clone()
+    torch.manual_seed(9)
+    l_sup = sup_o(fine.cpu(), class_labels=sample["weather"])
+    l_pix = pix_o(fine0.cpu(), labels=labels, predict=before.cpu())
+    l_seg = foc_o(seg.cpu(), labels, {"label_distance_weight": sample["label_distance_weight"]})
+    total = (l_sup + l_pix) * (1.0 / B) + l_seg * 1.2
+    ref_opt.zero_grad()
+    total.backward()
+    ref_opt.step()
+    assert abs(out["supcon_loss"].item() - l_sup.item()) <= LOSS_RTOL * abs(l_sup.item())
+    assert abs(out["pixelcontrast_loss"].item() - l_pix.item()) <= LOSS_RTOL * abs(l_pix.item())
+    assert abs(out["seg_loss"].item() - l_seg.item()) <= LOSS_RTOL * abs(l_seg.item())
+    assert abs(out["total_loss"].item() - total.item()) <= LOSS_RTOL * abs(total.item())
+    worst = 0.0
+    for (name, p), q in zip(step.net.named_parameters(), ref_net.parameters()):
+        assert p.grad is not None and q.grad is not None, name
+        worst = max(worst, float((p.grad - q.grad).abs().max() / q.grad.abs().max().clamp_min(1e-20)))
+    assert worst <= GRAD_RTOL, worst
+    # Adam's first step moves a weight by lr * g / (|g| + eps): identical wherever the gradient is not tiny, at most
+    # 2 lr apart anywhere (a sign flip of a near-zero gradient); the segmentation head is not optimised
+    moved = 0
+    with torch.no_grad():
+        for (name, p), q in zip(step.net.named_parameters(), ref_net.parameters()):
+            if name.startswith("segmentation."):
+                assert torch.equal(p, q), name
+                continue
+            moved += 1
+            lr = 4e-4 if "upsample_" in name else 1e-4
+            d = (p - q).abs()
+            assert float(d.max()) <= 2.05 * lr, name
+            big = q.grad.abs() > 1e-2 * q.grad.abs().max()
+            assert float(d[big].max()) <= 0.05 * lr, name
+    assert moved == 83
+    assert step.num_iter == 1
