@@ -252,11 +252,19 @@ class Timer:
         # they queue on NVML's lock) then land in the barrier, not in the first timed step
         if Timer.clocks is not None:
             Timer.clocks.start()
+        # like timeit: no cyclic garbage collection inside the timed region (a generation-2 pass is a millisecond,
+        # several sub-millisecond steps); collected right before instead
+        import gc
+        gc_was = gc.isenabled()
+        gc.collect()
+        gc.disable()
         time.sleep(0.005)
         self.barrier()
         try:
             return self._run(step, steps, first_seed, marks)
         finally:
+            if gc_was:
+                gc.enable()
             if Timer.clocks is not None:
                 Timer.clocks.stop()
 
@@ -318,9 +326,9 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
         del ref, xf, full, loss_ref
         torch.cuda.empty_cache()
 
-    sim_events = []
-    if not os.environ.get("DCL_BENCH_NO_HOOK"):            # experiments only: the similarity events are the roofline's clock
-        L.set_profile_hook(lambda name, a, b: sim_events.append((name, a, b)))
+    # the roofline's clock: events around the contrast forward / backward of every timed step, recorded by the library on
+    # the step's stream (DCL_BENCH_NO_HOOK: experiments without them)
+    sim_on = not os.environ.get("DCL_BENCH_NO_HOOK")
     # Identical CPU generator state on every rank, set ONCE: every rank consumes the same stream (each replays the
     # global plan), so the states stay identical, and an untouched generator lets the library keep its look-ahead
     # of the mt19937 stream (host thread + device mirror) running off the step's critical path.
@@ -350,13 +358,16 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
         step(s)
     barrier()
     host_log.clear()
-    sim_events.clear()
     L.reset_launch_count()
+    if sim_on:
+        L.set_sim_timing(True)
     total, per = Timer(barrier).run(step, args.steps)
     launches = L.launch_count()
     n_global = crit.last_n_global
     n_local = crit.last_layout.n
-    sim_ms = sum(a.elapsed_time(b) for _, a, b in sim_events)
+    sim_fwd, sim_bwd, sim_steps = L.sim_times() if sim_on else (0.0, 0.0, 0)
+    L.set_sim_timing(False)
+    sim_ms = sim_fwd + sim_bwd
     t = torch.tensor([total, float(np.median(per))], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,8 +385,7 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
         print("  look-ahead waits: total %.3f ms, longest %.3f ms" % (w[0] / 1e6, w[1] / 1e6), file=sys.stderr, flush=True)
     out.update(value=n_global * args.steps / (total * 1e-3), ms_per_step=total / args.steps, ms_per_step_median=med,
                anchors=n_global, anchors_per_gpu=n_local, gpu_launches=launches, sim_ms_per_step=sim_ms / args.steps,
-               timed_calls=len(sim_events), embed_mb=feats.numel() * 4 / 1e6)
-    L.set_profile_hook(None)
+               timed_calls=2 * sim_steps, embed_mb=feats.numel() * 4 / 1e6)
 
     # ---- end to end: pinned host inputs, H2D inside the timed region, loss read back
     if with_e2e:
@@ -573,6 +583,8 @@ def config_of(wl, m, world):
             "anchors": m["anchors"], "anchors_per_gpu": m.get("anchors_per_gpu", m["anchors"]),
             "sampler_rng": "exact (torch CPU mt19937; look-ahead stream mirrored on the GPU, permutations replayed there)",
             "l2": "inputs (%.0f MB embeddings per GPU) exceed the 126 MB L2; no explicit flush" % m["embed_mb"],
+            "timed_region": "CUDA events on the step's stream, barrier + synchronize on both sides, Python's cyclic GC "
+                            "off inside it (timeit convention)",
             "parallelism": "rows sharded x%d, contrast set NCCL all-gathered" % world if world > 1 else "single GPU"}
 
 

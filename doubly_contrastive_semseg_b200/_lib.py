@@ -50,6 +50,8 @@ SIGNATURES = {
     "dcl_step_begin": (_i, [_vp, _vp]),
     "dcl_step_fwd": (_i, [_vp, _vp]),
     "dcl_step_timing": (_i, [_vp]),
+    "dcl_step_sim_timing": (_i, [_i]),
+    "dcl_step_sim_elapsed": (_i, [_vp, _vp, _vp]),
     "dcl_step_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "dcl_focal_workspace_bytes": (_sz, [_i, _i, _i]),
     "dcl_focal_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -154,37 +154,6 @@ __device__ __forceinline__ float rcpf(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// packed fp32 pairs (FFMA2 / FADD2): one issue slot for two lanes of work
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ float sum2(f32x2 v) {
-    float lo, hi;
-    unpack2(v, lo, hi);
-    return lo + hi;
-}
-
 // tcgen05.wait::ld with the destination registers threaded through as in/out operands, so the
 // compiler cannot schedule a use of the asynchronously written registers above the wait.
 __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
@@ -1495,6 +1464,48 @@ __device__ __forceinline__ void bwd_chunk_masked(const uint32_t (&v)[32], const 
     }
 }
 
+// dF_I = sum of a row block's segment partials in segment order (the last CTA of the block to arrive; eight epilogue
+// warps).  kNs > 0: all segments of eight rows per warp are in flight at once; kNs == 0: any count, one segment at a time.
+template <int kNs>
+__device__ __forceinline__ void reduce_segments(const float* __restrict__ part, float* __restrict__ dst, int ns, int warp,
+                                                int lane) {
+#pragma unroll 1
+    for (int r0 = warp; r0 < 128; r0 += 64) {
+        float4 acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kNs > 0) {
+            float4 v[kNs > 0 ? kNs : 1][8];
+#pragma unroll
+            for (int sg = 0; sg < kNs; ++sg)
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[sg][u] = __ldcg(reinterpret_cast<const float4*>(part + (static_cast<size_t>(sg) * 128 + r0 + 8 * u) * 128 + lane * 4));
+#pragma unroll
+            for (int sg = 0; sg < kNs; ++sg)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc[u].x += v[sg][u].x; acc[u].y += v[sg][u].y; acc[u].z += v[sg][u].z; acc[u].w += v[sg][u].w;
+                }
+        } else {
+#pragma unroll 1
+            for (int sg = 0; sg < ns; ++sg) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = __ldcg(reinterpret_cast<const float4*>(part + (static_cast<size_t>(sg) * 128 + r0 + 8 * u) * 128 + lane * 4));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(dst + (static_cast<size_t>(r0) + 8 * u) * 128 + lane * 4) = acc[u];
+    }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -1874,29 +1885,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_backward(const Params p) {
                     if (*sTicket == static_cast<unsigned int>(ns - 1)) {
                         __threadfence();
                         const float* part = p.pD + static_cast<size_t>(I) * p.maxsegD * 128 * 128;
-                        // warp w: rows w, w+8, ..; a warp reads 512 contiguous bytes per (row, segment); eight rows
-                        // in flight per batch so the L2 round trips overlap
-#pragma unroll 1
-                        for (int r0 = warp; r0 < 128; r0 += 64) {
-                            float4 acc[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                            for (int sg = 0; sg < ns; ++sg) {
-                                float4 v[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u)
-                                    v[u] = __ldcg(reinterpret_cast<const float4*>(
-                                        part + (static_cast<size_t>(sg) * 128 + r0 + 8 * u) * 128 + lane * 4));
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                *reinterpret_cast<float4*>(p.dF + (static_cast<size_t>(I) * 128 + r0 + 8 * u) * 128 + lane * 4) = acc[u];
-                        }
+                        // warp w: rows w, w+8, ..; a warp reads 512 contiguous bytes per (row, segment).  Two or three
+                        // segments (the usual case: a row block shared by 2-3 CTAs) are loaded in one batch so that the
+                        // L2 round trips of all segments overlap; the sums keep the segment order either way.
+                        float* dst = p.dF + static_cast<size_t>(I) * 128 * 128;
+                        if (ns == 2) reduce_segments<2>(part, dst, ns, warp, lane);
+                        else if (ns == 3) reduce_segments<3>(part, dst, ns, warp, lane);
+                        else reduce_segments<0>(part, dst, ns, warp, lane);
                     }
                 }
             }

@@ -23,6 +23,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include "dcl_common.cuh"
+#include "dcl_ptx.cuh"
 
 namespace dcl {
 
@@ -74,26 +75,7 @@ constexpr int kFocalCols = 31;      // owned columns per warp (lane 0 is the han
 constexpr int kFocalRun = 4;        // label pixels of a run whose loads are issued together
 constexpr int kFocalStage = 33;     // staged low-resolution columns per warp: the 32 lanes' own and one to the right
 
-// packed fp32 pairs (FFMA2 / FADD2): the kernel is bound by issue slots, two classes share one
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
+// (packed fp32 pairs, FFMA2 / FADD2, from dcl_ptx.cuh: the kernel is bound by issue slots, two classes share one)
 // z - (a == b ? s : 0) as a compare and a predicated subtract (the compiler turns the plain form, unrolled over the
 // classes, into a jump table on the pixel's label: one divergent branch per pixel)
 __device__ __forceinline__ float sub_if_eq(float z, float s, int a, int b) {

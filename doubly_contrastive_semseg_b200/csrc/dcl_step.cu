@@ -44,7 +44,12 @@ struct PerDevice {
     cudaEvent_t ev_up = nullptr, ev_need = nullptr, ev_used = nullptr;
     bool used_recorded = false;
     uint64_t last_window = 0;
+    // dcl_step_sim_timing: the library's own events around the contrast forward / backward of every step
+    cudaEvent_t* sim_ev = nullptr;        // [kSimRing][4]
+    long long sim_steps = 0;
+    bool sim_on = false;
 };
+constexpr int kSimRing = 2048;
 PerDevice g_dev[kMaxDevices];
 std::mutex g_mu;
 // diagnostics: host nanoseconds of the last dcl_step_fwd at the end of each of its sections (dcl_step_timing)
@@ -305,14 +310,26 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
         if (int e = comm_all_gather(s->comm, tl, s->tiles, tile_bytes, st)) return e;
     }
     const int nI = n_pad / DCL_TILE_ROWS, nJ = nI * world, rb0 = nI * rank;
-    if (s->ev_fwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_begin), st));
+    // similarity timing: the caller's events, else (dcl_step_sim_timing) the next slot of the library's ring
+    cudaEvent_t ev_sim[4] = {static_cast<cudaEvent_t>(s->ev_fwd_begin), static_cast<cudaEvent_t>(s->ev_fwd_end),
+                             static_cast<cudaEvent_t>(s->ev_bwd_begin), static_cast<cudaEvent_t>(s->ev_bwd_end)};
+    if (pd->sim_on && !ev_sim[0] && !ev_sim[1] && !ev_sim[2] && !ev_sim[3]) {
+        cudaEvent_t* slot = pd->sim_ev + 4 * (pd->sim_steps % kSimRing);
+        for (int i = 0; i < 4; ++i) ev_sim[i] = slot[i];
+        ++pd->sim_steps;
+        if (!s->dF) {                                        // no backward in this step: an empty interval
+            DCL_CUDA(cudaEventRecord(ev_sim[2], st));
+            DCL_CUDA(cudaEventRecord(ev_sim[3], st));
+        }
+    }
+    if (ev_sim[0]) DCL_CUDA(cudaEventRecord(ev_sim[0], st));
     // one GPU: the forward's last block writes the loss where the caller wants it and the backward is chained onto
     // the forward (no copy and no stream drain between the two)
     if (int e = contrast_fwd_ex(tiles_all, s->y_dev, s->sqnorm, nJ, rb0, nI, n_global, DCL_MODE_PIXEL, s->temperature,
                                 s->base_temperature, s->workspace, s->workspace_bytes, s->colA, s->colB, s->rowloss,
                                 s->loss_sum, world == 1 ? s->loss : nullptr, stream))
         return e;
-    if (s->ev_fwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_fwd_end), st));
+    if (ev_sim[1]) DCL_CUDA(cudaEventRecord(ev_sim[1], st));
     g_step_ns[5] = now_ns() - t0;                            // + select, gather, forward issued
     if (world > 1) {
         // every rank's row constants (32 B per row: the dS_ki terms of the backward) and loss partial, one message
@@ -330,18 +347,61 @@ extern "C" int dcl_step_fwd(const dcl_step_t* s, void* stream) {
         }
     }
     if (s->dF) {
-        if (s->ev_bwd_begin) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_begin), st));
-        const bool chained = world == 1 && !s->ev_fwd_end && !s->ev_bwd_begin;      // nothing was recorded in between
+        if (ev_sim[2]) DCL_CUDA(cudaEventRecord(ev_sim[2], st));
+        // one GPU: the backward's first kernel is a programmatic dependent of the forward's last one (with an event
+        // recorded in between the launch simply orders normally)
+        const bool chained = world == 1;
         if (int e = contrast_bwd_ex(tiles_all, s->y_dev, s->colA, s->colB, nJ, rb0, nI, DCL_MODE_PIXEL, s->workspace,
                                     s->workspace_bytes, s->dF, chained, stream))
             return e;
-        if (s->ev_bwd_end) DCL_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->ev_bwd_end), st));
+        if (ev_sim[3]) DCL_CUDA(cudaEventRecord(ev_sim[3], st));
     }
     if (s->zero_fill && s->zero_fill_bytes && s->side_stream)
         DCL_CUDA(cudaStreamWaitEvent(st, pd->ev_zero, 0));   // the cleared buffer is ordered before anything later on st
     if (dp.taken)
         if (int e = mirror_prefetch(*pd, dp)) return e;
     g_step_ns[6] = now_ns() - t0;                            // + exchange, backward, generator prefetch issued
+    return 0;
+}
+
+// Measurement aid (bench.py): with timing enabled every dcl_step_fwd on the current device records events of the
+// library's own around its contrast forward and backward (a ring of kSimRing steps; creating and recording events
+// from Python costs the host more than a small step can hide).  Enabling resets the ring.
+extern "C" int dcl_step_sim_timing(int enable) {
+    if (int e = dcl_check_device()) return e;
+    std::lock_guard<std::mutex> lock(g_mu);
+    PerDevice* pd = nullptr;
+    if (int e = device_slot(pd)) return e;
+    if (enable && !pd->sim_ev) {
+        pd->sim_ev = new cudaEvent_t[4 * kSimRing];
+        for (int i = 0; i < 4 * kSimRing; ++i) DCL_CUDA(cudaEventCreate(&pd->sim_ev[i]));
+    }
+    const int old = pd->sim_on ? 1 : 0;
+    pd->sim_on = enable != 0;
+    if (enable) pd->sim_steps = 0;
+    return old;
+}
+
+// Sums of the recorded intervals in milliseconds over the last min(steps, kSimRing) steps since timing was enabled;
+// the stream must have been synchronized.  *steps = how many steps the sums cover.
+extern "C" int dcl_step_sim_elapsed(double* fwd_ms, double* bwd_ms, long long* steps) {
+    if (!fwd_ms || !bwd_ms || !steps) return fail(DCL_ERR_ARG, "null pointer argument");
+    std::lock_guard<std::mutex> lock(g_mu);
+    PerDevice* pd = nullptr;
+    if (int e = device_slot(pd)) return e;
+    *fwd_ms = *bwd_ms = 0.0;
+    *steps = 0;
+    if (!pd->sim_ev) return 0;
+    const long long n = pd->sim_steps < kSimRing ? pd->sim_steps : kSimRing;
+    for (long long i = 0; i < n; ++i) {
+        const cudaEvent_t* slot = pd->sim_ev + 4 * ((pd->sim_steps - 1 - i) % kSimRing);
+        float a = 0.f, b = 0.f;
+        DCL_CUDA(cudaEventElapsedTime(&a, slot[0], slot[1]));
+        DCL_CUDA(cudaEventElapsedTime(&b, slot[2], slot[3]));
+        *fwd_ms += a;
+        *bwd_ms += b;
+    }
+    *steps = n;
     return 0;
 }
 

@@ -58,6 +58,21 @@ def set_profile_hook(fn):
     _PROFILE_HOOK = fn
 
 
+def set_sim_timing(on: bool) -> None:
+    """Measurement aid: have dcl_step_fwd bracket its contrast forward / backward with events owned by the library
+    (current device; cheaper than `set_profile_hook`, which creates and records four events per step from Python)."""
+    rc = _lib.load().dcl_step_sim_timing(1 if on else 0)
+    if rc < 0:
+        raise _lib.DclError("dcl_step_sim_timing failed: %s" % _lib.load().dcl_last_error().decode("utf-8", "replace"))
+
+
+def sim_times():
+    """-> (forward ms, backward ms, steps) summed over the steps recorded since `set_sim_timing(True)`; synchronize first."""
+    f, b, n = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_longlong(0)
+    _lib.call("dcl_step_sim_elapsed", ctypes.byref(f), ctypes.byref(b), ctypes.byref(n))
+    return f.value, b.value, int(n.value)
+
+
 def _count(n):
     global _LAUNCHES
     _LAUNCHES += n

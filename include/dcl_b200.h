@@ -320,6 +320,14 @@ int dcl_step_bwd(const float* dF, const int32_t* pix, const int32_t* rowof, int 
  * for upload, + plan kernel (or row copies) issued, + select / gather / forward issued, + exchange / backward issued, -. */
 int dcl_step_timing(long long* out);
 
+/* Measurement aid (bench.py): similarity-kernel time of the steps.  With timing enabled, every dcl_step_fwd on the
+ * current device whose descriptor carries no events of its own brackets its contrast forward and backward with events
+ * owned by the library (a ring of 2048 steps).  dcl_step_sim_timing returns the previous setting and resets the ring
+ * when enabling; dcl_step_sim_elapsed sums the recorded intervals (milliseconds) of the last min(steps, 2048) steps -
+ * synchronize the stream first. */
+int dcl_step_sim_timing(int enable);
+int dcl_step_sim_elapsed(double* fwd_ms, double* bwd_ms, long long* steps);
+
 /* Measurement aid (bench.py): a native thread samples the CURRENT device's SM clock, throttle reasons and power through
  * NVML every period_us microseconds while a timed region runs (`nvidia-smi -lms` itself slows a sub-millisecond step).
  * dcl_clock_sampler_stop: out[5] = samples, median SM MHz, max SM MHz, OR of NVML throttle-reason masks (0x4 sw power
