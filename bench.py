@@ -246,7 +246,7 @@ class Timer:
     def __init__(self, barrier):
         self.barrier = barrier
 
-    def run(self, step, steps, first_seed=100):
+    def run(self, step, steps, first_seed=100, before_timed=None):
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         # the sampler thread starts BEFORE the barrier: its first NVML queries (the slow ones, and with several ranks
         # they queue on NVML's lock) then land in the barrier, not in the first timed step
@@ -258,7 +258,12 @@ class Timer:
         gc_was = gc.isenabled()
         gc.collect()
         gc.disable()
-        time.sleep(0.005)
+        # two more untimed steps instead of a sleep: the sampler's first NVML queries land here and in the barrier, and the
+        # host thread enters the timed region warm (a 5 ms sleep made the first timed step 2-3x slower on the host side)
+        for s in range(2):
+            step(first_seed - 2 + s)
+        if before_timed is not None:
+            before_timed()
         self.barrier()
         try:
             return self._run(step, steps, first_seed, marks)
@@ -357,11 +362,14 @@ def measure_pixel(pkg, L, wl, world, rank, dev, args, barrier, dist, with_e2e=Tr
     for s in range(args.warmup):
         step(s)
     barrier()
-    host_log.clear()
-    L.reset_launch_count()
-    if sim_on:
-        L.set_sim_timing(True)
-    total, per = Timer(barrier).run(step, args.steps)
+
+    def before_timed():
+        host_log.clear()
+        L.reset_launch_count()
+        if sim_on:
+            L.set_sim_timing(True)
+
+    total, per = Timer(barrier).run(step, args.steps, before_timed=before_timed)
     launches = L.launch_count()
     n_global = crit.last_n_global
     n_local = crit.last_layout.n
@@ -440,8 +448,7 @@ def measure_doubly(pkg, L, wl, dev, args, barrier):
     for s in range(args.warmup):
         step(s)
     barrier()
-    L.reset_launch_count()
-    total, per = Timer(barrier).run(step, args.steps)
+    total, per = Timer(barrier).run(step, args.steps, before_timed=L.reset_launch_count)
     launches = L.launch_count()
     n_pix = crit.pixel.last_layout.n
     rows = n_pix + 2 * wl.B
