@@ -681,7 +681,7 @@ def run_ours(args):
             # BASELINE.json configs[4] on ONE of its eight GPUs: the full SwiftNet-RN18 training step (network in
             # cuDNN under bf16 autocast, the three losses of this repository, fused Adam), 8 images x 2 crops per GPU
             from tools import train_bench
-            t5 = train_bench.run(train_bench.parse(["--steps", str(min(args.steps, 10)), "--warmup", "3"]), init_dist=False)
+            t5 = train_bench.run(train_bench.parse(["--steps", str(min(args.steps, 10)), "--warmup", "5"]), init_dist=False)
             line.setdefault("workloads", {})["cfg5"] = {
                 "value": t5["value"], "unit": t5["unit"], "ms_per_step": t5["ms_per_step"], "config": t5["config"],
                 "losses": t5["losses"], "peak_mem_gb": t5["peak_mem_gb"],
