@@ -142,9 +142,9 @@ class WeatherNet(nn.Module):
             fine_feat0 = fine_feat[: fine_feat.shape[0] // 2] if return_supcon_feature else fine_feat
             before_up = self.segmentation(fine_feat0)
         # the losses work in fp32 on contiguous NCHW tensors
-        fine_feat = fine_feat.float().contiguous()
+        fine_feat = fine_feat.to(dtype=torch.float32, memory_format=torch.contiguous_format)      # one pass (bf16 NHWC -> f32 NCHW)
         fine_feat0 = fine_feat[: fine_feat.shape[0] // 2] if return_supcon_feature else fine_feat
-        before_up = before_up.float().contiguous()
+        before_up = before_up.to(dtype=torch.float32, memory_format=torch.contiguous_format)
         seg = None
         if self.upsample_logits:
             seg = F.interpolate(before_up, left_img.shape[2:], mode="bilinear", align_corners=False)

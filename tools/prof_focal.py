@@ -29,4 +29,21 @@ for i in range(reps):
     if i == reps - 1:
         ev[1].record()
 torch.cuda.synchronize()
-print("focal loss", float(loss), "last fwd+bwd %.1f us" % (ev[0].elapsed_time(ev[1]) * 1e3))
+print("focal loss", float(loss.detach()), "last fwd+bwd %.1f us" % (ev[0].elapsed_time(ev[1]) * 1e3))
+if len(sys.argv) > 2 and sys.argv[2] == "torch":
+    # the same loss as plain PyTorch on the GPU (the oracle's restatement of loss.py:27-80: up-sampled logits, log-softmax,
+    # gather, weights), for scale only
+    from oracle import dcl_oracle as O
+    port = O.BoundaryFocalPort(gamma=0.5, num_classes=C, ignore_id=255, weight=torch.ones(C, device="cuda"), device="cuda", opts=opts)
+    xr = logits.detach().clone().requires_grad_(True)
+    for i in range(3):
+        xr.grad = None
+        if i == 2:
+            torch.cuda.synchronize()
+            ev[0].record()
+        lr_ = port(xr, target.clone(), {"label_distance_weight": alpha})
+        lr_.backward()
+    ev[1].record()
+    torch.cuda.synchronize()
+    print("plain torch on the GPU: loss", float(lr_.detach()), "fwd+bwd %.1f us, peak memory %.2f GB"
+          % (ev[0].elapsed_time(ev[1]) * 1e3, torch.cuda.max_memory_allocated() / 2 ** 30))

@@ -27,6 +27,10 @@ def parse(argv=None):
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--no-amp", action="store_true")
+    ap.add_argument("--max-samples", type=int, default=0,
+                    help="PixelContrastLoss.max_samples; 0 = max(1024, 128 x global batch): the reference's 1024 gives "
+                         "n_view = 0 (and the reference crashes, loss.py:345) once the global batch holds more than 1024 "
+                         "(image, class) pairs, e.g. 64 images x 19 classes")
     ap.add_argument("--no-cudnn-benchmark", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="contiguous NCHW activations instead of channels_last")
     ap.add_argument("--profile", action="store_true", help="CUPTI kernel table of two steps after the timed ones (stderr)")
@@ -48,6 +52,7 @@ def run(a, init_dist=True):
     opts = types.SimpleNamespace(amp=not a.no_amp, batch_size=a.batch * world, channels_last=not a.nchw)
     step = pkg.TrainStep(opts, device=dev)
     fill_deterministic(step.net, 1)
+    step.pixelcontrast_criterion.max_samples = a.max_samples if a.max_samples > 0 else max(1024, 128 * a.batch * world)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     B, H, W = a.batch, a.height, a.width
     coarse = torch.randint(0, 19, (B, H // 64, W // 64), generator=g, device=dev)
@@ -93,7 +98,8 @@ def run(a, init_dist=True):
         res = ({"workload": "cfg5", "metric": "train_step_images_per_sec", "value": B * world / (float(t) * 1e-3),
                           "unit": "images/s", "n_gpus": world, "ms_per_step": float(t), "steps": a.steps, "warmup": a.warmup,
                           "config": {"model": "SwiftNet-RN18 pyramid (random init)", "images_per_gpu": B, "crops_per_image": 2,
-                                     "image_hw": [H, W], "embed_hw": [H // 4, W // 4], "criterion": step.opts.criterion,
+                                     "image_hw": [H, W], "embed_hw": [H // 4, W // 4], "criterion": step.opts.criterion, "max_samples": step.pixelcontrast_criterion.max_samples,
+                                     "max_views": step.pixelcontrast_criterion.max_views,
                                      "amp_bf16": not a.no_amp, "channels_last": not a.nchw, "cudnn_benchmark": not a.no_cudnn_benchmark, "optimizer": "Adam (fused), two lr groups"},
                           "losses": {k: float(v) for k, v in out.items()}, "weights_in_sync": sync,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
