@@ -221,3 +221,20 @@ def test_boundary_focal_port_zero_weight_returns_zero():
     loss = crit(x, torch.zeros(1, 8, 8, dtype=torch.long), {"label_distance_weight": torch.zeros(1, 8, 8)})
     assert loss.item() == 0.0
     loss.backward()
+
+
+def test_focal_kernel_decomposition_prototype():
+    """The work decomposition of k_focal (csrc/dcl_focal.cu) restated in numpy (tools/proto_focal.py): runs of label
+    columns by first tap, hand-over of the lx parts to the next column's owner, strips of low-resolution rows with a
+    spill row - against the fp64 closed form on two reference-generated fixtures, for strip heights that exercise
+    the spill path and the single-strip path."""
+    from tools import proto_focal as P
+    for name in ("focal_ragged", "focal_no_edt"):
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        mode, gamma = str(g["mode"]), float(g["gamma"])
+        ref_loss, ref_grad, _ = O.focal_closed_form(g["logits"], g["target"], g["alpha"], g["weight"], gamma, mode)
+        for strip in (2, g["logits"].shape[2]):
+            loss, grad, t = P.emulate(g["logits"], g["target"], g["alpha"], g["weight"], gamma, mode, strip)
+            assert abs(loss - ref_loss) <= 1e-12 * abs(ref_loss)
+            assert np.abs(grad - ref_grad).max() <= 1e-12 * np.abs(ref_grad).max()
+            assert np.array_equal(t, g["target_after"].astype(np.int64))
