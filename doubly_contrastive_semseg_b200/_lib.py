@@ -40,6 +40,9 @@ SIGNATURES = {
     "dcl_zero_fill": (_i, [_vp, _sz, _i, _vp]),
     "dcl_contrast_small_max_rows": (_i, []),
     "dcl_contrast_small": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dcl_supcon_mlp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "dcl_supcon_mlp_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dcl_group_ids": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "dcl_dense_grad": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "dcl_unpack_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
     "dcl_gap_fwd": (_i, [_vp, _i, _i, _vp, _vp]),

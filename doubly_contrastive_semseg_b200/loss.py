@@ -335,6 +335,7 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 # ----------------------------------------------------------------------------------------------
 # the one-call step (dcl_step_fwd / dcl_step_bwd): cached sizes, persistent scratch, raw pointers
 # ----------------------------------------------------------------------------------------------
+_FUSED_HEAD = os.environ.get("DCL_FUSED_HEAD", "1") != "0"       # image-level head: fused kernels (0: torch MLP + glue)
 _DEBUG_PY_TIMES = [] if os.environ.get("DCL_DEBUG_PY_TIMES") else None      # diagnostics: host milliseconds of _run_step's parts
 _FUSED_STEP = os.environ.get("DCL_FUSED_STEP", "1") != "0"     # 0: the stage-by-stage Python path (same results)
 _DEVICE_PLAN = os.environ.get("DCL_DEVICE_PLAN", "1") != "0"   # 0: always replay the generator on the host (same results)
@@ -728,6 +729,43 @@ class _ContrastRowsFn(torch.autograd.Function):
         return dZ, None, None, None, None
 
 
+class _SupConHeadFn(torch.autograd.Function):
+    """Everything between the pooled rows and the image-level loss at its real size (2B <= 128 rows, 128 channels):
+    projection MLP, row-normalised contrast, and their gradients - one launch for the MLP, one for the contrast
+    (forward and dZ together), two for the MLP's backward (csrc/dcl_contrast_small.cu).  loss.py:120, :161-204."""
+
+    @staticmethod
+    def forward(ctx, pooled, W1, b1, W2, b2, yy, T, Tb):
+        n = pooled.shape[0]
+        dev = pooled.device
+        X = pooled.contiguous()
+        W1c, b1c, W2c, b2c = W1.contiguous(), b1.contiguous(), W2.contiguous(), b2.contiguous()
+        H = torch.empty((n, _DIM), dtype=torch.float32, device=dev)
+        Z = torch.empty((n, _DIM), dtype=torch.float32, device=dev)
+        dZ = torch.empty((n, _DIM), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        st = _stream()
+        _lib.call("dcl_supcon_mlp_fwd", _p(X), _p(W1c), _p(b1c), _p(W2c), _p(b2c), n, _p(H), _p(Z), st)
+        _lib.call("dcl_contrast_small", _p(Z), _p(yy), n, MODE_SUPCON, float(T), float(Tb), _p(loss), _p(dZ), st)
+        _count(2)
+        ctx.save_for_backward(X, W1c, W2c, H, dZ)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        X, W1, W2, H, dZ = ctx.saved_tensors
+        n = X.shape[0]
+        dev = X.device
+        g = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_contiguous()) else grad_out.to(torch.float32).contiguous()
+        buf = torch.empty((2 * n + 2 * _DIM + 2, _DIM), dtype=torch.float32, device=dev)     # dH | dX | dW1 | dW2 | db1 | db2
+        dH, dX, dW1, dW2 = buf[:n], buf[n:2 * n], buf[2 * n:2 * n + _DIM], buf[2 * n + _DIM:2 * n + 2 * _DIM]
+        db1, db2 = buf[2 * n + 2 * _DIM], buf[2 * n + 2 * _DIM + 1]
+        _lib.call("dcl_supcon_mlp_bwd", _p(X), _p(W1), _p(W2), _p(H), _p(dZ), _p(g), n, _p(dH), _p(dX), _p(dW1), _p(db1),
+                  _p(dW2), _p(db2), _stream())
+        _count(2)
+        return dX, dW1, db1, dW2, db2, None, None, None
+
+
 class _GapFn(torch.autograd.Function):
     """nn.AdaptiveAvgPool2d((1,1)) + flatten, loss.py:115-116."""
 
@@ -1088,6 +1126,9 @@ class SupConLoss(nn.Module):
             raise ValueError("features must hold two crops per image: the leading dimension must be even, got %d"
                              % pooled.shape[0])
         bsz = pooled.shape[0] // 2
+        fused = self._fused_head(pooled, class_labels, mask)
+        if fused is not None:
+            return fused
         z = torch.stack([pooled[:bsz], pooled[bsz:2 * bsz]], dim=1)          # loss.py:117-119
         z = self.projection(z)                                               # loss.py:120
         labels = class_labels
@@ -1115,6 +1156,43 @@ class SupConLoss(nn.Module):
         Z = torch.cat(torch.unbind(z, dim=1), dim=0)                         # loss.py:161
         yy = y.repeat(n_views)
         return _ContrastRowsFn.apply(Z, yy, MODE_SUPCON, self.temperature, self.base_temperature)
+
+
+    def _fused_head(self, pooled, class_labels, mask):
+        """The image-level head in four launches when it has its usual form: 128-channel pooled rows on the GPU, at
+        most 128 of them, the reference's projection (Linear 128-128, ReLU, Linear 128-128) in fp32, and labels that
+        are absent, int32 / int64, or given as a mask.  stack -> projection -> unbind -> cat (loss.py:117-120, :161) is
+        the projection applied to the rows in their order, and labels.repeat(2) is the group id of row i mod bsz.
+        Returns None when the torch path has to run (other shapes / dtypes; same results)."""
+        n, bsz = pooled.shape[0], pooled.shape[0] // 2
+        proj = self.projection
+        if (not pooled.is_cuda or pooled.dtype != torch.float32 or pooled.dim() != 2 or pooled.shape[1] != _DIM
+                or n > _SMALL_ROWS or not _FUSED_HEAD or len(proj) != 3 or self.contrast_mode != "all"):
+            return None
+        l1, l2 = proj[0], proj[2]
+        if not (isinstance(l1, nn.Linear) and isinstance(l2, nn.Linear) and isinstance(proj[1], nn.ReLU)
+                and l1.weight.shape == (_DIM, _DIM) and l2.weight.shape == (_DIM, _DIM) and l1.bias is not None
+                and l2.bias is not None and l1.weight.dtype == torch.float32 and l1.weight.device == pooled.device
+                and l2.weight.device == pooled.device):
+            return None
+        if class_labels is not None and mask is not None:
+            raise ValueError("Cannot define both `labels` and `mask`")
+        dev = pooled.device
+        if mask is not None:
+            yy = _mask_to_labels(_on_device(mask, dev, "mask"), bsz).to(torch.int32).repeat(2).contiguous()
+        else:
+            lab = None
+            if class_labels is not None:
+                lab = _on_device(class_labels.contiguous().view(-1, 1), dev, "class_labels")
+                if lab.shape[0] != bsz:
+                    raise ValueError("Num of labels does not match num of features")
+                if lab.dtype not in (torch.int32, torch.int64):
+                    return None                                      # float labels: compared by value on the torch path
+            yy = torch.empty(2 * bsz, dtype=torch.int32, device=dev)
+            _lib.call("dcl_group_ids", _p(lab) if lab is not None else None, lab.element_size() if lab is not None else 0,
+                      bsz, 2, _p(yy), _stream())
+            _count(1)
+        return _SupConHeadFn.apply(pooled, l1.weight, l1.bias, l2.weight, l2.bias, yy, self.temperature, self.base_temperature)
 
 
 class DoublyContrastiveLoss(nn.Module):

@@ -207,6 +207,22 @@ int dcl_contrast_small_max_rows(void);
 int dcl_contrast_small(const float* Z, const int32_t* y, int n, int mode, float temperature, float base_temperature,
                        float* loss, float* dZ, void* stream);
 
+/* The rest of the image-level head at that size, so that the term is four launches instead of ~45 torch ones:
+ * SupConLoss.projection (Linear 128->128, ReLU, Linear 128->128; reference loss.py:102-106, applied at :120) and the
+ * group ids of the label mask (loss.py:151-159: mask = eq(labels, labels^T), or the identity without labels).
+ *   X [n,128] f32 pooled rows; W1, W2 [128,128] f32 (nn.Linear weight, [out,in]); b1, b2 [128]
+ *   H [n,128] out = relu(X W1^T + b1);  Z [n,128] out = H W2^T + b2
+ *   backward: dZ [n,128] (unscaled, from dcl_contrast_small), grad_out [1] device scalar; dH [n,128] scratch;
+ *             dX [n,128], dW1, dW2 [128,128], db1, db2 [128] out (all scaled by *grad_out)
+ *   dcl_group_ids: labels [n] int32 / int64 (elem_bytes 4 / 8) or NULL; y [views*n] i32 out, y[v*n+i] = first k with
+ *             labels[k] == labels[i] (i itself without labels) */
+int dcl_supcon_mlp_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, int n,
+                       float* H, float* Z, void* stream);
+int dcl_supcon_mlp_bwd(const float* X, const float* W1, const float* W2, const float* H, const float* dZ,
+                       const float* grad_out, int n, float* dH, float* dX, float* dW1, float* db1, float* dW2,
+                       float* db2, void* stream);
+int dcl_group_ids(const void* labels, int elem_bytes, int n, int views, int32_t* y, void* stream);
+
 /* ---------------------------------------------------------------- gradient back to NCHW
  * Replaces autograd of the gather (index_put into a zero tensor per class):
  * row n's gradient * (*grad_out) is written at pixel pix[n] of dfeats [B,128,h*w] f32 (pix < 0 skipped).

@@ -789,3 +789,39 @@ def test_train_step_vs_ports(dcl):
             assert float(d[big].max()) <= 0.05 * lr, name
     assert moved == 83
     assert step.num_iter == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("labels_kind", ["int64", "int32", "none", "mask"])
+def test_supcon_fused_head_equals_torch_head(dcl, labels_kind):
+    """The image-level head as four launches (projection MLP forward / backward, group ids, fp32 contrast;
+    csrc/dcl_contrast_small.cu) against the same module with the torch MLP and glue: loss, d features, d projection."""
+    from doubly_contrastive_semseg_b200 import loss as L
+    B = 6
+    g = torch.Generator().manual_seed(40)
+    feats = torch.randn(2 * B, 128, 6, 10, generator=g)
+    weather = torch.tensor([0, 3, 1, 3, 0, 2])
+    opts = types.SimpleNamespace(deeplab=False)
+    torch.manual_seed(12)
+    crit = dcl.SupConLoss(device="cuda", opts=opts)
+    kw = {"int64": dict(class_labels=weather.cuda()), "int32": dict(class_labels=weather.int().cuda().view(-1, 1)),
+          "none": {}, "mask": dict(mask=(weather[:, None] == weather[None, :]).float().cuda())}[labels_kind]
+    res = []
+    for fused in (True, False):
+        L._FUSED_HEAD = fused
+        try:
+            for p in crit.projection.parameters():
+                p.grad = None
+            x = feats.cuda().requires_grad_(True)
+            n0 = L.launch_count()
+            loss = crit(x, **kw)
+            (3.0 * loss).backward()
+            res.append((loss.item(), x.grad.clone(), [p.grad.clone() for p in crit.projection.parameters()], L.launch_count() - n0))
+        finally:
+            L._FUSED_HEAD = True
+    (la, ga, pa, na), (lb, gb, pb, nb) = res
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    assert _relmax(ga.cpu(), gb.cpu()) <= 1e-4
+    for a, b in zip(pa, pb):
+        assert _relmax(a.cpu(), b.cpu()) <= 1e-4
+    assert na >= 5                                       # pool, (group ids), MLP, contrast, MLP backward x2, pool backward
