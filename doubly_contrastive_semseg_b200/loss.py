@@ -335,6 +335,7 @@ def contrast_backward(tiles, y, colA, colB, nJ, rb0, nI, mode):
 # ----------------------------------------------------------------------------------------------
 # the one-call step (dcl_step_fwd / dcl_step_bwd): cached sizes, persistent scratch, raw pointers
 # ----------------------------------------------------------------------------------------------
+_POOL_AFTER_CLASSIFY = os.environ.get("DCL_POOL_AFTER_CLASSIFY", "1") != "0"   # doubly step: pool issued behind the step's classify
 _FUSED_HEAD = os.environ.get("DCL_FUSED_HEAD", "1") != "0"       # image-level head: fused kernels (0: torch MLP + glue)
 _DEBUG_PY_TIMES = [] if os.environ.get("DCL_DEBUG_PY_TIMES") else None      # diagnostics: host milliseconds of _run_step's parts
 _FUSED_STEP = os.environ.get("DCL_FUSED_STEP", "1") != "0"     # 0: the stage-by-stage Python path (same results)
@@ -455,7 +456,7 @@ class _StepResult:
     __slots__ = ("loss", "keep", "p_pix", "p_dF", "p_rowof", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info")
 
 
-def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
+def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_begin=None):
     """Issue one pixel-term step on feats [B,128,h,w] (contiguous f32) through dcl_step_fwd.  `shard` is None or
     (world, rank, comm).  `zero_fill`: allocate and clear the dense gradient buffer next to the step."""
     B, C, h, w = feats.shape
@@ -511,7 +512,17 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill):
     lib = _lib.load()
     if _t is not None:
         _t.append(time.perf_counter())
-    rc = lib.dcl_step_fwd(ctypes.byref(step), _stream())
+    if after_begin is not None:
+        # split issue: classify + count-table copy first, the caller's launches behind them, then the rest of the step
+        rc0 = lib.dcl_step_begin(ctypes.byref(step), _stream())
+        if rc0 != 0:
+            raise _lib.DclError("dcl_step_begin failed with status %d: %s" % (rc0, lib.dcl_last_error().decode("utf-8", "replace")))
+        after_begin()
+        step.begun = 1
+    try:
+        rc = lib.dcl_step_fwd(ctypes.byref(step), _stream())
+    finally:
+        step.begun = 0
     if _t is not None:
         _t.append(time.perf_counter())
         _DEBUG_PY_TIMES.append([(b - a) * 1e3 for a, b in zip(_t[:-1], _t[1:])])      # buffers+dzero, carve, rng+struct, C call
@@ -656,9 +667,19 @@ class _DoublyFn(torch.autograd.Function):
         B2, C, h, w = feats2.shape
         B = labels.shape[0]
         pooled = torch.empty((B2, C), dtype=torch.float32, device=feats2.device)
-        _lib.call("dcl_gap_fwd", _p(feats2), B2 * C, h * w, _p(pooled), _stream())
-        _count(1)
-        res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False)
+
+        def pool():
+            _lib.call("dcl_gap_fwd", _p(feats2), B2 * C, h * w, _p(pooled), _stream())
+            _count(1)
+
+        # Order on the stream: classify + count-table copy of the pixel step, THEN the pool (HBM-bound, 0.3 ms at the
+        # cfg3 shapes), then the rest of the step - the host waits for the count table and plans while the pool runs,
+        # instead of the GPU idling through that round trip after a pool that was issued first.
+        if _POOL_AFTER_CLASSIFY:
+            res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False, after_begin=pool)
+        else:
+            pool()
+            res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False)
         ctx.res = res
         ctx.shape2 = (B2, C, h, w)
         out, res.loss = res.loss, None           # no reference cycle through the output (see _StepFn.forward)
