@@ -453,12 +453,17 @@ def _peer_arena(group, world, rank, B, cap):
 
 class _StepResult:
     """What one dcl_step_fwd left behind: the loss, and for the backward the sampled pixels and the eager dF."""
-    __slots__ = ("loss", "keep", "p_pix", "p_dF", "p_rowof", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info")
+    __slots__ = ("loss", "keep", "p_pix", "p_dF", "p_rowof", "n_pad", "n", "n_global", "empty", "dzero", "shape", "info",
+                 "finish")
 
 
-def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_begin=None):
+def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_begin=None, defer=False):
     """Issue one pixel-term step on feats [B,128,h,w] (contiguous f32) through dcl_step_fwd.  `shard` is None or
-    (world, rank, comm).  `zero_fill`: allocate and clear the dense gradient buffer next to the step."""
+    (world, rank, comm).  `zero_fill`: allocate and clear the dense gradient buffer next to the step.
+    `after_begin`: split issue - classify and the count-table copy go first (dcl_step_begin), then the callback's
+    launches, then the rest.  `defer` (with `after_begin`): return after the callback with `res.loss` allocated and
+    `res.finish` set; the caller issues more work and then calls `res.finish()` exactly once (the rest of the step:
+    the wait for the count table, plan, select, gather, contrast), which completes `res`."""
     B, C, h, w = feats.shape
     dev = feats.device
     hw = h * w
@@ -519,6 +524,22 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_b
             raise _lib.DclError("dcl_step_begin failed with status %d: %s" % (rc0, lib.dcl_last_error().decode("utf-8", "replace")))
         after_begin()
         step.begun = 1
+    res.loss = loss.reshape(())
+    res.finish = None
+
+    def finish():
+        _finish_step(crit, res, sb, step, lib, st, loss, ev, want_grad, world, rank, dev, (p_pix, p_dF, p_rowof), _t)
+        return res
+
+    if defer and after_begin is not None:
+        res.finish = finish
+        return res
+    return finish()
+
+
+def _finish_step(crit, res, sb, step, lib, st, loss, ev, want_grad, world, rank, dev, ptrs, _t):
+    """Second half of _run_step: dcl_step_fwd and what it leaves behind."""
+    p_pix, p_dF, p_rowof = ptrs
     try:
         rc = lib.dcl_step_fwd(ctypes.byref(step), _stream())
     finally:
@@ -543,7 +564,7 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_b
     if res.empty:                                          # no class qualifies: zero loss, zero gradient
         _count(2)
         crit.last_plan = None
-        res.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        loss.zero_()                                       # res.loss is a view of it (it may already have been handed out)
         res.n = res.n_pad = res.n_global = 0
         return res
     torch.set_rng_state(st)
@@ -554,7 +575,6 @@ def _run_step(crit, feats, labels, predict, shard, want_grad, zero_fill, after_b
     A, n_view, n, n_pad, n_global, on_device = res.info[:6]
     res.n, res.n_pad, res.n_global = n, n_pad, n_global
     res.p_pix, res.p_dF, res.p_rowof = p_pix, p_dF, p_rowof
-    res.loss = loss.reshape(())
     # last_plan / last_layout / last_pix are built on first access (device buffers of this step: valid until the
     # next forward of this module)
     crit.__dict__["_last_step"] = (res.info, sb, res.keep, rank, world)
@@ -675,8 +695,13 @@ class _DoublyFn(torch.autograd.Function):
         # Order on the stream: classify + count-table copy of the pixel step, THEN the pool (HBM-bound, 0.3 ms at the
         # cfg3 shapes), then the rest of the step - the host waits for the count table and plans while the pool runs,
         # instead of the GPU idling through that round trip after a pool that was issued first.
+        # ... and the rest of the step is DEFERRED (res.finish, called by DoublyContrastiveLoss.forward after it has issued
+        # the image-level head on `pooled`): the head's launches and their host time then also fall under the pool.
         if _POOL_AFTER_CLASSIFY:
-            res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False, after_begin=pool)
+            res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False, after_begin=pool,
+                            defer=True)
+            crit.__dict__["_pending_finish"] = res.finish
+            res.finish = None                    # no cycle output -> grad_fn -> ctx -> res -> closure -> output
         else:
             pool()
             res = _run_step(crit, feats2[:B], labels, predict, None, ctx.needs_input_grad[0], False)
@@ -1253,7 +1278,12 @@ class DoublyContrastiveLoss(nn.Module):
                     self.pixel(fine_feat[:B], labels=labels, predict=predict))
         with torch.cuda.device(x.device):
             pooled, pixel_loss = _DoublyFn.apply(x, labels_c, predict_c, self.pixel)
-            supcon_loss = self.supcon.forward_pooled(pooled, class_labels, mask)
+            try:
+                supcon_loss = self.supcon.forward_pooled(pooled, class_labels, mask)
+            finally:
+                finish = self.pixel.__dict__.pop("_pending_finish", None)
+                if finish is not None:
+                    finish()                     # the rest of the pixel step (its value lands in pixel_loss's storage)
         return supcon_loss, pixel_loss
 
 
