@@ -2,7 +2,8 @@
 (`/root/reference/network/weathernet.py` on the resnet18 pyramid trunk), build container only:
     python tests/golden/make_golden_net.py
 Writes tests/golden/swiftnet_rn18.npz (outputs of an eval forward, of a train-mode forward / backward, the updated
-batch-norm statistics) and swiftnet_rn18_keys.json (state_dict key -> shape, optimiser group sizes).  The reference
+batch-norm statistics), swiftnet_rn18_keys.json and swiftnet_rn34_keys.json (state_dict key -> shape, optimiser
+group shapes).  The reference
 package needs matplotlib (stubbed) and downloads ImageNet weights (stubbed to an empty dict: strict=False makes that a
 no-op); weights come from swiftnet.fill_deterministic, applied identically on both sides."""
 import contextlib
@@ -38,6 +39,14 @@ def main():
     groups = {"random_init": [list(p.shape) for p in net.random_init_params()],
               "fine_tune": [list(p.shape) for p in net.fine_tune_params()]}
     json.dump({"state_dict": keys, "groups": groups}, open(os.path.join(HERE, "swiftnet_rn18_keys.json"), "w"), indent=0)
+    # the ResNet-34 trunk (WeatherNet's default backbone): names, shapes and optimiser groups only
+    with contextlib.redirect_stdout(io.StringIO()):
+        net34 = WeatherNet(types.SimpleNamespace(deeplab=False), backbone="resnet34")
+    json.dump({"state_dict": {k: list(v.shape) for k, v in net34.state_dict().items()},
+               "groups": {"random_init": [list(p.shape) for p in net34.random_init_params()],
+                          "fine_tune": [list(p.shape) for p in net34.fine_tune_params()]}},
+              open(os.path.join(HERE, "swiftnet_rn34_keys.json"), "w"), indent=0)
+    del net34
     g = torch.Generator().manual_seed(9)
     img = torch.rand(2, 3, 64, 128, generator=g) * 255.0                   # two views of one image
     out = {"image": img.numpy()}

@@ -41,6 +41,16 @@ def test_state_dict_and_groups_are_the_reference_s(gold):
         WeatherNet(None, backbone="efficientnetb0")
 
 
+def test_resnet34_trunk_has_the_reference_s_names_and_groups():
+    keys = json.load(open(os.path.join(GOLD, "swiftnet_rn34_keys.json")))
+    net = WeatherNet(None, backbone="resnet34")
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(keys["state_dict"].keys())
+    assert all(list(sd[k].shape) == v for k, v in keys["state_dict"].items())
+    assert [list(p.shape) for p in net.random_init_params()] == keys["groups"]["random_init"]
+    assert [list(p.shape) for p in net.fine_tune_params()] == keys["groups"]["fine_tune"]
+
+
 def test_forward_matches_the_reference_network(gold):
     g, _ = gold
     net = WeatherNet(None, backbone="resnet18")
