@@ -118,3 +118,17 @@ def test_optimizer_groups_schedule_and_checkpoint(tmp_path):
         assert torch.equal(a, b), k
     with pytest.raises(NotImplementedError):
         TrainStep(types.SimpleNamespace(criterion="crossentropy"), device="cpu")
+
+
+def test_train_step_has_no_cpu_fallback():
+    """The step's losses are CUDA kernels: on a machine without a GPU the step fails loudly instead of computing them
+    some other way (the network itself is plain torch and runs anywhere)."""
+    from doubly_contrastive_semseg_b200 import _lib
+    st = TrainStep(types.SimpleNamespace(amp=False, batch_size=1), device="cpu")
+    g = torch.Generator().manual_seed(2)
+    sample = {"left": torch.rand(2, 3, 64, 128, generator=g) * 255.0, "label": torch.randint(0, 19, (1, 64, 128), generator=g),
+              "weather": torch.zeros(1, dtype=torch.long), "label_distance_weight": torch.rand(1, 64, 128, generator=g)}
+    with pytest.raises(_lib.DclError):
+        st(sample)
+    with pytest.raises(ValueError):                                   # 'supcon' criteria need both crops
+        st({**sample, "left": sample["left"][:1]})
